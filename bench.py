@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for linfa_linalg_b200.
+
+Step = one pass of the hot path over one synthetic input.  Headline workload (BASELINE.json
+configs[1]): lower Cholesky of a 16384 x 16384 synthetic SPD f64 matrix on one B200, reported in
+GFLOP/s (algorithmic n^3/3).  Cholesky of ONE matrix does not shard ("replicas only"):
+with --gpus N every rank factors its own replica and `value` is the aggregate (weak scaling).
+The sharded paths of the north star -- batched 32x32 f32 QR (batch-sharded, no collective) and
+TSQR (row-sharded, one NCCL all-gather of the R factors) -- and the 16384^2 f64 QR are timed in the
+same run and reported under "extras".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 16384] [--no-extras]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "QR/Cholesky f64 GFLOP/s vs FP64 peak @1/2/4/8 B200; batched QR matrices/s"
+FP64_NOMINAL_TFLOPS = 37.0  # B200 FP64 (vector = tensor), nominal; MEASURED_PEAKS.json has no FP64 entry
+
+
+def env_int(k, d):
+    try:
+        return int(os.environ.get(k, d))
+    except ValueError:
+        return d
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm for the same metric/config, timed on the
+    box's host cores.  The Rust crate cannot be built in this image (no rustc/cargo), so this runs
+    the oracle port of src/cholesky.rs:51-83 -- single-threaded, like the reference."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    import numpy as np
+    import oracle as O
+    n = args.ref_n
+    g = np.random.default_rng(0x1F2E3D4C + 1).uniform(-1, 1, (n, n))
+    s0 = (g + g.T) / 2 + n * np.eye(n)
+    for _ in range(min(args.warmup, 1)):
+        s = s0.copy(); O.cholesky(s)
+    t = 0.0
+    for _ in range(args.steps):
+        s = s0.copy()
+        t0 = time.perf_counter(); st, _ = O.cholesky(s); t += time.perf_counter() - t0
+        assert st == 0
+    flops = n ** 3 / 3.0
+    val = flops * args.steps / t / 1e9
+    sample = f"Cholesky f64 n={n} per step (same algorithm as the n={args.n} workload; time scales as n^3)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Cholesky {args.n}x{args.n} SPD f64 (configs[1])", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--ref-n", type=int, default=2048)
+    ap.add_argument("--cpu-n", type=int, default=3072)
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import linfa_linalg_b200 as L
+    eng = L.Engine(local_rank)
+    lib = eng.lib
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    n = args.n
+    seed = 0x1F2E3D4C + 1 + rank
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    # S = (G + G^T)/2 + n I  (strictly diagonally dominant => SPD), built on the device
+    S = torch.rand((n, n), dtype=torch.float64, device=dev, generator=gen).mul_(2).sub_(1)
+    S = S.add_(S.t().clone()).mul_(0.5)
+    S.diagonal().add_(float(n))
+    work = torch.empty_like(S)
+    info = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def chol_step():
+        work.copy_(S)  # restore the input (in-place factorisation); 2 n^2 * 8 B of copy traffic, < 1 % of a step
+        st = lib.lfb_cholesky_dev_f64(eng.h, C.c_void_p(work.data_ptr()), n, n, 0, C.c_void_p(info.data_ptr()))
+        if st != 0:
+            raise RuntimeError(f"lfb_cholesky_dev_f64 status {st}: {lib.lfb_last_error(eng.h)}")
+
+    sampler = ClockSampler(local_rank)
+    # warm-up first so that the clock samples cover the timed region only
+    for _ in range(args.warmup):
+        chol_step()
+    barrier()
+    launches0 = eng.launch_count
+    sampler.start()
+    ms = timed(chol_step, args.steps, 0)
+    clocks = sampler.stop()
+    launches = eng.launch_count - launches0  # kernels of liblinfa_b200 launched inside the timed region
+    assert int(info.item()) == 0
+    flops = n ** 3 / 3.0
+    value = world * flops * args.steps / (ms * 1e-3) / 1e9
+
+    # residual check of the last factor (size-independent property): ||S - L L^T||_F / ||S||_F on a block
+    # (torch views the column-major buffer transposed: the lower factor L appears as triu(work) = L^T)
+    Lf = torch.triu(work[:2048, :2048]).t()
+    resid = float((Lf @ Lf.t() - S[:2048, :2048]).norm() / S[:2048, :2048].norm())
+
+    # ---- roofline of the dominant kernel (FP64 GEMM launches), measured live with CUDA events ----
+    peak_dmma = C.c_double(0.0); peak_dfma = C.c_double(0.0)
+    lib.lfb_microbench_fp64(eng.h, 1, C.byref(peak_dmma))
+    lib.lfb_microbench_fp64(eng.h, 0, C.byref(peak_dfma))
+    lib.lfb_profile_begin(eng.h)
+    chol_step()
+    g_ms, g_fl, g_calls = C.c_double(0), C.c_double(0), C.c_int64(0)
+    lib.lfb_profile_end(eng.h, C.byref(g_ms), C.byref(g_fl), C.byref(g_calls))
+    peak_tf = max(peak_dmma.value, peak_dfma.value) / 1e3
+    achieved_tf = g_fl.value / (g_ms.value * 1e-3) / 1e12 if g_ms.value > 0 else 0.0
+    roofline = {
+        "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": None,
+        "kernel": "dgemm (FP64 DMMA.8x8x4) launches of one Cholesky step",
+        "launches": int(g_calls.value), "kernel_ms_per_step": g_ms.value, "kernel_share_of_step": g_ms.value / (ms / args.steps),
+        "peak_source": ("measured in this run by lfb_microbench_fp64 (register-resident DMMA / DFMA chains); "
+                        "MEASURED_PEAKS.json has no FP64 entry"),
+        "peak_dmma_tflops": peak_dmma.value / 1e3, "peak_dfma_tflops": peak_dfma.value / 1e3,
+        "nominal_fp64_tflops": FP64_NOMINAL_TFLOPS,
+        "step_tflops": flops / (ms / args.steps * 1e-3) / 1e12,
+        "step_frac_of_measured_peak": flops / (ms / args.steps * 1e-3) / 1e12 / peak_tf if peak_tf > 0 else None,
+        "step_frac_of_nominal_peak": flops / (ms / args.steps * 1e-3) / 1e12 / FP64_NOMINAL_TFLOPS,
+    }
+
+    # ---- end to end through the public host API (pinned host buffers, H2D + D2H inside) ----
+    e2e = None
+    if not args.no_e2e:
+        host_src = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
+        host_src.copy_(S)
+        host_work = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
+        torch.cuda.synchronize()
+        eng.set_stream(None)
+        ksteps = max(1, min(args.steps, 3))
+        t_e2e = 0.0
+        fail = C.c_int64(-1)
+        for it in range(ksteps + 1):
+            host_work.copy_(host_src)
+            barrier()
+            t0 = time.perf_counter()
+            st = lib.lfb_cholesky_f64(eng.h, C.c_void_p(host_work.data_ptr()), n, n, n, 1, 0, C.byref(fail))
+            dt = time.perf_counter() - t0
+            if st != 0:
+                raise RuntimeError(f"lfb_cholesky_f64 status {st}")
+            if it > 0:
+                t_e2e += dt
+        t_e2e_ms = max_over_ranks(t_e2e * 1e3)
+        e2e = {"value": world * flops * ksteps / (t_e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
+               "h2d_bytes_per_step": n * n * 8, "d2h_bytes_per_step": n * n * 8 + 8, "steps": ksteps,
+               "ms_per_step": t_e2e_ms / ksteps, "api": "lfb_cholesky_f64 (host view, pinned, in place)"}
+        eng.set_stream(stream.cuda_stream)
+        del host_src, host_work
+
+    del S, work
+    torch.cuda.empty_cache()
+
+    extras = {}
+    if not args.no_extras:
+        extras = run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle as O
+        cn = args.cpu_n
+        g = np.random.default_rng(1).uniform(-1, 1, (cn, cn))
+        s0 = (g + g.T) / 2 + cn * np.eye(cn)
+        t0 = time.perf_counter(); st, _ = O.cholesky(s0); dt = time.perf_counter() - t0
+        cpu_baseline = {"value": cn ** 3 / 3.0 / dt / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": "port",
+                        "sample": f"oracle restatement of src/cholesky.rs:51-83 on one n={cn} SPD matrix ({dt:.1f} s; the "
+                                  f"n={n} workload extrapolates as n^3 to {dt * (n / cn) ** 3 / 60:.1f} min); reference is single-threaded"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Cholesky {n}x{n} SPD f64, lower, in place (BASELINE configs[1])",
+                       "parallelism": "replicas only (one matrix per GPU; the path does not shard)" if world > 1 else "single GPU",
+                       "l2": f"input {n * n * 8 / 2**20:.0f} MiB > 126 MiB L2 (inputs larger than L2; restored by a device copy each step)",
+                       "residual_block": resid},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "extras": extras,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
+    """C2' (QR 16384^2 f64, replicas), C3 (batched QR, batch-sharded), C4 (TSQR, row-sharded)."""
+    import torch
+    import torch.distributed as dist
+    out = {}
+    # ---- C2': blocked Householder QR, n = 16384 f64 ----
+    try:
+        n = args.n
+        gen = torch.Generator(device=dev).manual_seed(0x1F2E3D4C + 2 + rank)
+        A0 = torch.rand((n, n), dtype=torch.float64, device=dev, generator=gen).mul_(2).sub_(1)
+        A = torch.empty_like(A0)
+        diag = torch.empty(n, dtype=torch.float64, device=dev)
+
+        def qr_step():
+            A.copy_(A0)
+            st = lib.lfb_qr_dev_f64(eng.h, C.c_void_p(A.data_ptr()), n, n, n, C.c_void_p(diag.data_ptr()))
+            if st != 0:
+                raise RuntimeError(f"lfb_qr_dev_f64 status {st}")
+        ms = timed(qr_step, 2, 1)
+        fl = 4.0 / 3.0 * n ** 3
+        out["qr_f64"] = {"workload": f"QR {n}x{n} f64 (C2')", "gflops": world * fl * 2 / (ms * 1e-3) / 1e9, "ms_per_step": ms / 2,
+                         "frac_of_nominal_fp64": fl * 2 / (ms * 1e-3) / 1e12 / FP64_NOMINAL_TFLOPS}
+        del A0, A
+        torch.cuda.empty_cache()
+    except Exception as ex:  # keep the headline line alive
+        out["qr_f64"] = {"error": str(ex)[:200]}
+    # ---- C3: batched 32x32 f32 QR, batch-sharded (strong scaling) ----
+    try:
+        B = 262144
+        per = B // world
+        gen = torch.Generator(device=dev).manual_seed(0x1F2E3D4C + 3 + rank)
+        M0 = torch.rand((per, 32, 32), dtype=torch.float32, device=dev, generator=gen).mul_(2).sub_(1)
+        M = torch.empty_like(M0)
+        d = torch.empty((per, 32), dtype=torch.float32, device=dev)
+
+        def bq_step():
+            M.copy_(M0)
+            st = lib.lfb_qr_batched_dev_f32(eng.h, C.c_void_p(M.data_ptr()), per, 32, 32, C.c_void_p(d.data_ptr()))
+            if st != 0:
+                raise RuntimeError(f"lfb_qr_batched_dev_f32 status {st}")
+
+        def copy_only():
+            M.copy_(M0)
+        ms_all = timed(bq_step, 20, 5)
+        ms_copy = timed(copy_only, 20, 5)
+        ms_k = max(ms_all - ms_copy, 1e-6)
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        gbs = per * 8320 * 20 / (ms_k * 1e-3) / 1e9
+        out["batched_qr_f32"] = {"workload": f"{B} x (32x32) f32, {per} per GPU (C3)", "matrices_per_s": B * 20 / (ms_k * 1e-3),
+                                 "ms_per_step": ms_k / 20, "kernel_GBps_per_gpu": gbs, "hbm_peak_GBps": hbm,
+                                 "frac_of_hbm": gbs / hbm, "scaling": "strong", "note": "restore copy timed separately and subtracted"}
+        del M0, M
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["batched_qr_f32"] = {"error": str(ex)[:200]}
+    # ---- C4: TSQR, rows sharded across ranks, R factors all-gathered over NCCL ----
+    try:
+        rows_total, cols = 4194304, 256
+        rows = rows_total // world
+        gen = torch.Generator(device=dev).manual_seed(0x1F2E3D4C + 4 + rank)
+        # column-major rows x cols block == row-major (cols, rows) tensor
+        T0 = torch.rand((cols, rows), dtype=torch.float64, device=dev, generator=gen).mul_(2).sub_(1)
+        Tw = torch.empty_like(T0)
+        R = torch.zeros((cols, cols), dtype=torch.float64, device=dev)
+        Rall = torch.zeros((world * cols, cols), dtype=torch.float64, device=dev) if world > 1 else None
+        stack = torch.zeros((cols, world * cols), dtype=torch.float64, device=dev) if world > 1 else None
+        diag = torch.zeros(cols, dtype=torch.float64, device=dev)
+
+        def tsqr_step():
+            Tw.copy_(T0)
+            st = lib.lfb_tsqr_local_r_dev_f64(eng.h, C.c_void_p(Tw.data_ptr()), rows, cols, rows, C.c_void_p(R.data_ptr()), cols)
+            if st != 0:
+                raise RuntimeError(f"lfb_tsqr_local_r_dev_f64 status {st}")
+            if world > 1:
+                # R is column-major (cols x cols) == row-major R^T; gather R^T blocks, stack rows of R
+                dist.all_gather_into_tensor(Rall, R)
+                # Rall[g] = R_g^T (row-major).  Column-major stacked matrix [R_0; R_1; ...] (world*cols x cols)
+                # is the row-major tensor of shape (cols, world*cols) whose [:, g*cols:(g+1)*cols] = R_g^T.
+                stack.copy_(Rall.view(world, cols, cols).permute(1, 0, 2).reshape(cols, world * cols))
+                st = lib.lfb_qr_dev_f64(eng.h, C.c_void_p(stack.data_ptr()), world * cols, cols, world * cols, C.c_void_p(diag.data_ptr()))
+                if st != 0:
+                    raise RuntimeError(f"lfb_qr_dev_f64 (stacked R) status {st}")
+        ms = timed(tsqr_step, 2, 1)
+        fl = 2.0 * rows_total * cols * cols - 2.0 / 3.0 * cols ** 3
+        out["tsqr_f64"] = {"workload": f"TSQR {rows_total}x{cols} f64, {rows} rows per GPU (C4)", "gflops": fl * 2 / (ms * 1e-3) / 1e9,
+                           "ms_per_step": ms / 2, "scaling": "strong", "exchange": "NCCL all_gather of 256x256 R per rank" if world > 1 else "none"}
+    except Exception as ex:
+        out["tsqr_f64"] = {"error": str(ex)[:200]}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,167 @@
+/*
+ * linfa_b200.h -- C ABI of liblinfa_b200.so, the B200 (sm_100a) dense-factorisation engine behind
+ * linfa-linalg's Householder / Cholesky / triangular hot path.
+ *
+ * The reference (rust-ml/linfa-linalg v0.2.1) has no FFI of its own: its "interface" is the set of
+ * blanket trait impls on ndarray ArrayBase<S, Ix2>.  Each entry point below replaces the BODY of one
+ * of those trait methods (cited per function as file:line under /root/reference) and is what the
+ * Rust shim in INTEGRATION.md binds with `extern "C"`.  One call per whole factorisation -- never
+ * per reflector -- so the blocked compact-WY structure lives behind the boundary.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  `*_f32` / `*_f64` symbol families (A: NdFloat is f32|f64).
+ *  - HOST entry points take ndarray-style strided views: (ptr, rows, cols, row_stride, col_stride),
+ *    strides in ELEMENTS and SIGNED (negative and non-unit strides are legal, tests/common.rs:12-43).
+ *    Results are written back in place into the caller's storage, exactly like the `*_into` /
+ *    `*_inplace` trait methods.  The library never keeps a host pointer after it returns.
+ *  - DEVICE entry points (`*_dev_*`) take device pointers to COLUMN-MAJOR buffers with a leading
+ *    dimension (the engine's HBM layout) and run asynchronously on the handle's stream.
+ *  - Every function returns an lfb_status.  Data-dependent failures (NotPositiveDefinite) are
+ *    status codes, shape errors mirror LinalgError (src/lib.rs:33-60), CUDA failures are >= 100.
+ *  - There is NO CPU fallback: without a CUDA device lfb_create fails with LFB_ERR_CUDA.
+ *  - Blocking: host entry points synchronise the stream before returning.  A handle may be used
+ *    from any thread, one call at a time.
+ */
+#ifndef LINFA_B200_H
+#define LINFA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lfb_handle lfb_handle;
+
+typedef enum lfb_status {
+    LFB_OK = 0,
+    LFB_NOT_POSITIVE_DEFINITE = 1, /* LinalgError::NotPositiveDefinite (cholesky.rs:69-71) */
+    LFB_NOT_THIN = 2,              /* LinalgError::NotThin            (qr.rs:34-36)        */
+    LFB_NOT_SQUARE = 3,            /* LinalgError::NotSquare          (lib.rs:64-71)       */
+    LFB_EMPTY_MATRIX = 4,          /* LinalgError::EmptyMatrix        (tridiagonal.rs:33-35, bidiagonal.rs:30-32) */
+    LFB_WRONG_ROWS = 5,            /* LinalgError::WrongRows          (triangular.rs:103-108, qr.rs:128-133) */
+    LFB_NON_INVERTIBLE = 6,        /* LinalgError::NonInvertible      (qr.rs:134-136)      */
+    LFB_INVALID_ARGUMENT = 7,
+    LFB_UNSUPPORTED = 8,
+    LFB_ERR_CUDA = 100,
+    LFB_ERR_ALLOC = 101
+} lfb_status;
+
+/* triangular.rs:10-13  enum UPLO */
+#define LFB_UPPER 0
+#define LFB_LOWER 1
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Creates a handle on CUDA device `device` (own non-blocking stream, workspace pool). */
+int lfb_create(lfb_handle **out, int device);
+int lfb_destroy(lfb_handle *h);
+/* Message of the last failure on this handle ("" if none).  Valid until the next call. */
+const char *lfb_last_error(lfb_handle *h);
+/* Run subsequent calls on a caller-owned cudaStream_t (NULL restores the handle's own stream). */
+int lfb_set_stream(lfb_handle *h, void *cuda_stream);
+int lfb_synchronize(lfb_handle *h);
+/* Version / build string, and the number of kernels this handle has launched so far. */
+const char *lfb_version(void);
+int64_t lfb_launch_count(lfb_handle *h);
+/* Tunables: "qr_nb", "qr_sub", "chol_base", "gemm_tma" (0/1), ...; returns LFB_INVALID_ARGUMENT if unknown. */
+int lfb_set_option(lfb_handle *h, const char *key, int64_t value);
+
+/* ---- QR: qr.rs:29-45 QRInto::qr_into (driver loop :38-41 over householder.rs:34-51) --------- */
+/* In place: on return a[i.., i] holds the unit-norm reflector v_i, a[i, i+1..] row i of R (sign
+ * scaled as the reference does), diag[i] the signed pivot (QRDecomp{qr,diag}, qr.rs:68-73).
+ * rows < cols -> LFB_NOT_THIN.  0x0 is legal. */
+int lfb_qr_f64(lfb_handle *h, double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double *diag);
+int lfb_qr_f32(lfb_handle *h, float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, float *diag);
+
+/* householder.rs:68-93 assemble_q (used by qr.rs:86-88 generate_q, tridiagonal.rs:90-92,
+ * bidiagonal.rs:90-109).  m is the compact factor (rows x cols, read only), signs[i] = diag_fn(i)
+ * (min(rows,cols) - shift entries are read), q is rows x min(rows,cols) written with (q_rs,q_cs). */
+int lfb_assemble_q_f64(lfb_handle *h, const double *m, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                       int64_t shift, const double *signs, double *q, int64_t q_rs, int64_t q_cs);
+int lfb_assemble_q_f32(lfb_handle *h, const float *m, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                       int64_t shift, const float *signs, float *q, int64_t q_rs, int64_t q_cs);
+
+/* qr.rs:110-120 QRDecomp::qt_mul: b <- Q^T b in place, b is rows x bcols. */
+int lfb_qt_mul_f64(lfb_handle *h, const double *qr, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                   const double *diag, double *b, int64_t bcols, int64_t b_rs, int64_t b_cs);
+int lfb_qt_mul_f32(lfb_handle *h, const float *qr, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                   const float *diag, float *b, int64_t bcols, int64_t b_rs, int64_t b_cs);
+
+/* ---- Cholesky: cholesky.rs:51-83 cholesky_inplace_dirty / cholesky_inplace ------------------- */
+/* Reads only the lower triangle.  clean != 0 zeroes the strict upper triangle (:78-82), clean == 0
+ * leaves it untouched.  On LFB_NOT_POSITIVE_DEFINITE *fail_index (may be NULL) is the first row j
+ * whose pivot is <= 0 (:69-71); the matrix is then partially overwritten, as in the reference. */
+int lfb_cholesky_f64(lfb_handle *h, double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                     int clean, int64_t *fail_index);
+int lfb_cholesky_f32(lfb_handle *h, float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                     int clean, int64_t *fail_index);
+
+/* ---- triangular.rs:95-144 solve_triangular_system ------------------------------------------- */
+/* Solves a x = b in place on b (n x bcols); reads only the `uplo` triangle of a.  ext_diag == NULL
+ * takes the diagonal from a (SolveTriangularInplace, :161-168); otherwise diag_fn(i) = ext_diag[i]
+ * (qr.rs:149,176 pass |diag|).  A zero diagonal yields inf/NaN, never an error (:274-276). */
+int lfb_solve_triangular_f64(lfb_handle *h, const double *a, int64_t a_rows, int64_t a_cols, int64_t a_rs, int64_t a_cs,
+                             double *b, int64_t b_rows, int64_t b_cols, int64_t b_rs, int64_t b_cs,
+                             int uplo, const double *ext_diag);
+int lfb_solve_triangular_f32(lfb_handle *h, const float *a, int64_t a_rows, int64_t a_cols, int64_t a_rs, int64_t a_cs,
+                             float *b, int64_t b_rows, int64_t b_cols, int64_t b_rs, int64_t b_cs,
+                             int uplo, const float *ext_diag);
+
+/* triangular.rs:37-53 triangular_inplace (zero the other strict triangle). */
+int lfb_triangular_inplace_f64(lfb_handle *h, double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int uplo);
+int lfb_triangular_inplace_f32(lfb_handle *h, float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int uplo);
+
+/* ---- tridiagonal.rs:31-66 sym_tridiagonal ---------------------------------------------------- */
+/* In place: diag(a) becomes the tridiagonal's diagonal, a[i+1.., i] the reflectors; off (n-1) gets
+ * the SIGNED off-diagonal (TridiagonalDecomp, :71-77).  n == 0 -> LFB_EMPTY_MATRIX. */
+int lfb_sym_tridiagonal_f64(lfb_handle *h, double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double *off);
+int lfb_sym_tridiagonal_f32(lfb_handle *h, float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, float *off);
+
+/* ---- bidiagonal.rs:27-59 bidiagonal ---------------------------------------------------------- */
+/* In place: signed diagonal d (min(r,c)) and off-diagonal e (min(r,c)-1); reflectors stay in a
+ * (BidiagonalDecomp, :64-69).  Empty -> LFB_EMPTY_MATRIX. */
+int lfb_bidiagonal_f64(lfb_handle *h, double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double *d, double *e);
+int lfb_bidiagonal_f32(lfb_handle *h, float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, float *d, float *e);
+
+/* ---- batched thin QR of `batch` packed row-major m x n matrices (qr.rs:32-44 per matrix) ------ */
+/* a: [batch][m][n] contiguous, diag: [batch][n].  Batch-sharded across GPUs by the caller. */
+int lfb_qr_batched_f32(lfb_handle *h, float *a, int64_t batch, int64_t m, int64_t n, float *diag);
+int lfb_qr_batched_f64(lfb_handle *h, double *a, int64_t batch, int64_t m, int64_t n, double *diag);
+
+/* ---- device-resident entry points (column-major, leading dimension, async on the stream) ----- */
+int lfb_qr_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_diag);
+int lfb_qr_dev_f32(lfb_handle *h, float *d_a, int64_t rows, int64_t cols, int64_t ld, float *d_diag);
+/* lower Cholesky of a column-major matrix (== upper^T of the row-major view); d_info[0] = 0 or fail row + 1 */
+int lfb_cholesky_dev_f64(lfb_handle *h, double *d_a, int64_t n, int64_t ld, int clean, int64_t *d_info);
+int lfb_cholesky_dev_f32(lfb_handle *h, float *d_a, int64_t n, int64_t ld, int clean, int64_t *d_info);
+/* q (rows x min(rows,cols), column-major ldq) from a compact factor, as lfb_assemble_q */
+int lfb_assemble_q_dev_f64(lfb_handle *h, const double *d_m, int64_t rows, int64_t cols, int64_t ld,
+                           int64_t shift, const double *d_signs, double *d_q, int64_t ldq);
+int lfb_sym_tridiagonal_dev_f64(lfb_handle *h, double *d_a, int64_t n, int64_t ld, double *d_off);
+int lfb_bidiagonal_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_d, double *d_e);
+/* batched: d_a is [batch][m][n] row-major packed (the ndarray layout), in place */
+int lfb_qr_batched_dev_f32(lfb_handle *h, float *d_a, int64_t batch, int64_t m, int64_t n, float *d_diag);
+/* Tall-skinny local stage of TSQR: R (cols x cols, column-major ldr, diag >= 0, strict lower zeroed)
+ * of a rows x cols column-major block.  d_a is overwritten (compact local factor). */
+int lfb_tsqr_local_r_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_r, int64_t ldr);
+/* General column-major GEMM on the engine's own kernels (used by tests / yard-stick benches):
+ * C = alpha op(A) op(B) + beta C,  ta/tb: 0 = N, 1 = T. */
+int lfb_gemm_dev_f64(lfb_handle *h, int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha,
+                     const double *d_a, int64_t lda, const double *d_b, int64_t ldb, double beta, double *d_c, int64_t ldc);
+int lfb_gemm_dev_f32(lfb_handle *h, int ta, int tb, int64_t m, int64_t n, int64_t k, float alpha,
+                     const float *d_a, int64_t lda, const float *d_b, int64_t ldb, float beta, float *d_c, int64_t ldc);
+
+/* ---- GEMM profiler for the roofline line of bench.py: CUDA events around every FP64 GEMM launch
+ * between begin and end; end synchronises and returns summed device time, algorithmic flops, calls. */
+int lfb_profile_begin(lfb_handle *h);
+int lfb_profile_end(lfb_handle *h, double *gemm_ms, double *gemm_flops, int64_t *gemm_calls);
+
+/* ---- micro-benchmarks used by bench.py to measure the FP64 pipe ceiling in the same run ------- */
+/* kind: 0 = DFMA register chain, 1 = DMMA.8x8x4 (mma.sync f64).  Returns achieved GFLOP/s. */
+int lfb_microbench_fp64(lfb_handle *h, int kind, double *gflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LINFA_B200_H */

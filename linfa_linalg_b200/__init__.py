@@ -1,0 +1,466 @@
+"""linfa_linalg_b200 -- host-side mirror of linfa-linalg's public traits over liblinfa_b200.so.
+
+Names, argument meaning and error behaviour follow the reference (rust-ml/linfa-linalg v0.2.1):
+`qr`/`qr_into` + `QRDecomp` (src/qr.rs), `cholesky*`/`solvec*`/`invc*` (src/cholesky.rs),
+`solve_triangular*`/`into_triangular`/`is_triangular` (src/triangular.rs), `sym_tridiagonal` +
+`TridiagonalDecomp` (src/tridiagonal.rs), `bidiagonal` + `BidiagonalDecomp` (src/bidiagonal.rs).
+numpy arrays of any strides stand in for ndarray views; the `*_into` / `*_inplace` variants work in
+place on the caller's storage.  All arithmetic runs on the GPU through the C ABI; nothing here
+falls back to the CPU (importing works without a GPU, the first call does not).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import LOWER, UPPER  # noqa: F401  (triangular.rs:10-13 UPLO)
+
+__all__ = [
+    "LinalgError", "NotSquare", "NotThin", "NotPositiveDefinite", "NonInvertible", "EmptyMatrix", "WrongRows",
+    "Engine", "engine", "UPPER", "LOWER",
+    "qr", "qr_into", "QRDecomp", "least_squares", "least_squares_into", "qr_batched",
+    "cholesky", "cholesky_dirty", "cholesky_into", "cholesky_into_dirty", "cholesky_inplace", "cholesky_inplace_dirty",
+    "solvec", "solvec_into", "solvec_inplace", "invc", "invc_inplace",
+    "solve_triangular", "solve_triangular_into", "solve_triangular_inplace", "triangular_inplace", "into_triangular",
+    "is_triangular", "sym_tridiagonal", "TridiagonalDecomp", "bidiagonal", "BidiagonalDecomp",
+]
+
+
+# ---- errors: src/lib.rs:33-60 ----------------------------------------------------------------
+class LinalgError(Exception):
+    pass
+
+
+class NotSquare(LinalgError):
+    def __init__(self, rows, cols):
+        super().__init__(f"Matrix of ({rows}, {cols}) is not square")
+        self.rows, self.cols = rows, cols
+
+
+class NotThin(LinalgError):
+    def __init__(self, rows, cols):
+        super().__init__(f"Expected matrix rows({rows}) >= cols({cols})")
+        self.rows, self.cols = rows, cols
+
+
+class NotPositiveDefinite(LinalgError):
+    def __init__(self, index=None):
+        super().__init__("Matrix is not positive definite")
+        self.index = index
+
+
+class NonInvertible(LinalgError):
+    def __init__(self):
+        super().__init__("Matrix is non-invertible")
+
+
+class EmptyMatrix(LinalgError):
+    def __init__(self):
+        super().__init__("Matrix is empty")
+
+
+class WrongRows(LinalgError):
+    def __init__(self, expected, actual):
+        super().__init__(f"Matrix must have {expected} rows, not {actual}")
+        self.expected, self.actual = expected, actual
+
+
+class DeviceError(LinalgError):
+    """CUDA / allocation failure (a new variant; the reference enum is #[non_exhaustive])."""
+
+
+# ---- engine handle ---------------------------------------------------------------------------
+def _sfx(a: np.ndarray) -> str:
+    if a.dtype == np.float64:
+        return "_f64"
+    if a.dtype == np.float32:
+        return "_f32"
+    raise TypeError(f"A: NdFloat means f32 or f64, got {a.dtype}")
+
+
+def _view(a: np.ndarray):
+    assert a.ndim == 2
+    it = a.itemsize
+    return (C.c_void_p(a.ctypes.data), a.shape[0], a.shape[1], a.strides[0] // it, a.strides[1] // it)
+
+
+def _vecp(v: np.ndarray):
+    return C.c_void_p(v.ctypes.data)
+
+
+class Engine:
+    """Owns one lfb_handle (one CUDA device, one stream, one workspace pool)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _ffi.load()
+        hp = C.c_void_p()
+        st = self.lib.lfb_create(C.byref(hp), device)
+        if st != _ffi.OK:
+            raise DeviceError(f"lfb_create(device={device}) failed with status {st}: no usable CUDA device "
+                              "(linfa_linalg_b200 has no CPU fallback)")
+        self.h = hp
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lfb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        if self.lib.lfb_set_option(self.h, key.encode(), int(value)) != _ffi.OK:
+            raise ValueError(f"unknown option {key}")
+
+    def set_stream(self, cuda_stream: int | None):
+        self.lib.lfb_set_stream(self.h, C.c_void_p(cuda_stream or 0))
+
+    def synchronize(self):
+        self._check(self.lib.lfb_synchronize(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.lfb_launch_count(self.h))
+
+    def _check(self, st: int):
+        if st == _ffi.OK:
+            return
+        msg = (self.lib.lfb_last_error(self.h) or b"").decode()
+        raise DeviceError(f"liblinfa_b200 status {st}: {msg}")
+
+    def call(self, name: str, *args) -> int:
+        return getattr(self.lib, name)(self.h, *args)
+
+
+_default: Engine | None = None
+
+
+def engine() -> Engine:
+    global _default
+    if _default is None:
+        _default = Engine(0)
+    return _default
+
+
+def _owned(a) -> np.ndarray:
+    """`to_owned()`: a fresh row-major copy (qr.rs:61, cholesky.rs:107)."""
+    a = np.asarray(a)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    return np.array(a, order="C", copy=True)
+
+
+def _check_square(a):  # lib.rs:64-71
+    if a.shape[0] != a.shape[1]:
+        raise NotSquare(a.shape[0], a.shape[1])
+    return a.shape[0]
+
+
+# ---- QR: src/qr.rs ---------------------------------------------------------------------------
+class QRDecomp:
+    """qr.rs:68-73: compact factor `qr` + signed `diag`."""
+
+    def __init__(self, qr_: np.ndarray, diag: np.ndarray, eng: Engine):
+        self.qr, self.diag, self._e = qr_, diag, eng
+
+    def generate_q(self) -> np.ndarray:  # qr.rs:86-88
+        return _assemble_q(self._e, self.qr, 0, self.diag)
+
+    def into_r(self) -> np.ndarray:  # qr.rs:91-98 (host-side slicing, as in the reference)
+        n = self.qr.shape[1]
+        r = self.qr[:n, :n]
+        triangular_inplace(r, UPPER, eng=self._e) if n > 64 else _host_triangular(r, UPPER)
+        r[np.arange(n), np.arange(n)] = np.abs(self.diag)
+        return r
+
+    def into_decomp(self):  # qr.rs:101-104
+        q = self.generate_q()
+        return q, self.into_r()
+
+    def qt_mul(self, b: np.ndarray) -> None:  # qr.rs:110-120 (in place)
+        st = self._e.call("lfb_qt_mul" + _sfx(self.qr), *_view(self.qr), _vecp(self.diag), *_view(b)[:1],
+                          b.shape[1], *_view(b)[3:])
+        self._e._check(st)
+
+    def is_invertible(self) -> bool:  # qr.rs:194-197
+        return bool(np.all(self.diag != 0))
+
+    def solve_into(self, b: np.ndarray) -> np.ndarray:  # qr.rs:124-152
+        if self.qr.shape[0] != b.shape[0]:
+            raise WrongRows(self.qr.shape[0], b.shape[0])
+        if not self.is_invertible():
+            raise NonInvertible()
+        self.qt_mul(b)
+        n = self.qr.shape[1]
+        x = b[:n, :]
+        _solve_tri(self._e, self.qr[:n, :n], x, UPPER, np.abs(self.diag))
+        return x
+
+    def solve_tr_into(self, b: np.ndarray) -> np.ndarray:  # qr.rs:156-181
+        n = self.qr.shape[1]
+        if n != b.shape[0]:
+            raise WrongRows(n, b.shape[0])
+        if not self.is_invertible():
+            raise NonInvertible()
+        _solve_tri(self._e, self.qr[:n, :n].T, b, LOWER, np.abs(self.diag))
+        return self.generate_q() @ b  # :180 (Q.dot(b) is ndarray GEMM in the reference too)
+
+    def solve(self, b):  # qr.rs:184-186
+        return self.solve_into(_owned(b).astype(self.qr.dtype, copy=False))
+
+    def solve_tr(self, b):  # qr.rs:189-191
+        return self.solve_tr_into(_owned(b).astype(self.qr.dtype, copy=False))
+
+    def inverse(self) -> np.ndarray:  # qr.rs:200-203
+        _check_square(self.qr)
+        return self.solve_into(np.eye(len(self.diag), dtype=self.qr.dtype))
+
+
+def qr_into(a: np.ndarray, eng: Engine | None = None) -> QRDecomp:
+    """qr.rs:29-45 QRInto::qr_into -- factors `a` in place."""
+    e = eng or engine()
+    rows, cols = a.shape
+    if rows < cols:
+        raise NotThin(rows, cols)
+    diag = np.zeros(cols, dtype=a.dtype)
+    st = e.call("lfb_qr" + _sfx(a), *_view(a), _vecp(diag))
+    e._check(st)
+    return QRDecomp(a, diag, e)
+
+
+def qr(a, eng: Engine | None = None) -> QRDecomp:
+    """qr.rs:57-63 QR::qr (by reference: copies first)."""
+    return qr_into(_owned(a), eng)
+
+
+def least_squares_into(a: np.ndarray, b: np.ndarray, eng: Engine | None = None) -> np.ndarray:
+    """qr.rs:207-229."""
+    if a.shape[0] >= a.shape[1]:
+        return np.array(qr_into(a, eng).solve_into(b))
+    return qr_into(a.T, eng).solve_tr_into(b)
+
+
+def least_squares(a: np.ndarray, b, eng: Engine | None = None) -> np.ndarray:
+    """qr.rs:233-248."""
+    return least_squares_into(a, _owned(b).astype(a.dtype, copy=False), eng)
+
+
+def _assemble_q(e: Engine, m: np.ndarray, shift: int, signs: np.ndarray) -> np.ndarray:
+    """householder.rs:68-93."""
+    rows, cols = m.shape
+    dim = min(rows, cols)
+    if shift > dim:
+        raise IndexError("shift exceeds matrix dimension (the reference panics here)")
+    q = np.zeros((rows, dim), dtype=m.dtype)
+    signs = np.ascontiguousarray(signs, dtype=m.dtype)
+    sbuf = signs if signs.size else np.zeros(1, dtype=m.dtype)
+    st = e.call("lfb_assemble_q" + _sfx(m), *_view(m), shift, _vecp(sbuf), *_view(q)[:1], *_view(q)[3:])
+    e._check(st)
+    return q
+
+
+def qr_batched(a: np.ndarray, eng: Engine | None = None) -> np.ndarray:
+    """qr.rs:32-44 over a C-contiguous [batch][m][n] array, in place; returns diag [batch][n]."""
+    e = eng or engine()
+    assert a.ndim == 3 and a.flags.c_contiguous
+    batch, m, n = a.shape
+    if m < n:
+        raise NotThin(m, n)
+    diag = np.zeros((batch, n), dtype=a.dtype)
+    st = e.call("lfb_qr_batched" + _sfx(a), C.c_void_p(a.ctypes.data), batch, m, n, _vecp(diag))
+    e._check(st)
+    return diag
+
+
+# ---- Cholesky: src/cholesky.rs -----------------------------------------------------------------
+def _chol(a: np.ndarray, clean: bool, e: Engine):
+    n = a.shape[0]
+    if a.shape[0] != a.shape[1]:
+        raise NotSquare(a.shape[0], a.shape[1])
+    fail = C.c_int64(-1)
+    st = e.call("lfb_cholesky" + _sfx(a), *_view(a), int(clean), C.byref(fail))
+    if st == _ffi.NOT_POSITIVE_DEFINITE:
+        raise NotPositiveDefinite(fail.value)
+    e._check(st)
+    return a
+
+
+def cholesky_inplace_dirty(a, eng=None):  # cholesky.rs:51-76
+    return _chol(a, False, eng or engine())
+
+
+def cholesky_inplace(a, eng=None):  # cholesky.rs:78-82
+    return _chol(a, True, eng or engine())
+
+
+cholesky_into_dirty = cholesky_inplace_dirty  # cholesky.rs:24-31
+cholesky_into = cholesky_inplace  # cholesky.rs:37-43
+
+
+def cholesky_dirty(a, eng=None):  # cholesky.rs:106-109
+    return _chol(_owned(a), False, eng or engine())
+
+
+def cholesky(a, eng=None):  # cholesky.rs:111-114
+    return _chol(_owned(a), True, eng or engine())
+
+
+def solvec_inplace(a: np.ndarray, b: np.ndarray, eng=None) -> np.ndarray:  # cholesky.rs:136-144
+    e = eng or engine()
+    chol = cholesky_inplace_dirty(a, e)
+    _solve_tri(e, chol, b, LOWER, None)
+    _solve_tri(e, chol.T, b, UPPER, None)
+    return b
+
+
+def solvec_into(a, b, eng=None):  # cholesky.rs:127-130
+    return solvec_inplace(a, b, eng)
+
+
+def solvec(a, b, eng=None):  # cholesky.rs:155-163
+    return solvec_inplace(a, _owned(b).astype(a.dtype, copy=False), eng)
+
+
+def invc_inplace(a, eng=None):  # cholesky.rs:178-182
+    return solvec_into(a, np.eye(a.shape[0], dtype=a.dtype), eng)
+
+
+def invc(a, eng=None):  # cholesky.rs:193-199
+    return invc_inplace(_owned(a), eng)
+
+
+# ---- triangular: src/triangular.rs ---------------------------------------------------------------
+def _host_triangular(a, uplo):
+    n = a.shape[0]
+    for i in range(n):
+        if uplo == UPPER:
+            a[i, :i] = 0
+        else:
+            a[i, i + 1:] = 0
+
+
+def triangular_inplace(a: np.ndarray, uplo: int, eng=None):  # triangular.rs:37-53
+    _check_square(a)
+    e = eng or engine()
+    e._check(e.call("lfb_triangular_inplace" + _sfx(a), *_view(a), uplo))
+    return a
+
+
+into_triangular = triangular_inplace  # triangular.rs:32-35
+
+
+def is_triangular(a: np.ndarray, uplo: int) -> bool:  # triangular.rs:67-90 (a host-side predicate)
+    if a.shape[0] != a.shape[1]:
+        return False
+    return bool(np.all(np.tril(a, -1) == 0)) if uplo == UPPER else bool(np.all(np.triu(a, 1) == 0))
+
+
+def _solve_tri(e: Engine, a: np.ndarray, b: np.ndarray, uplo: int, ext_diag):
+    _check_square(a)  # triangular.rs:102
+    if b.shape[0] != a.shape[0]:
+        raise WrongRows(a.shape[0], b.shape[0])  # :103-108
+    dp = None
+    if ext_diag is not None:
+        ext_diag = np.ascontiguousarray(ext_diag, dtype=a.dtype)
+        dp = _vecp(ext_diag)
+    st = e.call("lfb_solve_triangular" + _sfx(a), *_view(a), *_view(b), uplo, dp)
+    e._check(st)
+    return b
+
+
+def solve_triangular_inplace(a, b, uplo, eng=None):  # triangular.rs:161-168
+    return _solve_tri(eng or engine(), a, b, uplo, None)
+
+
+def solve_triangular_into(a, b, uplo, eng=None):  # triangular.rs:152-155
+    return _solve_tri(eng or engine(), a, b, uplo, None)
+
+
+def solve_triangular(a, b, uplo, eng=None):  # triangular.rs:184-186
+    return _solve_tri(eng or engine(), a, _owned(b).astype(a.dtype, copy=False), uplo, None)
+
+
+# ---- tridiagonal: src/tridiagonal.rs -------------------------------------------------------------
+class TridiagonalDecomp:
+    """tridiagonal.rs:71-77."""
+
+    def __init__(self, diag_matrix, off_diagonal, eng):
+        self.diag_matrix, self.off_diagonal, self._e = diag_matrix, off_diagonal, eng
+
+    def generate_q(self):  # :90-92
+        return _assemble_q(self._e, self.diag_matrix, 1, self.off_diagonal)
+
+    def into_diagonals(self):  # :96-101
+        return np.array(np.diag(self.diag_matrix)), np.abs(self.off_diagonal)
+
+    def into_tridiag_matrix(self):  # :104-113
+        m = self.diag_matrix
+        n = m.shape[0]
+        d = np.array(np.diag(m))
+        m[...] = 0
+        idx = np.arange(n)
+        m[idx, idx] = d
+        off = np.abs(self.off_diagonal)
+        m[idx[1:], idx[:-1]] = off
+        m[idx[:-1], idx[1:]] = off
+        return m
+
+
+def sym_tridiagonal(a: np.ndarray, eng=None) -> TridiagonalDecomp:
+    """tridiagonal.rs:31-66 -- consumes `a` (in place)."""
+    e = eng or engine()
+    n = _check_square(a)
+    if n < 1:
+        raise EmptyMatrix()
+    off = np.zeros(n - 1, dtype=a.dtype)
+    obuf = off if off.size else np.zeros(1, dtype=a.dtype)
+    st = e.call("lfb_sym_tridiagonal" + _sfx(a), *_view(a), _vecp(obuf))
+    e._check(st)
+    return TridiagonalDecomp(a, off, e)
+
+
+# ---- bidiagonal: src/bidiagonal.rs ---------------------------------------------------------------
+class BidiagonalDecomp:
+    """bidiagonal.rs:64-69."""
+
+    def __init__(self, uv, diagonal, off_diagonal, upper_diag, eng):
+        self.uv, self.diagonal, self.off_diagonal, self.upper_diag, self._e = uv, diagonal, off_diagonal, upper_diag, eng
+
+    def is_upper_diag(self):  # :85-87
+        return self.upper_diag
+
+    def generate_u(self):  # :90-97
+        shift = 0 if self.upper_diag else 1
+        return _assemble_q(self._e, self.uv, shift, self.diagonal if self.upper_diag else self.off_diagonal)
+
+    def generate_vt(self):  # :101-109
+        shift = 1 if self.upper_diag else 0
+        return _assemble_q(self._e, self.uv.T, shift, self.off_diagonal if self.upper_diag else self.diagonal).T
+
+    def into_diagonals(self):  # :126-131
+        return np.abs(self.diagonal), np.abs(self.off_diagonal)
+
+    def into_b(self):  # :113-123
+        d, e = self.into_diagonals()
+        return np.diag(d) + (np.diag(e, 1) if self.upper_diag else np.diag(e, -1))
+
+
+def bidiagonal(a: np.ndarray, eng=None) -> BidiagonalDecomp:
+    """bidiagonal.rs:27-59 -- consumes `a` (in place)."""
+    e = eng or engine()
+    rows, cols = a.shape
+    md = min(rows, cols)
+    if md == 0:
+        raise EmptyMatrix()
+    d = np.zeros(md, dtype=a.dtype)
+    off = np.zeros(md - 1, dtype=a.dtype)
+    obuf = off if off.size else np.zeros(1, dtype=a.dtype)
+    st = e.call("lfb_bidiagonal" + _sfx(a), *_view(a), _vecp(d), _vecp(obuf))
+    e._check(st)
+    return BidiagonalDecomp(a, d, off, rows >= cols, e)

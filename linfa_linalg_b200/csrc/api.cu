@@ -1,0 +1,458 @@
+// extern "C" entry points of liblinfa_b200.so (include/linfa_b200.h): argument checks that mirror
+// the reference's LinalgError behaviour, packing of arbitrary-stride host views into the engine's
+// column-major HBM layout, and the device-resident variants.
+#include "common.cuh"
+
+using namespace lfb;
+
+namespace {
+
+enum Layout { L_ROW, L_COL, L_GEN };
+
+Layout classify(int64_t rows, int64_t cols, int64_t rs, int64_t cs, int64_t *ld) {
+    if (cs == 1 && (rows == 1 || rs >= cols) && rs > 0) { *ld = rows == 1 ? cols : rs; return L_ROW; }
+    if (rows == 1 && cs == 1) { *ld = cols; return L_ROW; }
+    if (rs == 1 && (cols == 1 || cs >= rows) && cs > 0) { *ld = cols == 1 ? rows : cs; return L_COL; }
+    if (cols == 1 && rs == 1) { *ld = rows; return L_COL; }
+    return L_GEN;
+}
+
+// Host view -> device column-major (rows x cols, ldd).
+template <typename T>
+void upload(lfb_handle &h, const T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *d, int64_t ldd) {
+    if (rows <= 0 || cols <= 0) return;
+    int64_t ld = 0;
+    Layout lay = classify(rows, cols, rs, cs, &ld);
+    if (lay == L_COL) {
+        LFB_CUDA(cudaMemcpy2DAsync(d, ldd * sizeof(T), a, ld * sizeof(T), rows * sizeof(T), cols, cudaMemcpyHostToDevice, h.stream));
+        return;
+    }
+    const T *src = a;
+    if (lay == L_GEN) {
+        T *pk = (T *)h.pinned_buf(sizeof(T) * rows * cols);
+        for (int64_t i = 0; i < rows; ++i)
+            for (int64_t j = 0; j < cols; ++j) pk[i * cols + j] = a[i * rs + j * cs];
+        src = pk;
+        ld = cols;
+    }
+    DevBuf<T> tmp(h, (size_t)ld * rows);
+    LFB_CUDA(cudaMemcpyAsync(tmp.get(), src, sizeof(T) * ((rows - 1) * ld + cols), cudaMemcpyHostToDevice, h.stream));
+    transpose<T>(h, tmp.get(), cols, rows, ld, d, ldd);
+    if (lay == L_GEN) LFB_CUDA(cudaStreamSynchronize(h.stream));  // pinned staging buffer is reused
+}
+
+// Device column-major -> host view (in place into the caller's storage).  Synchronises.
+template <typename T>
+void download(lfb_handle &h, const T *d, int64_t ldd, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs) {
+    if (rows <= 0 || cols <= 0) return;
+    int64_t ld = 0;
+    Layout lay = classify(rows, cols, rs, cs, &ld);
+    if (lay == L_COL) {
+        LFB_CUDA(cudaMemcpy2DAsync(a, ld * sizeof(T), d, ldd * sizeof(T), rows * sizeof(T), cols, cudaMemcpyDeviceToHost, h.stream));
+        LFB_CUDA(cudaStreamSynchronize(h.stream));
+        return;
+    }
+    if (lay == L_GEN) ld = cols;
+    DevBuf<T> tmp(h, (size_t)ld * rows);
+    transpose<T>(h, d, rows, cols, ldd, tmp.get(), ld);   // tmp: cols x rows column-major == row-major rows x cols
+    if (lay == L_ROW) {
+        // copy row by row extents only (do not touch padding between rows)
+        LFB_CUDA(cudaMemcpy2DAsync(a, ld * sizeof(T), tmp.get(), ld * sizeof(T), cols * sizeof(T), rows, cudaMemcpyDeviceToHost, h.stream));
+        LFB_CUDA(cudaStreamSynchronize(h.stream));
+    } else {
+        T *pk = (T *)h.pinned_buf(sizeof(T) * rows * cols);
+        LFB_CUDA(cudaMemcpyAsync(pk, tmp.get(), sizeof(T) * rows * cols, cudaMemcpyDeviceToHost, h.stream));
+        LFB_CUDA(cudaStreamSynchronize(h.stream));
+        for (int64_t i = 0; i < rows; ++i)
+            for (int64_t j = 0; j < cols; ++j) a[i * rs + j * cs] = pk[i * cols + j];
+    }
+}
+
+template <typename T>
+void upload_vec(lfb_handle &h, const T *v, int64_t n, T *d) {
+    if (n > 0) LFB_CUDA(cudaMemcpyAsync(d, v, sizeof(T) * n, cudaMemcpyHostToDevice, h.stream));
+}
+template <typename T>
+void download_vec(lfb_handle &h, const T *d, int64_t n, T *v) {
+    if (n > 0) LFB_CUDA(cudaMemcpyAsync(v, d, sizeof(T) * n, cudaMemcpyDeviceToHost, h.stream));
+    LFB_CUDA(cudaStreamSynchronize(h.stream));
+}
+
+int fail(lfb_handle *h, int code, const char *msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define LFB_API_BEGIN(h)                                   \
+    if (!(h)) return LFB_INVALID_ARGUMENT;                 \
+    (h)->err.clear();                                      \
+    try {                                                  \
+        LFB_CUDA(cudaSetDevice((h)->device));
+#define LFB_API_END(h)                                     \
+    }                                                      \
+    catch (const lfb::CudaError &e) {                      \
+        (h)->err = e.what();                               \
+        cudaGetLastError();                                \
+        return e.code;                                     \
+    }                                                      \
+    catch (const std::exception &e) {                      \
+        (h)->err = e.what();                               \
+        return LFB_ERR_CUDA;                               \
+    }                                                      \
+    return LFB_OK;
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+int qr_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *diag) {
+    if (rows < 0 || cols < 0) return fail(h, LFB_INVALID_ARGUMENT, "negative dimension");
+    if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");           // qr.rs:34-36
+    if (cols == 0) return LFB_OK;                                                            // 0x0 legal, qr.rs:383-388
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(rows, 2);
+    DevBuf<T> dA(*h, (size_t)ld * cols), dD(*h, cols);
+    upload<T>(*h, a, rows, cols, rs, cs, dA, ld);
+    qr_factor<T>(*h, dA, rows, cols, ld, dD);
+    download<T>(*h, dA, ld, a, rows, cols, rs, cs);
+    download_vec<T>(*h, dD, cols, diag);
+    LFB_API_END(h)
+}
+
+template <typename T>
+int assemble_q_host(lfb_handle *h, const T *m, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int64_t shift,
+                    const T *signs, T *q, int64_t q_rs, int64_t q_cs) {
+    if (rows < 0 || cols < 0 || shift < 0) return fail(h, LFB_INVALID_ARGUMENT, "negative dimension");
+    const int64_t dim = std::min(rows, cols);
+    if (shift > dim) return fail(h, LFB_INVALID_ARGUMENT, "shift exceeds matrix dimension");   // householder.rs:67 (panics there)
+    if (rows == 0 || dim == 0) return LFB_OK;
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(rows, 2);
+    const int64_t nref = dim - shift;
+    DevBuf<T> dM(*h, (size_t)ld * cols), dQ(*h, (size_t)ld * dim), dS(*h, std::max<int64_t>(nref, 1));
+    upload<T>(*h, m, rows, cols, rs, cs, dM, ld);
+    upload_vec<T>(*h, signs, nref, dS);
+    assemble_q<T>(*h, dM, rows, cols, ld, shift, dS, dQ, ld);
+    download<T>(*h, dQ, ld, q, rows, dim, q_rs, q_cs);
+    LFB_API_END(h)
+}
+
+template <typename T>
+int qt_mul_host(lfb_handle *h, const T *qr, int64_t rows, int64_t cols, int64_t rs, int64_t cs, const T *diag, T *b,
+                int64_t bcols, int64_t b_rs, int64_t b_cs) {
+    if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
+    if (rows == 0 || cols == 0 || bcols == 0) return LFB_OK;
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(rows, 2);
+    DevBuf<T> dM(*h, (size_t)ld * cols), dB(*h, (size_t)ld * bcols), dD(*h, cols);
+    upload<T>(*h, qr, rows, cols, rs, cs, dM, ld);
+    upload<T>(*h, b, rows, bcols, b_rs, b_cs, dB, ld);
+    upload_vec<T>(*h, diag, cols, dD);
+    qt_mul<T>(*h, dM, rows, cols, ld, dD, dB, bcols, ld);
+    download<T>(*h, dB, ld, b, rows, bcols, b_rs, b_cs);
+    LFB_API_END(h)
+}
+
+template <typename T>
+int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int clean, int64_t *fail_index) {
+    if (rows != cols) return fail(h, LFB_NOT_SQUARE, "Matrix is not square");                 // lib.rs:64-71
+    if (fail_index) *fail_index = -1;
+    const int64_t n = rows;
+    if (n == 0) return LFB_OK;                                                               // cholesky.rs:270-272
+    int64_t info = 0;
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(n, 2);
+    DevBuf<T> dA(*h, (size_t)ld * n);
+    DevBuf<int64_t> dInfo(*h, 1);
+    upload<T>(*h, a, n, n, rs, cs, dA, ld);
+    cholesky_lower<T>(*h, dA, n, ld, clean, dInfo);
+    LFB_CUDA(cudaMemcpyAsync(&info, dInfo.get(), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    download<T>(*h, dA, ld, a, n, n, rs, cs);
+    if (info != 0) {
+        if (fail_index) *fail_index = info - 1;
+        h->err = "Matrix is not positive definite";
+        return LFB_NOT_POSITIVE_DEFINITE;
+    }
+    LFB_API_END(h)
+}
+
+template <typename T>
+int solve_triangular_host(lfb_handle *h, const T *a, int64_t a_rows, int64_t a_cols, int64_t a_rs, int64_t a_cs, T *b,
+                          int64_t b_rows, int64_t b_cols, int64_t b_rs, int64_t b_cs, int uplo, const T *ext_diag) {
+    if (a_rows != a_cols) return fail(h, LFB_NOT_SQUARE, "Matrix is not square");            // triangular.rs:102
+    if (b_rows != a_rows) return fail(h, LFB_WRONG_ROWS, "Matrix has the wrong number of rows");  // :103-108
+    if (uplo != LFB_UPPER && uplo != LFB_LOWER) return fail(h, LFB_INVALID_ARGUMENT, "bad uplo");
+    const int64_t n = a_rows;
+    if (n == 0 || b_cols == 0) return LFB_OK;
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(n, 2);
+    DevBuf<T> dA(*h, (size_t)ld * n), dB(*h, (size_t)ld * b_cols), dD(*h, n);
+    upload<T>(*h, a, n, n, a_rs, a_cs, dA, ld);
+    upload<T>(*h, b, n, b_cols, b_rs, b_cs, dB, ld);
+    if (ext_diag) upload_vec<T>(*h, ext_diag, n, dD);
+    trsm_left<T>(*h, uplo == LFB_LOWER, 0, n, b_cols, dA, ld, ext_diag ? dD.get() : (const T *)nullptr, dB, ld);
+    download<T>(*h, dB, ld, b, n, b_cols, b_rs, b_cs);
+    LFB_API_END(h)
+}
+
+template <typename T>
+int triangular_inplace_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int uplo) {
+    if (rows != cols) return fail(h, LFB_NOT_SQUARE, "Matrix is not square");
+    if (rows == 0) return LFB_OK;
+    LFB_API_BEGIN(h)
+    const int64_t n = rows, ld = round_up(n, 2);
+    DevBuf<T> dA(*h, (size_t)ld * n);
+    upload<T>(*h, a, n, n, rs, cs, dA, ld);
+    triangular_zero<T>(*h, dA, n, ld, uplo == LFB_LOWER);
+    download<T>(*h, dA, ld, a, n, n, rs, cs);
+    LFB_API_END(h)
+}
+
+template <typename T>
+int sym_tridiagonal_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *off) {
+    if (rows != cols) return fail(h, LFB_NOT_SQUARE, "Matrix is not square");                 // tridiagonal.rs:32
+    if (rows < 1) return fail(h, LFB_EMPTY_MATRIX, "Matrix is empty");                        // :33-35
+    const int64_t n = rows;
+    if (n == 1) return LFB_OK;
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(n, 2);
+    DevBuf<T> dA(*h, (size_t)ld * n), dOff(*h, n);
+    upload<T>(*h, a, n, n, rs, cs, dA, ld);
+    sym_tridiagonal<T>(*h, dA, n, ld, dOff);
+    download<T>(*h, dA, ld, a, n, n, rs, cs);
+    download_vec<T>(*h, dOff, n - 1, off);
+    LFB_API_END(h)
+}
+
+template <typename T>
+int bidiagonal_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *d, T *e) {
+    const int64_t md = std::min(rows, cols);
+    if (md <= 0) return fail(h, LFB_EMPTY_MATRIX, "Matrix is empty");                         // bidiagonal.rs:30-32
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(rows, 2);
+    DevBuf<T> dA(*h, (size_t)ld * cols), dD(*h, md), dE(*h, md);
+    upload<T>(*h, a, rows, cols, rs, cs, dA, ld);
+    bidiagonal<T>(*h, dA, rows, cols, ld, dD, dE);
+    download<T>(*h, dA, ld, a, rows, cols, rs, cs);
+    download_vec<T>(*h, dD, md, d);
+    if (md > 1) download_vec<T>(*h, dE, md - 1, e);
+    LFB_API_END(h)
+}
+
+template <typename T>
+int qr_batched_host(lfb_handle *h, T *a, int64_t batch, int64_t m, int64_t n, T *diag) {
+    if (m < n) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
+    if (m > 32 || n > 32) return fail(h, LFB_UNSUPPORTED, "batched QR supports m, n <= 32");
+    if (batch <= 0 || n == 0) return LFB_OK;
+    LFB_API_BEGIN(h)
+    DevBuf<T> dA(*h, (size_t)batch * m * n), dD(*h, (size_t)batch * n);
+    LFB_CUDA(cudaMemcpyAsync(dA.get(), a, sizeof(T) * batch * m * n, cudaMemcpyHostToDevice, h->stream));
+    qr_batched<T>(*h, dA, batch, m, n, dD);
+    LFB_CUDA(cudaMemcpyAsync(a, dA.get(), sizeof(T) * batch * m * n, cudaMemcpyDeviceToHost, h->stream));
+    LFB_CUDA(cudaMemcpyAsync(diag, dD.get(), sizeof(T) * batch * n, cudaMemcpyDeviceToHost, h->stream));
+    LFB_CUDA(cudaStreamSynchronize(h->stream));
+    LFB_API_END(h)
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *lfb_version(void) { return "linfa_b200 0.1 (sm_100a; DMMA FP64 GEMM core; compact-WY QR; recursive Cholesky)"; }
+
+int lfb_create(lfb_handle **out, int device) {
+    if (!out) return LFB_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return LFB_ERR_CUDA;  // no CPU fallback by design
+    }
+    lfb_handle *h = new lfb_handle();
+    h->device = device;
+    try {
+        LFB_CUDA(cudaSetDevice(device));
+        LFB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
+        cudaDeviceProp prop;
+        LFB_CUDA(cudaGetDeviceProperties(&prop, device));
+        h->sm_count = prop.multiProcessorCount;
+        h->smem_optin = prop.sharedMemPerBlockOptin;
+    } catch (const std::exception &) {
+        delete h;
+        return LFB_ERR_CUDA;
+    }
+    *out = h;
+    return LFB_OK;
+}
+
+int lfb_destroy(lfb_handle *h) {
+    if (!h) return LFB_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto &b : h->blocks) cudaFree(b.p);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return LFB_OK;
+}
+
+const char *lfb_last_error(lfb_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int lfb_set_stream(lfb_handle *h, void *s) {
+    if (!h) return LFB_INVALID_ARGUMENT;
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return LFB_OK;
+}
+
+int lfb_synchronize(lfb_handle *h) {
+    LFB_API_BEGIN(h)
+    LFB_CUDA(cudaStreamSynchronize(h->stream));
+    LFB_API_END(h)
+}
+
+int64_t lfb_launch_count(lfb_handle *h) { return h ? h->launches : 0; }
+
+int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
+    if (!h || !key) return LFB_INVALID_ARGUMENT;
+    std::string k(key);
+    if (k == "qr_nb") h->opt.qr_nb = value;
+    else if (k == "qr_sub") h->opt.qr_sub = value;
+    else if (k == "chol_base") h->opt.chol_base = value;
+    else if (k == "gemm_tma") h->opt.gemm_tma = value;
+    else if (k == "gemm_splitk") h->opt.gemm_splitk = value;
+    else if (k == "panel_cluster") h->opt.panel_cluster = value;
+    else return LFB_INVALID_ARGUMENT;
+    return LFB_OK;
+}
+
+#define DEF2(name, T, sfx, args, call) \
+    int name##sfx args { return call; }
+
+int lfb_qr_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *diag) { return qr_host<double>(h, a, r, c, rs, cs, diag); }
+int lfb_qr_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *diag) { return qr_host<float>(h, a, r, c, rs, cs, diag); }
+
+int lfb_assemble_q_f64(lfb_handle *h, const double *m, int64_t r, int64_t c, int64_t rs, int64_t cs, int64_t shift, const double *signs, double *q, int64_t qrs, int64_t qcs) {
+    return assemble_q_host<double>(h, m, r, c, rs, cs, shift, signs, q, qrs, qcs);
+}
+int lfb_assemble_q_f32(lfb_handle *h, const float *m, int64_t r, int64_t c, int64_t rs, int64_t cs, int64_t shift, const float *signs, float *q, int64_t qrs, int64_t qcs) {
+    return assemble_q_host<float>(h, m, r, c, rs, cs, shift, signs, q, qrs, qcs);
+}
+int lfb_qt_mul_f64(lfb_handle *h, const double *qr, int64_t r, int64_t c, int64_t rs, int64_t cs, const double *diag, double *b, int64_t bc, int64_t brs, int64_t bcs) {
+    return qt_mul_host<double>(h, qr, r, c, rs, cs, diag, b, bc, brs, bcs);
+}
+int lfb_qt_mul_f32(lfb_handle *h, const float *qr, int64_t r, int64_t c, int64_t rs, int64_t cs, const float *diag, float *b, int64_t bc, int64_t brs, int64_t bcs) {
+    return qt_mul_host<float>(h, qr, r, c, rs, cs, diag, b, bc, brs, bcs);
+}
+int lfb_cholesky_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, int clean, int64_t *fi) { return cholesky_host<double>(h, a, r, c, rs, cs, clean, fi); }
+int lfb_cholesky_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, int clean, int64_t *fi) { return cholesky_host<float>(h, a, r, c, rs, cs, clean, fi); }
+int lfb_solve_triangular_f64(lfb_handle *h, const double *a, int64_t ar, int64_t ac, int64_t ars, int64_t acs, double *b, int64_t br, int64_t bc, int64_t brs, int64_t bcs, int uplo, const double *ed) {
+    return solve_triangular_host<double>(h, a, ar, ac, ars, acs, b, br, bc, brs, bcs, uplo, ed);
+}
+int lfb_solve_triangular_f32(lfb_handle *h, const float *a, int64_t ar, int64_t ac, int64_t ars, int64_t acs, float *b, int64_t br, int64_t bc, int64_t brs, int64_t bcs, int uplo, const float *ed) {
+    return solve_triangular_host<float>(h, a, ar, ac, ars, acs, b, br, bc, brs, bcs, uplo, ed);
+}
+int lfb_triangular_inplace_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, int uplo) { return triangular_inplace_host<double>(h, a, r, c, rs, cs, uplo); }
+int lfb_triangular_inplace_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, int uplo) { return triangular_inplace_host<float>(h, a, r, c, rs, cs, uplo); }
+int lfb_sym_tridiagonal_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *off) { return sym_tridiagonal_host<double>(h, a, r, c, rs, cs, off); }
+int lfb_sym_tridiagonal_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *off) { return sym_tridiagonal_host<float>(h, a, r, c, rs, cs, off); }
+int lfb_bidiagonal_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *d, double *e) { return bidiagonal_host<double>(h, a, r, c, rs, cs, d, e); }
+int lfb_bidiagonal_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *d, float *e) { return bidiagonal_host<float>(h, a, r, c, rs, cs, d, e); }
+int lfb_qr_batched_f32(lfb_handle *h, float *a, int64_t batch, int64_t m, int64_t n, float *diag) { return qr_batched_host<float>(h, a, batch, m, n, diag); }
+int lfb_qr_batched_f64(lfb_handle *h, double *a, int64_t batch, int64_t m, int64_t n, double *diag) { return qr_batched_host<double>(h, a, batch, m, n, diag); }
+
+// ---- device-resident variants (async on the handle's stream) ----
+int lfb_qr_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_diag) {
+    if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
+    LFB_API_BEGIN(h)
+    qr_factor<double>(*h, d_a, rows, cols, ld, d_diag);
+    LFB_API_END(h)
+}
+int lfb_qr_dev_f32(lfb_handle *h, float *d_a, int64_t rows, int64_t cols, int64_t ld, float *d_diag) {
+    if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
+    LFB_API_BEGIN(h)
+    qr_factor<float>(*h, d_a, rows, cols, ld, d_diag);
+    LFB_API_END(h)
+}
+int lfb_cholesky_dev_f64(lfb_handle *h, double *d_a, int64_t n, int64_t ld, int clean, int64_t *d_info) {
+    LFB_API_BEGIN(h)
+    cholesky_lower<double>(*h, d_a, n, ld, clean, d_info);
+    LFB_API_END(h)
+}
+int lfb_cholesky_dev_f32(lfb_handle *h, float *d_a, int64_t n, int64_t ld, int clean, int64_t *d_info) {
+    LFB_API_BEGIN(h)
+    cholesky_lower<float>(*h, d_a, n, ld, clean, d_info);
+    LFB_API_END(h)
+}
+int lfb_assemble_q_dev_f64(lfb_handle *h, const double *d_m, int64_t rows, int64_t cols, int64_t ld, int64_t shift,
+                           const double *d_signs, double *d_q, int64_t ldq) {
+    if (shift > std::min(rows, cols)) return fail(h, LFB_INVALID_ARGUMENT, "shift exceeds matrix dimension");
+    LFB_API_BEGIN(h)
+    assemble_q<double>(*h, d_m, rows, cols, ld, shift, d_signs, d_q, ldq);
+    LFB_API_END(h)
+}
+int lfb_sym_tridiagonal_dev_f64(lfb_handle *h, double *d_a, int64_t n, int64_t ld, double *d_off) {
+    if (n < 1) return fail(h, LFB_EMPTY_MATRIX, "Matrix is empty");
+    LFB_API_BEGIN(h)
+    sym_tridiagonal<double>(*h, d_a, n, ld, d_off);
+    LFB_API_END(h)
+}
+int lfb_bidiagonal_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_d, double *d_e) {
+    if (std::min(rows, cols) < 1) return fail(h, LFB_EMPTY_MATRIX, "Matrix is empty");
+    LFB_API_BEGIN(h)
+    bidiagonal<double>(*h, d_a, rows, cols, ld, d_d, d_e);
+    LFB_API_END(h)
+}
+int lfb_qr_batched_dev_f32(lfb_handle *h, float *d_a, int64_t batch, int64_t m, int64_t n, float *d_diag) {
+    if (m < n) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
+    if (m > 32 || n > 32) return fail(h, LFB_UNSUPPORTED, "batched QR supports m, n <= 32");
+    LFB_API_BEGIN(h)
+    qr_batched<float>(*h, d_a, batch, m, n, d_diag);
+    LFB_API_END(h)
+}
+int lfb_tsqr_local_r_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_r, int64_t ldr) {
+    if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
+    LFB_API_BEGIN(h)
+    tsqr_local_r<double>(*h, d_a, rows, cols, ld, d_r, ldr);
+    LFB_API_END(h)
+}
+int lfb_gemm_dev_f64(lfb_handle *h, int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const double *d_a,
+                     int64_t lda, const double *d_b, int64_t ldb, double beta, double *d_c, int64_t ldc) {
+    LFB_API_BEGIN(h)
+    gemm<double>(*h, ta, tb, m, n, k, alpha, d_a, lda, d_b, ldb, beta, d_c, ldc);
+    LFB_API_END(h)
+}
+int lfb_gemm_dev_f32(lfb_handle *h, int ta, int tb, int64_t m, int64_t n, int64_t k, float alpha, const float *d_a,
+                     int64_t lda, const float *d_b, int64_t ldb, float beta, float *d_c, int64_t ldc) {
+    LFB_API_BEGIN(h)
+    gemm<float>(*h, ta, tb, m, n, k, alpha, d_a, lda, d_b, ldb, beta, d_c, ldc);
+    LFB_API_END(h)
+}
+int lfb_profile_begin(lfb_handle *h) {
+    if (!h) return LFB_INVALID_ARGUMENT;
+    h->prof_on = true;
+    h->prof_used = 0;
+    h->prof_flops = 0.0;
+    return LFB_OK;
+}
+int lfb_profile_end(lfb_handle *h, double *gemm_ms, double *gemm_flops, int64_t *gemm_calls) {
+    LFB_API_BEGIN(h)
+    h->prof_on = false;
+    LFB_CUDA(cudaStreamSynchronize(h->stream));
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+        float t = 0.f;
+        LFB_CUDA(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
+        ms += t;
+    }
+    if (gemm_ms) *gemm_ms = ms;
+    if (gemm_flops) *gemm_flops = h->prof_flops;
+    if (gemm_calls) *gemm_calls = (int64_t)(h->prof_used / 2);
+    LFB_API_END(h)
+}
+int lfb_microbench_fp64(lfb_handle *h, int kind, double *gflops) {
+    if (!gflops) return LFB_INVALID_ARGUMENT;
+    LFB_API_BEGIN(h)
+    *gflops = microbench_fp64(*h, kind);
+    LFB_API_END(h)
+}
+
+}  // extern "C"

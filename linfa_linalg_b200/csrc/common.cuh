@@ -1,0 +1,166 @@
+// Shared host-side plumbing of liblinfa_b200: handle, workspace pool, error handling.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/linfa_b200.h"
+
+namespace lfb {
+
+struct CudaError : std::runtime_error {
+    int code;
+    CudaError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define LFB_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            char buf__[512];                                                                    \
+            snprintf(buf__, sizeof buf__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                     __FILE__, __LINE__);                                                       \
+            throw ::lfb::CudaError(e__ == cudaErrorMemoryAllocation ? LFB_ERR_ALLOC : LFB_ERR_CUDA, buf__); \
+        }                                                                                       \
+    } while (0)
+
+#define LFB_LAUNCH_CHECK(h)                 \
+    do {                                    \
+        (h).launches++;                     \
+        LFB_CUDA(cudaGetLastError());       \
+    } while (0)
+
+struct Options {
+    int64_t qr_nb = 128;     // outer panel width of blocked compact-WY QR
+    int64_t qr_sub = 32;     // inner BLAS-2 sub-panel width (<= 32)
+    int64_t chol_base = 64;  // recursion base of Cholesky / TRSM (<= 64)
+    int64_t gemm_tma = 1;    // use the TMA-fed DGEMM when operands are 16-byte aligned
+    int64_t gemm_splitk = 1; // allow split-K for skinny-output GEMMs
+    int64_t panel_cluster = 1; // use the cluster/DSMEM panel kernel when the panel fits
+};
+
+}  // namespace lfb
+
+// The opaque C handle.
+struct lfb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // stream in use
+    cudaStream_t own_stream = nullptr;  // created by lfb_create
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    std::string err;
+    int64_t launches = 0;
+    lfb::Options opt;
+
+    // ---- caching device allocator (the engine reuses workspaces across calls) ----
+    struct Block { void *p; size_t bytes; bool used; };
+    std::vector<Block> blocks;
+    void *pinned = nullptr; size_t pinned_bytes = 0;
+
+    // ---- optional GEMM profiler (bench.py roofline): CUDA events around every GEMM launch ----
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
+    double prof_flops = 0.0;
+    cudaEvent_t prof_event() {
+        if (prof_used == prof_ev.size()) {
+            cudaEvent_t e;
+            LFB_CUDA(cudaEventCreate(&e));
+            prof_ev.push_back(e);
+        }
+        return prof_ev[prof_used++];
+    }
+
+    void *dalloc(size_t bytes) {
+        if (bytes == 0) bytes = 256;
+        bytes = (bytes + 255) & ~size_t(255);
+        int best = -1;
+        for (int i = 0; i < (int)blocks.size(); ++i)
+            if (!blocks[i].used && blocks[i].bytes >= bytes && blocks[i].bytes <= 2 * bytes + (1 << 20))
+                if (best < 0 || blocks[i].bytes < blocks[best].bytes) best = i;
+        if (best >= 0) { blocks[best].used = true; return blocks[best].p; }
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            // free cached blocks and retry once
+            cudaGetLastError();
+            trim();
+            e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                throw lfb::CudaError(LFB_ERR_ALLOC, "device allocation of " + std::to_string(bytes) + " bytes failed");
+            }
+        }
+        blocks.push_back({p, bytes, true});
+        return p;
+    }
+    void dfree(void *p) {
+        for (auto &b : blocks) if (b.p == p) { b.used = false; return; }
+    }
+    void trim() {
+        std::vector<Block> keep;
+        for (auto &b : blocks) { if (b.used) keep.push_back(b); else cudaFree(b.p); }
+        blocks.swap(keep);
+    }
+    void *pinned_buf(size_t bytes) {
+        if (bytes > pinned_bytes) {
+            if (pinned) cudaFreeHost(pinned);
+            pinned = nullptr; pinned_bytes = 0;
+            LFB_CUDA(cudaMallocHost(&pinned, bytes));
+            pinned_bytes = bytes;
+        }
+        return pinned;
+    }
+};
+
+namespace lfb {
+
+// RAII device buffer from the handle's pool.
+template <typename T>
+struct DevBuf {
+    lfb_handle *h; T *p; size_t n;
+    DevBuf(lfb_handle &hh, size_t count) : h(&hh), p((T *)hh.dalloc(count * sizeof(T))), n(count) {}
+    ~DevBuf() { if (p) h->dfree(p); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    T *get() const { return p; }
+    operator T *() const { return p; }
+};
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int64_t round_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
+
+// ---- internal engine API (all column-major device pointers, async on h.stream) ----
+template <typename T>
+void gemm(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int64_t K, T alpha, const T *A, int64_t lda,
+          const T *B, int64_t ldb, T beta, T *C, int64_t ldc, int lower_only = 0);
+
+template <typename T> void transpose(lfb_handle &h, const T *in, int64_t rows, int64_t cols, int64_t ldin, T *out, int64_t ldout);
+template <typename T> void transpose_inplace_square(lfb_handle &h, T *a, int64_t n, int64_t ld);
+template <typename T> void fill(lfb_handle &h, T *p, int64_t rows, int64_t cols, int64_t ld, T offdiag, T diag);
+template <typename T> void copy2d(lfb_handle &h, const T *in, int64_t ldin, T *out, int64_t ldout, int64_t rows, int64_t cols);
+
+template <typename T> void qr_factor(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld, T *diag);
+template <typename T> void assemble_q(lfb_handle &h, const T *M, int64_t rows, int64_t cols, int64_t ld, int64_t shift,
+                                      const T *signs, T *Q, int64_t ldq);
+template <typename T> void qt_mul(lfb_handle &h, const T *QR, int64_t rows, int64_t cols, int64_t ld, const T *diag,
+                                  T *B, int64_t bcols, int64_t ldb);
+template <typename T> void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64_t *d_info);
+// op(A) X = B, A n x n column-major, lower != 0 -> A is lower triangular; trans != 0 -> solve A^T X = B.
+template <typename T> void trsm_left(lfb_handle &h, int lower, int trans, int64_t n, int64_t nrhs, const T *A, int64_t lda,
+                                     const T *ext_diag, T *B, int64_t ldb);
+template <typename T> void sym_tridiagonal(lfb_handle &h, T *A, int64_t n, int64_t ld, T *off);
+template <typename T> void bidiagonal(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *d, T *e);
+template <typename T> void qr_batched(lfb_handle &h, T *A, int64_t batch, int64_t m, int64_t n, T *diag);
+template <typename T> void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *R, int64_t ldr);
+template <typename T> void triangular_zero(lfb_handle &h, T *A, int64_t n, int64_t ld, int keep_lower);
+double microbench_fp64(lfb_handle &h, int kind);
+
+}  // namespace lfb

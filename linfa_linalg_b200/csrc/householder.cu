@@ -1,0 +1,432 @@
+// Householder panel kernels + blocked compact-WY drivers (QR, assemble_q, qt_mul).
+//
+// Replaces: src/householder.rs:9-28 (reflection_axis_mut), :34-51 (clear_column), :68-93
+// (assemble_q); src/reflection.rs:26-32 (reflect_cols hot loop); src/qr.rs:38-41 (driver loop),
+// :110-120 (qt_mul).
+//
+// Mathematics: the reference applies s_j * H_j per column (H_j = I - 2 v v^T with a
+// UNIT-NORM v, s_j = signum of the returned pivot).  Because the +-1 row scalings commute with all
+// later reflectors, the whole factorisation equals a standard Householder QR (no scaling) followed
+// by one O(mn) sign fix-up:  P_j = sgn(beta_j) (P_j = P_{j-1} for a zero column),
+//   diag_ref[j] = P_{j-1} beta_j,  R_ref[i, j>i] = P_i R[i, j],  v_ref,j = P_{j-1} v_j.
+// The standard QR is blocked: BLAS-2 sub-panels of width <= 32 (one fused kernel per column: scale
+// the reflector, update the sub-panel, and accumulate the NEXT column's Gram row in the same pass,
+// so a column costs one launch and one pass over the sub-panel), compact-WY block reflectors
+// I - V T V^T with T = (striu(V^T V) + I/2)^-1 (tau = 2 for unit-norm v), and GEMM trailing updates.
+#include "common.cuh"
+
+namespace lfb {
+namespace {
+
+constexpr int W = 32;  // max sub-panel width
+
+template <typename T> __device__ __forceinline__ T t_sqrt(T x);
+template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
+template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
+template <typename T> __device__ __forceinline__ T t_abs(T x) { return x < T(0) ? -x : x; }
+// Rust signum: +1 for +0.0, -1 for -0.0
+template <typename T> __device__ __forceinline__ T t_signum(T x) { return signbit(x) ? T(-1) : T(1); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-reduce `cnt` per-thread partials (part[0..cnt)) and atomically add them to out[0..cnt).
+template <typename T, int NT>
+__device__ __forceinline__ void block_reduce_add(T *part, int cnt, T *out, T *sred /* [NT/32][W] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < W; ++t) {
+        if (t < cnt) {
+            T s = warp_sum(part[t]);
+            if (lane == 0) sred[warp * W + t] = s;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < cnt) {
+        T s = T(0);
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) s += sred[w * W + threadIdx.x];
+        atomicAdd(out + threadIdx.x, s);
+    }
+}
+
+// Gram row + head row of the first column of a sub-panel:
+//   gram[t] = sum_{r >= c} A[r,c] A[r,c+t],  head[t] = A[c, c+t],  t = 0..w-1
+template <typename T>
+__global__ void __launch_bounds__(256) hh_gram_init(const T *__restrict__ A, int64_t ld, int64_t m, int64_t c, int w,
+                                                    T *gram, T *head) {
+    __shared__ T sred[8 * W];
+    T part[W];
+#pragma unroll
+    for (int t = 0; t < W; ++t) part[t] = T(0);
+    const T *col = A + c * ld;
+    for (int64_t r = c + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < m; r += (int64_t)gridDim.x * blockDim.x) {
+        T x = col[r];
+#pragma unroll
+        for (int t = 0; t < W; ++t)
+            if (t < w) {
+                T a = col[r + t * ld];
+                part[t] += x * a;
+                if (r == c) head[t] = a;
+            }
+    }
+    block_reduce_add<T, 256>(part, w, gram, sred);
+}
+
+// One Householder column step (see file header).  Column c = c0 + j of a sub-panel [c0, c0+w).
+//   gram_cur[t] = x . A[:, c+t] over rows >= c (t = 0..w-j-1), head_cur[t] = A[c, c+t].
+// Writes v in place, updates columns c+1 .. c0+w-1, accumulates gram_next / head_next for column
+// c+1, stores beta[c] (= -signed_norm, 0 for a `None` column), zeroes gram_zero for the step after.
+template <typename T>
+__global__ void __launch_bounds__(256) hh_col_step(T *__restrict__ A, int64_t ld, int64_t m, int64_t c, int nrem,
+                                                   const T *__restrict__ gram_cur, T *gram_next, T *gram_zero,
+                                                   const T *__restrict__ head_cur, T *head_next, T *beta) {
+    __shared__ T sred[8 * W];
+    __shared__ T sfac[W];
+    __shared__ T sscal[3];  // s, d, some
+    if (threadIdx.x == 0) {
+        T nsq = gram_cur[0];
+        T nrm = t_sqrt(nsq);                          // householder.rs:13
+        T f = head_cur[0];
+        T s = t_signum(f) * nrm;                      // :16
+        T newsq = (nsq + t_abs(f) * nrm) * T(2);      // :19-20
+        bool some = newsq != T(0);                    // :22  (false for an all-zero / underflowed column)
+        T d = t_sqrt(newsq);
+        sscal[0] = s; sscal[1] = d; sscal[2] = some ? T(1) : T(0);
+        if (blockIdx.x == 0) beta[c] = some ? -s : T(0);   // :24 / :26
+    }
+    if (blockIdx.x == 0 && threadIdx.x < W) gram_zero[threadIdx.x] = T(0);
+    __syncthreads();
+    const T s = sscal[0], d = sscal[1];
+    const bool some = sscal[2] != T(0);
+    if (threadIdx.x >= 1 && threadIdx.x <= nrem) {
+        // v . A_t = (x . A_t + s * A_t[head]) / d ; reflection.rs:29 factor = -2 * (axis . col)
+        int t = threadIdx.x;
+        sfac[t] = some ? T(-2) * ((gram_cur[t] + s * head_cur[t]) / d) : T(0);
+    }
+    __syncthreads();
+
+    T part[W];
+#pragma unroll
+    for (int t = 0; t < W; ++t) part[t] = T(0);
+    T *col = A + c * ld;
+    for (int64_t r = c + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < m; r += (int64_t)gridDim.x * blockDim.x) {
+        T x = col[r];
+        T v = T(0);
+        if (some) {
+            v = ((r == c) ? x + s : x) / d;           // householder.rs:17,23
+            col[r] = v;
+        }
+        T a1 = T(0);
+#pragma unroll
+        for (int t = 1; t < W; ++t)
+            if (t <= nrem) {
+                T a = col[r + t * ld];
+                if (some) {
+                    a += sfac[t] * v;                 // reflection.rs:30 scaled_add
+                    col[r + t * ld] = a;
+                }
+                if (t == 1) a1 = a;
+                if (r > c) {
+                    part[t - 1] += a1 * a;
+                    if (r == c + 1) head_next[t - 1] = a;
+                }
+            }
+    }
+    if (nrem > 0) block_reduce_add<T, 256>(part, nrem, gram_next, sred);
+}
+
+// Vout (rows x w, ldv) = V part of A[r0:, c0:c0+w): element (i, j) is zero for i < j ("upper" part
+// holds R), and whole column j is zeroed when beta != nullptr and beta[c0+j] == 0 (a `None` column:
+// the reference applies no reflection there).
+template <typename T>
+__global__ void copy_v_kernel(const T *__restrict__ A, int64_t ld, int64_t r0, int64_t c0, int64_t rows, int w,
+                              const T *__restrict__ beta, T *__restrict__ V, int64_t ldv) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    for (int j = blockIdx.y; j < w; j += gridDim.y) {
+        T v = T(0);
+        if (i >= j && !(beta && beta[c0 + j] == T(0))) v = A[(r0 + i) + (c0 + j) * ld];
+        V[i + (int64_t)j * ldv] = v;
+    }
+}
+
+// T = (striu(G) + I/2)^-1 for an nb x nb Gram matrix G = V^T V (single CTA, nb <= 128).
+// Column j of T solves U t = e_j by back substitution; one thread per column.
+template <typename T>
+__global__ void tinv_kernel(const T *__restrict__ G, int64_t ldg, int nb, T *__restrict__ Tm, int64_t ldt) {
+    extern __shared__ unsigned char smem_raw[];
+    T *U = reinterpret_cast<T *>(smem_raw);  // nb x (nb+1), U[i*(nb+1)+k] = U(i,k), i<k
+    const int lds = nb + 1;
+    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
+        int i = e % nb, k = e / nb;
+        U[i * lds + k] = (i < k) ? G[i + (int64_t)k * ldg] : T(0);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+        T *tcol = Tm + (int64_t)j * ldt;
+        for (int i = j + 1; i < nb; ++i) tcol[i] = T(0);
+        tcol[j] = T(2);
+        for (int i = j - 1; i >= 0; --i) {
+            T sum = T(0);
+            for (int k = i + 1; k <= j; ++k) sum += U[i * lds + k] * tcol[k];
+            tcol[i] = T(-2) * sum;
+        }
+    }
+}
+
+// psign[j] = P_j (running sign, header comment); diag[j] = P_{j-1} * beta[j].  Single thread scan.
+template <typename T>
+__global__ void sign_scan_kernel(const T *__restrict__ beta, int64_t n, T *__restrict__ psign, T *__restrict__ diag) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    T p = T(1);
+    for (int64_t j = 0; j < n; ++j) {
+        T b = beta[j];
+        diag[j] = p * b;
+        if (b != T(0)) p = t_signum(b);
+        psign[j] = p;
+    }
+}
+
+// R part (r < c): *= P_r ; V part (r >= c): *= P_{c-1}.
+template <typename T>
+__global__ void sign_fix_kernel(T *A, int64_t ld, int64_t m, int64_t n, const T *__restrict__ psign) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    T pr = r < n ? psign[r] : T(1);
+    for (int64_t c = blockIdx.y; c < n; c += gridDim.y) {
+        T f = (r < c) ? pr : (c > 0 ? psign[c - 1] : T(1));
+        if (f < T(0)) A[r + c * ld] = -A[r + c * ld];
+    }
+}
+
+// cum[j] = prod_{i <= j} signum(signs[i]) for j < cnt.
+template <typename T>
+__global__ void sign_cumprod_kernel(const T *__restrict__ signs, int64_t cnt, T *__restrict__ cum) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    T p = T(1);
+    for (int64_t j = 0; j < cnt; ++j) {
+        p *= t_signum(signs[j]);
+        cum[j] = p;
+    }
+}
+
+// Q[:, c] *= cum[min(c - shift, cnt-1)]  (c >= shift)
+template <typename T>
+__global__ void scale_cols_kernel(T *Q, int64_t ldq, int64_t rows, int64_t cols, int64_t shift, int64_t cnt,
+                                  const T *__restrict__ cum) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    for (int64_t c = blockIdx.y; c < cols; c += gridDim.y) {
+        int64_t k = c - shift;
+        if (k < 0 || cnt <= 0) continue;
+        if (k > cnt - 1) k = cnt - 1;
+        if (cum[k] < T(0)) Q[r + c * ldq] = -Q[r + c * ldq];
+    }
+}
+
+// B[r, :] *= cum[min(r, cnt-1)]
+template <typename T>
+__global__ void scale_rows_kernel(T *B, int64_t ldb, int64_t rows, int64_t cols, int64_t cnt, const T *__restrict__ cum) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= rows || cnt <= 0) return;
+    T f = cum[r < cnt ? r : cnt - 1];
+    if (!(f < T(0))) return;
+    for (int64_t c = blockIdx.y; c < cols; c += gridDim.y) B[r + c * ldb] = -B[r + c * ldb];
+}
+
+inline unsigned ycap(int64_t n) { return (unsigned)(n < 1 ? 1 : (n < 65535 ? n : 65535)); }
+
+template <typename T>
+void copy_v(lfb_handle &h, const T *A, int64_t ld, int64_t r0, int64_t c0, int64_t rows, int w, const T *beta, T *V,
+            int64_t ldv) {
+    if (rows <= 0 || w <= 0) return;
+    dim3 grid((unsigned)cdiv(rows, 256), ycap(w));
+    copy_v_kernel<T><<<grid, 256, 0, h.stream>>>(A, ld, r0, c0, rows, w, beta, V, ldv);
+    LFB_LAUNCH_CHECK(h);
+}
+
+// Tm (nb x nb, ldt) from V (rows x nb, ldv); G is an nb x nb scratch.
+template <typename T>
+void build_t(lfb_handle &h, const T *V, int64_t ldv, int64_t rows, int nb, T *G, T *Tm, int64_t ldt) {
+    gemm<T>(h, 1, 0, nb, nb, rows, T(1), V, ldv, V, ldv, T(0), G, nb);
+    size_t smem = sizeof(T) * nb * (nb + 1);
+    static bool cfg = false;
+    if (!cfg) {
+        LFB_CUDA(cudaFuncSetAttribute(tinv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(T) * 128 * 129)));
+        cfg = true;
+    }
+    tinv_kernel<T><<<1, 128, smem, h.stream>>>(G, nb, nb, Tm, ldt);
+    LFB_LAUNCH_CHECK(h);
+}
+
+// C (rows x ncols, ldc) <- (I - V op(T) V^T) C,  op(T) = T^T if trans_t.  W1/W2: nb x ncols scratch.
+template <typename T>
+void apply_block_reflector(lfb_handle &h, const T *V, int64_t ldv, int64_t rows, int nb, const T *Tm, int64_t ldt,
+                           int trans_t, T *C, int64_t ldc, int64_t ncols, T *W1, T *W2) {
+    if (ncols <= 0 || rows <= 0) return;
+    gemm<T>(h, 1, 0, nb, ncols, rows, T(1), V, ldv, C, ldc, T(0), W1, nb);          // W1 = V^T C
+    gemm<T>(h, trans_t, 0, nb, ncols, nb, T(1), Tm, ldt, W1, nb, T(0), W2, nb);     // W2 = op(T) W1
+    gemm<T>(h, 0, 0, rows, ncols, nb, T(-1), V, ldv, W2, nb, T(1), C, ldc);         // C -= V W2
+}
+
+// Unblocked-in-sub-panel Householder on columns [c0, c0+w) of A (m x ., ld), rows >= c0.
+template <typename T>
+void factor_subpanel(lfb_handle &h, T *A, int64_t ld, int64_t m, int64_t c0, int w, T *beta, T *scratch /* 5*W */) {
+    T *gram[3] = {scratch, scratch + W, scratch + 2 * W};
+    T *head[2] = {scratch + 3 * W, scratch + 4 * W};
+    LFB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(T) * 5 * W, h.stream));
+    int64_t rows = m - c0;
+    unsigned nblk = (unsigned)std::min<int64_t>(cdiv(rows, 256), 2 * h.sm_count);
+    if (nblk < 1) nblk = 1;
+    hh_gram_init<T><<<nblk, 256, 0, h.stream>>>(A, ld, m, c0, w, gram[0], head[0]);
+    LFB_LAUNCH_CHECK(h);
+    for (int j = 0; j < w; ++j) {
+        int64_t c = c0 + j;
+        int64_t r = m - c;
+        unsigned nb = (unsigned)std::min<int64_t>(cdiv(r, 256), 2 * h.sm_count);
+        if (nb < 1) nb = 1;
+        hh_col_step<T><<<nb, 256, 0, h.stream>>>(A, ld, m, c, w - j - 1, gram[j % 3], gram[(j + 1) % 3], gram[(j + 2) % 3],
+                                                 head[j % 2], head[(j + 1) % 2], beta);
+        LFB_LAUNCH_CHECK(h);
+    }
+}
+
+}  // namespace
+
+// Standard (unscaled) blocked Householder QR of A (m x n, m >= n); beta[n] on device.
+template <typename T>
+static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld, T *beta) {
+    const int NB = (int)std::max<int64_t>(W, std::min<int64_t>(h.opt.qr_nb, 128));
+    const int SUB = (int)std::max<int64_t>(1, std::min<int64_t>(h.opt.qr_sub, W));
+    const int64_t ldv = round_up(m, 2);
+    DevBuf<T> V(h, (size_t)ldv * NB);
+    DevBuf<T> Tm(h, (size_t)NB * NB), G(h, (size_t)NB * NB);
+    DevBuf<T> W1(h, (size_t)NB * std::max<int64_t>(n, 1)), W2(h, (size_t)NB * std::max<int64_t>(n, 1));
+    DevBuf<T> scratch(h, 5 * W);
+
+    for (int64_t k0 = 0; k0 < n; k0 += NB) {
+        const int nb = (int)std::min<int64_t>(NB, n - k0);
+        for (int s0 = 0; s0 < nb; s0 += SUB) {
+            const int w = std::min(SUB, nb - s0);
+            const int64_t c0 = k0 + s0;
+            factor_subpanel<T>(h, A, ld, m, c0, w, beta, scratch);
+            const int64_t rest = (k0 + nb) - (c0 + w);  // remaining columns of this panel
+            if (rest > 0) {
+                const int64_t rows = m - c0;
+                copy_v<T>(h, A, ld, c0, c0, rows, w, beta, V, ldv);
+                build_t<T>(h, V, ldv, rows, w, G, Tm, NB);
+                apply_block_reflector<T>(h, V, ldv, rows, w, Tm, NB, /*trans_t=*/1, A + c0 + (c0 + w) * ld, ld, rest, W1, W2);
+            }
+        }
+        const int64_t trail = n - (k0 + nb);
+        if (trail > 0) {
+            const int64_t rows = m - k0;
+            copy_v<T>(h, A, ld, k0, k0, rows, nb, beta, V, ldv);
+            build_t<T>(h, V, ldv, rows, nb, G, Tm, NB);
+            apply_block_reflector<T>(h, V, ldv, rows, nb, Tm, NB, /*trans_t=*/1, A + k0 + (k0 + nb) * ld, ld, trail, W1, W2);
+        }
+    }
+}
+
+template <typename T>
+void qr_factor(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld, T *diag) {
+    if (n <= 0) return;
+    DevBuf<T> beta(h, n), psign(h, n);
+    qr_factor_std<T>(h, A, m, n, ld, beta);
+    sign_scan_kernel<T><<<1, 32, 0, h.stream>>>(beta, n, psign, diag);
+    LFB_LAUNCH_CHECK(h);
+    dim3 grid((unsigned)cdiv(m, 256), ycap(n));
+    sign_fix_kernel<T><<<grid, 256, 0, h.stream>>>(A, ld, m, n, psign);
+    LFB_LAUNCH_CHECK(h);
+}
+
+// R-only local QR for TSQR: R (n x n, upper, diag >= 0).  A is overwritten.
+template <typename T>
+__global__ void extract_r_kernel(const T *__restrict__ A, int64_t ld, int64_t n, const T *__restrict__ diag, T *__restrict__ R, int64_t ldr) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    for (int64_t c = blockIdx.y; c < n; c += gridDim.y) {
+        T v = T(0);
+        if (r < c) v = A[r + c * ld];
+        else if (r == c) v = diag[r] < T(0) ? -diag[r] : diag[r];   // qr.rs:96
+        R[r + c * ldr] = v;
+    }
+}
+
+template <typename T>
+void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *R, int64_t ldr) {
+    if (cols <= 0) return;
+    DevBuf<T> diag(h, cols);
+    qr_factor<T>(h, A, rows, cols, ld, diag);
+    dim3 grid((unsigned)cdiv(cols, 256), ycap(cols));
+    extract_r_kernel<T><<<grid, 256, 0, h.stream>>>(A, ld, cols, diag, R, ldr);
+    LFB_LAUNCH_CHECK(h);
+}
+
+template <typename T>
+void assemble_q(lfb_handle &h, const T *M, int64_t rows, int64_t cols, int64_t ld, int64_t shift, const T *signs, T *Q,
+                int64_t ldq) {
+    const int64_t dim = std::min(rows, cols);
+    if (rows <= 0 || dim <= 0) return;
+    fill<T>(h, Q, rows, dim, ldq, T(0), T(1));
+    const int64_t nref = dim - shift;
+    if (nref <= 0) return;
+    const int NB = 128;
+    const int64_t ldv = round_up(rows, 2);
+    DevBuf<T> V(h, (size_t)ldv * NB), Tm(h, (size_t)NB * NB), G(h, (size_t)NB * NB);
+    DevBuf<T> W1(h, (size_t)NB * dim), W2(h, (size_t)NB * dim), cum(h, nref);
+    const int64_t npanels = cdiv(nref, NB);
+    for (int64_t p = npanels - 1; p >= 0; --p) {
+        const int64_t i0 = p * NB;
+        const int nb = (int)std::min<int64_t>(NB, nref - i0);
+        const int64_t r0 = i0 + shift;
+        const int64_t prow = rows - r0;
+        copy_v<T>(h, M, ld, r0, i0, prow, nb, (const T *)nullptr, V, ldv);
+        build_t<T>(h, V, ldv, prow, nb, G, Tm, NB);
+        // householder.rs:87  res[i+shift.., i..]: only columns >= i0 are touched
+        apply_block_reflector<T>(h, V, ldv, prow, nb, Tm, NB, /*trans_t=*/0, Q + r0 + i0 * ldq, ldq, dim - i0, W1, W2);
+    }
+    sign_cumprod_kernel<T><<<1, 32, 0, h.stream>>>(signs, nref, cum);
+    LFB_LAUNCH_CHECK(h);
+    dim3 grid((unsigned)cdiv(rows, 256), ycap(dim));
+    scale_cols_kernel<T><<<grid, 256, 0, h.stream>>>(Q, ldq, rows, dim, shift, nref, cum);
+    LFB_LAUNCH_CHECK(h);
+}
+
+template <typename T>
+void qt_mul(lfb_handle &h, const T *QR, int64_t rows, int64_t cols, int64_t ld, const T *diag, T *B, int64_t bcols,
+            int64_t ldb) {
+    if (cols <= 0 || bcols <= 0 || rows <= 0) return;
+    const int NB = 128;
+    const int64_t ldv = round_up(rows, 2);
+    DevBuf<T> V(h, (size_t)ldv * NB), Tm(h, (size_t)NB * NB), G(h, (size_t)NB * NB);
+    DevBuf<T> W1(h, (size_t)NB * bcols), W2(h, (size_t)NB * bcols), cum(h, cols);
+    for (int64_t i0 = 0; i0 < cols; i0 += NB) {
+        const int nb = (int)std::min<int64_t>(NB, cols - i0);
+        const int64_t prow = rows - i0;
+        copy_v<T>(h, QR, ld, i0, i0, prow, nb, (const T *)nullptr, V, ldv);
+        build_t<T>(h, V, ldv, prow, nb, G, Tm, NB);
+        apply_block_reflector<T>(h, V, ldv, prow, nb, Tm, NB, /*trans_t=*/1, B + i0, ldb, bcols, W1, W2);
+    }
+    sign_cumprod_kernel<T><<<1, 32, 0, h.stream>>>(diag, cols, cum);
+    LFB_LAUNCH_CHECK(h);
+    dim3 grid((unsigned)cdiv(rows, 256), ycap(bcols));
+    scale_rows_kernel<T><<<grid, 256, 0, h.stream>>>(B, ldb, rows, bcols, cols, cum);
+    LFB_LAUNCH_CHECK(h);
+}
+
+#define INST(T)                                                                                                   \
+    template void qr_factor<T>(lfb_handle &, T *, int64_t, int64_t, int64_t, T *);                                \
+    template void tsqr_local_r<T>(lfb_handle &, T *, int64_t, int64_t, int64_t, T *, int64_t);                    \
+    template void assemble_q<T>(lfb_handle &, const T *, int64_t, int64_t, int64_t, int64_t, const T *, T *, int64_t); \
+    template void qt_mul<T>(lfb_handle &, const T *, int64_t, int64_t, int64_t, const T *, T *, int64_t, int64_t);
+INST(float)
+INST(double)
+#undef INST
+
+}  // namespace lfb

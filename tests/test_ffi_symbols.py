@@ -1,0 +1,67 @@
+"""CPU-only: the C-ABI library builds, loads, and exports every symbol include/linfa_b200.h declares.
+No compute call is made here (there is no GPU in the build container)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "linfa_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lfb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_both_scalar_families():
+    names = _declared()
+    for base in ("lfb_qr", "lfb_assemble_q", "lfb_qt_mul", "lfb_cholesky", "lfb_solve_triangular",
+                 "lfb_sym_tridiagonal", "lfb_bidiagonal"):
+        assert base + "_f32" in names and base + "_f64" in names
+
+
+def test_library_exports_every_declared_symbol():
+    from linfa_linalg_b200 import _ffi
+    assert os.path.exists(_ffi.LIB_PATH), "build with __graft_entry__.build()"
+    lib = C.CDLL(_ffi.LIB_PATH)
+    missing = [n for n in _declared() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_ffi_table_matches_header():
+    from linfa_linalg_b200 import _ffi
+    declared = set(_declared())
+    bound = set(_ffi.SIGNATURES)
+    assert bound <= declared, bound - declared
+    _ffi.load()  # declares prototypes; raises if a bound symbol is absent
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the engine must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import numpy as np
+    import linfa_linalg_b200 as L
+    with pytest.raises(L.LinalgError):
+        L.qr(np.eye(3))
+
+
+def test_shape_errors_raised_before_any_device_work():
+    """NotThin / NotSquare / WrongRows mirror src/qr.rs:34-36, src/lib.rs:64-71, src/triangular.rs:103-108."""
+    import numpy as np
+    import linfa_linalg_b200 as L
+    with pytest.raises(L.NotThin):
+        L.qr_into(np.zeros((2, 3)), eng=object())
+    with pytest.raises(L.NotSquare):
+        L.cholesky_inplace(np.zeros((2, 3)), eng=object())
+    with pytest.raises(L.NotSquare):
+        L.sym_tridiagonal(np.zeros((2, 3)), eng=object())
+    with pytest.raises(L.EmptyMatrix):
+        L.sym_tridiagonal(np.zeros((0, 0)), eng=object())
+    with pytest.raises(L.EmptyMatrix):
+        L.bidiagonal(np.zeros((0, 0)), eng=object())
+    with pytest.raises(L.WrongRows):
+        L.solve_triangular_inplace(np.eye(2), np.zeros((1, 2)), L.UPPER, eng=object())

@@ -1,0 +1,395 @@
+"""GPU parity tests: the CUDA path (through the C ABI, host views of arbitrary strides) against the
+CPU oracle on the same seeded inputs, plus the reference's KATs and error behaviour.
+
+Tolerances: elementwise |X - X_oracle| <= c * n * eps * ||A||_F, backward error and
+orthogonality <= c * n * eps; exact: diag(R) >= 0, triangular zeros, off >= 0, error variants.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+EPS = {np.float64: 2.220446049250313e-16, np.float32: 1.1920929e-07}
+
+
+@pytest.fixture(scope="module")
+def L():
+    import linfa_linalg_b200 as L
+    L.engine()  # fails loudly when the CUDA library / device is missing
+    return L
+
+
+def tol(a, c=8.0, n=None):
+    dt = a.dtype.type
+    n = n or max(a.shape)
+    return c * n * EPS[dt] * max(np.linalg.norm(a), 1e-300)
+
+
+def layouts(a, square_t=True):
+    """The layouts tests/common.rs:12-43 randomises over, plus strided slices."""
+    out = [("c", np.array(a, order="C")), ("f", np.array(a, order="F"))]
+    out.append(("revrows", np.array(a[::-1], order="C")[::-1]))
+    out.append(("revcols", np.array(a[:, ::-1], order="C")[:, ::-1]))
+    big = np.zeros((2 * a.shape[0], 3 * a.shape[1]), dtype=a.dtype)
+    v = big[::2, ::3]
+    v[...] = a
+    out.append(("strided", v))
+    if square_t and a.shape[0] == a.shape[1]:
+        out.append(("t", np.array(a.T, order="C").T))
+    return out
+
+
+def rnd(shape, dt=np.float64, seed=0, lo=-100.0, hi=100.0):
+    return np.random.default_rng(seed).uniform(lo, hi, shape).astype(dt)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (37, 19, 53), (128, 128, 128), (130, 257, 65), (256, 64, 4100), (32, 32, 20000)])
+def test_gemm_f64(L, ta, tb, m, n, k):
+    import ctypes as C
+    import torch
+    e = L.engine()
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n * 3 + k)
+    A = torch.rand((k, m) if ta else (m, k), dtype=torch.float64, device="cuda", generator=g) - 0.5
+    B = torch.rand((n, k) if tb else (k, n), dtype=torch.float64, device="cuda", generator=g) - 0.5
+    Cm = torch.rand((m, n), dtype=torch.float64, device="cuda", generator=g)
+    # torch tensors are row-major: a row-major X (r x c) is a column-major X^T (c x r, ld = c).
+    # Column-major C (m x n) = op(A) op(B)  <=>  we hand the library transposed storage.
+    Acm = A.t().contiguous()  # storage of column-major A
+    Bcm = B.t().contiguous()
+    Ccm = Cm.t().contiguous()
+    ref = 1.5 * ((A.t() if ta else A) @ (B.t() if tb else B)) + 0.5 * Cm
+    torch.cuda.synchronize()
+    e.set_stream(torch.cuda.current_stream().cuda_stream)
+    st = e.call("lfb_gemm_dev_f64", ta, tb, m, n, k, 1.5, C.c_void_p(Acm.data_ptr()), A.shape[0],
+                C.c_void_p(Bcm.data_ptr()), B.shape[0], 0.5, C.c_void_p(Ccm.data_ptr()), m)
+    e._check(st)
+    torch.cuda.synchronize()
+    e.set_stream(None)
+    got = Ccm.t()
+    assert torch.allclose(got, ref, rtol=0, atol=1e-11 * k)
+
+
+def test_gemm_f32(L):
+    import ctypes as C
+    import torch
+    e = L.engine()
+    for (ta, tb, m, n, k) in [(0, 0, 70, 33, 129), (1, 0, 64, 64, 3000), (0, 1, 5, 200, 17), (1, 1, 100, 100, 100)]:
+        A = torch.rand((k, m) if ta else (m, k), dtype=torch.float32, device="cuda") - 0.5
+        B = torch.rand((n, k) if tb else (k, n), dtype=torch.float32, device="cuda") - 0.5
+        Ccm = torch.zeros((n, m), dtype=torch.float32, device="cuda")
+        ref = (A.t() if ta else A).double() @ (B.t() if tb else B).double()
+        torch.cuda.synchronize()
+        e.set_stream(torch.cuda.current_stream().cuda_stream)
+        st = e.call("lfb_gemm_dev_f32", ta, tb, m, n, k, 1.0, C.c_void_p(A.t().contiguous().data_ptr()), A.shape[0],
+                    C.c_void_p(B.t().contiguous().data_ptr()), B.shape[0], 0.0, C.c_void_p(Ccm.data_ptr()), m)
+        e._check(st)
+        torch.cuda.synchronize()
+        e.set_stream(None)
+        assert torch.allclose(Ccm.t().double(), ref, rtol=0, atol=2e-6 * k)
+
+
+# ---- QR ---------------------------------------------------------------------------------------
+def test_qr_kats(L):  # src/qr.rs:257-276
+    a = np.array([[3.2, 1.3], [4.4, 5.2], [1.3, 6.7]])
+    q, r = L.qr(a).into_decomp()
+    np.testing.assert_allclose(q, [[0.5720674, -0.4115578], [0.7865927, 0.0301901], [0.2324024, 0.9108835]], atol=1e-5)
+    np.testing.assert_allclose(r, [[5.594, 6.391], [0.0, 5.725]], atol=1e-3)
+    q, r = L.qr(np.zeros((2, 2))).into_decomp()
+    np.testing.assert_array_equal(q, np.eye(2))
+    np.testing.assert_array_equal(r, np.zeros((2, 2)))
+    q, r = L.qr_into(np.zeros((0, 0))).into_decomp()  # qr.rs:383-388
+    assert q.size == 0 and r.size == 0
+    with pytest.raises(L.NotThin):
+        L.qr_into(np.zeros((2, 3)))
+    with pytest.raises(L.NotSquare):
+        L.qr_into(np.zeros((3, 2))).inverse()
+
+
+SHAPES = [(1, 1), (2, 2), (3, 2), (10, 10), (10, 3), (33, 17), (64, 64), (100, 37), (129, 128), (200, 200), (300, 131),
+          (513, 260), (640, 512)]
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_qr_parity(L, shape, dt):
+    a0 = rnd(shape, dt, seed=shape[0] * 1000 + shape[1])
+    ref = a0.copy()
+    dref = O.qr(ref)
+    for name, a in layouts(a0):
+        dec = L.qr_into(a)
+        t = tol(a0, c=16)
+        assert np.max(np.abs(a - ref)) <= t, (name, np.max(np.abs(a - ref)), t)
+        assert np.max(np.abs(dec.diag - dref)) <= t, name
+    dec = L.qr(a0)
+    q, r = dec.into_decomp()
+    n = shape[1]
+    assert np.all(np.diag(r) >= 0) and np.all(np.tril(r, -1) == 0)
+    e = EPS[dt]
+    assert np.linalg.norm(q.T.astype(np.float64) @ q - np.eye(n)) <= 16 * max(shape) * e
+    assert np.linalg.norm(q.astype(np.float64) @ r - a0) <= 16 * max(shape) * e * np.linalg.norm(a0)
+    qo = O.generate_q(ref, dref)
+    assert np.max(np.abs(q - qo)) <= 64 * max(shape) * e
+
+
+def test_qr_edge_cases(L):
+    # zero column in the middle -> None reflection, diag 0
+    a0 = rnd((40, 20), seed=5)
+    a0[:, 7] = 0.0
+    a0[:, 0] = 0.0
+    ref = a0.copy(); dref = O.qr(ref)
+    a = a0.copy(); dec = L.qr_into(a)
+    assert dec.diag[0] == 0.0 and dref[0] == 0.0
+    assert np.max(np.abs(a - ref)) <= tol(a0, 16) and np.max(np.abs(dec.diag - dref)) <= tol(a0, 16)
+    assert not dec.is_invertible()
+    # negative zero / negative pivots and a square matrix (length-1 last reflector)
+    a0 = -np.abs(rnd((50, 50), seed=6))
+    ref = a0.copy(); dref = O.qr(ref)
+    a = a0.copy(); dec = L.qr_into(a)
+    assert np.max(np.abs(a - ref)) <= tol(a0, 16)
+    assert np.array_equal(np.sign(dec.diag), np.sign(dref))
+    # tiny entries (tests/qr.rs:55-75)
+    inv = L.qr_into(np.eye(5) * 1e-20).inverse()
+    np.testing.assert_allclose(inv, np.eye(5) * 1e20, atol=1e-3)
+
+
+@pytest.mark.parametrize("shape,k", [((2, 2), 3), ((3, 2), 3), ((60, 60), 7), ((200, 150), 33), ((300, 300), 300)])
+def test_qr_solve_qtmul_inverse(L, shape, k):
+    a0 = rnd(shape, seed=11)
+    x = rnd((shape[1], k), seed=12)
+    b = a0 @ x
+    dec = L.qr(a0)
+    bb = b.copy(); dec.qt_mul(bb)
+    ref = a0.copy(); dref = O.qr(ref); bo = b.copy(); O.qt_mul(ref, dref, bo)
+    assert np.max(np.abs(bb - bo)) <= tol(b, 32)
+    sol = dec.solve(b)
+    assert np.max(np.abs(sol - x)) <= 1e-7 * np.max(np.abs(x)) * max(shape)
+    if shape[0] == shape[1]:
+        inv = dec.inverse()
+        assert np.max(np.abs(a0 @ inv - np.eye(shape[0]))) <= 1e-7
+    # wide least squares (qr.rs:220-227)
+    aw = rnd((shape[1], shape[0]), seed=13)
+    if aw.shape[0] < aw.shape[1]:
+        xw = rnd((aw.shape[1], 2), seed=14)
+        bw = aw @ xw
+        sw = L.least_squares(aw.copy(), bw)
+        assert np.max(np.abs(aw @ sw - bw)) <= 1e-7 * np.max(np.abs(bw)) * max(shape)
+
+
+def test_qr_errors(L):  # src/qr.rs:338-361
+    with pytest.raises(L.NonInvertible):
+        L.qr(np.zeros((2, 2))).inverse()
+    with pytest.raises(L.NonInvertible):
+        L.least_squares_into(np.zeros((2, 2)), np.zeros((2, 2)))
+    with pytest.raises(L.NonInvertible):
+        L.least_squares_into(np.zeros((2, 3)), np.zeros((2, 2)))
+    with pytest.raises(L.WrongRows):
+        L.qr(np.eye(3)).solve(np.zeros((2, 2)))
+
+
+# ---- Cholesky -----------------------------------------------------------------------------------
+def spd(n, dt=np.float64, seed=0):  # tests/cholesky.rs:9-19
+    g = rnd((n, n), np.float64, seed)
+    return (g.T @ g + np.eye(n)).astype(dt)
+
+
+def test_cholesky_kats(L):  # src/cholesky.rs:209-245, tests/cholesky.rs:87-95
+    for dt in (np.float64, np.float32):
+        arr = np.array([[25.0, 15, -5], [15, 18, 0], [-5, 0, 11]], dtype=dt)
+        ch = L.cholesky(arr)
+        np.testing.assert_allclose(ch, [[5.0, 0, 0], [3, 3, 0], [-1, 1, 3]], atol=1e-6)
+    with pytest.raises(L.NotSquare):
+        L.cholesky(np.array([[1.0, 2, 3], [3, 4, 5]]))
+    with pytest.raises(L.NotPositiveDefinite):
+        L.cholesky(np.array([[1.0, 2], [2, 1]]))
+    with pytest.raises(L.NotPositiveDefinite):
+        L.cholesky(np.zeros((2, 2)))
+    assert L.cholesky(np.zeros((0, 0))).shape == (0, 0)
+    assert L.cholesky(np.ones((1, 1)))[0, 0] == 1.0
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 63, 64, 65, 100, 128, 129, 200, 300, 515, 1030])
+def test_cholesky_parity(L, n, dt):
+    a0 = spd(n, dt, seed=n) if dt == np.float64 else (spd(n, np.float64, seed=n) / 1e4 + np.eye(n)).astype(dt)
+    ref = a0.copy(); st, _ = O.cholesky(ref, clean=True)
+    assert st == 0
+    t = tol(a0, 8) if dt == np.float64 else tol(a0, 64)
+    for name, a in layouts(a0):
+        got = L.cholesky_inplace(a)
+        assert np.max(np.abs(got - ref)) <= t, (name, np.max(np.abs(got - ref)), t)
+        assert np.all(np.triu(np.asarray(got), 1) == 0)
+    d = a0.copy(); L.cholesky_inplace_dirty(d)
+    np.testing.assert_array_equal(np.triu(d, 1), np.triu(a0, 1))   # upper untouched (cholesky.rs:17-19)
+    assert np.max(np.abs(np.tril(d) - ref)) <= t
+    l64 = np.tril(d).astype(np.float64)
+    assert np.linalg.norm(l64 @ l64.T - a0) <= 8 * n * EPS[dt] * np.linalg.norm(a0) * (1 if dt == np.float64 else 8)
+
+
+@pytest.mark.parametrize("n,bad", [(5, 3), (70, 0), (130, 64), (200, 199), (300, 150)])
+def test_cholesky_not_positive_definite(L, n, bad):
+    a = spd(n, seed=n + 1)
+    a[bad, bad] = -1.0
+    ref = a.copy(); st, fi = O.cholesky(ref)
+    assert st == 1
+    with pytest.raises(L.NotPositiveDefinite) as ei:
+        L.cholesky_inplace(a.copy())
+    assert ei.value.index == fi == bad
+
+
+@pytest.mark.parametrize("n,k", [(3, 4), (64, 5), (150, 150), (260, 31)])
+def test_solvec_invc(L, n, k):
+    a = spd(n, seed=3 * n)
+    x = rnd((n, k), seed=n + 5)
+    b = a @ x
+    out = L.solvec(a.copy(), b)
+    assert np.max(np.abs(out - x)) <= 1e-5 * max(1.0, np.max(np.abs(x)))      # tests/cholesky.rs:56-62
+    ao = a.copy(); bo = b.copy()
+    O.cholesky(ao, clean=False); O.solve_triangular(ao, bo, O.LOWER); O.solve_triangular(ao.T, bo, O.UPPER)
+    assert np.max(np.abs(out - bo)) <= 1e-6 * max(1.0, np.max(np.abs(x)))
+    if n <= 150:
+        a2 = (a / np.linalg.norm(a)) + np.eye(n)
+        inv = L.invc(a2)
+        assert np.max(np.abs(a2 @ inv - np.eye(n))) <= 1e-7                    # tests/cholesky.rs:64-67
+
+
+# ---- triangular ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("uplo", [0, 1])
+@pytest.mark.parametrize("n,k", [(1, 1), (2, 3), (9, 10), (64, 64), (65, 7), (130, 200), (300, 129), (520, 3)])
+def test_solve_triangular_parity(L, uplo, n, k):
+    a0 = rnd((n, n), seed=n * 31 + uplo)
+    d = np.diag(a0).copy(); d[np.abs(d) < 1.0] = 1.0                           # tests/triangular.rs:9-21
+    a0[np.arange(n), np.arange(n)] = d * 10
+    tri = np.triu(a0) if uplo == L.UPPER else np.tril(a0)
+    x = rnd((n, k), seed=n + k)
+    b0 = tri @ x
+    bo = b0.copy(); O.solve_triangular(a0, bo, uplo)                            # reads only the triangle
+    scale = np.max(np.abs(bo)) + 1.0
+    for (na, a) in layouts(a0):
+        for (nb, b) in layouts(b0, square_t=False)[:3]:
+            got = L.solve_triangular_inplace(a, b, uplo)
+            assert np.max(np.abs(got - bo)) <= 1e-9 * scale * n, (na, nb)
+    ext = np.abs(d) + 3.0
+    bo = b0.copy(); O.solve_triangular(a0, bo, uplo, ext_diag=ext)
+    import linfa_linalg_b200 as LL
+    got = LL._solve_tri(L.engine(), a0, b0.copy(), uplo, ext)
+    assert np.max(np.abs(got - bo)) <= 1e-9 * (np.max(np.abs(bo)) + 1) * n
+
+
+def test_triangular_kats(L):  # src/triangular.rs:233-299, tests/triangular.rs:49-180
+    from golden_vectors import TRI_KNOWN_A, TRI_KNOWN_X
+    a, x = np.array(TRI_KNOWN_A), np.array(TRI_KNOWN_X)
+    out = L.solve_triangular(a, a @ x, L.UPPER)
+    np.testing.assert_allclose(out, x, atol=1e-4)
+    with np.errstate(all="ignore"):
+        L.solve_triangular(np.array([[0.0, 3], [2, 0]]), np.zeros((2, 2)), L.LOWER)   # zero diagonal: no crash
+    assert L.solve_triangular(np.zeros((0, 0)), np.zeros((0, 0)), L.UPPER).shape == (0, 0)
+    with pytest.raises(L.NotSquare):
+        L.solve_triangular(np.array([[1.2, 3.3]]), np.array([[1.2, 3.3]]), L.LOWER)
+    with pytest.raises(L.WrongRows):
+        L.solve_triangular(np.array([[1.1, 2.2], [3.3, 2.1]]), np.array([[2.2, 3.3]]), L.UPPER)
+    sq = np.array([[1.0, 2, 3], [4, 5, 6], [7, 8, 9]])
+    np.testing.assert_array_equal(L.into_triangular(sq.copy(), L.UPPER), [[1, 2, 3], [0, 5, 6], [0, 0, 9]])
+    np.testing.assert_array_equal(L.into_triangular(sq.copy(), L.LOWER), [[1, 0, 0], [4, 5, 0], [7, 8, 9]])
+
+
+# ---- tridiagonal ---------------------------------------------------------------------------------
+def test_tridiagonal_kat(L):  # src/tridiagonal.rs:124-152
+    arr = np.array([[4.0, 1, -2, 2], [1, 2, 0, 1], [-2, 0, 3, -2], [2, 1, -2, -1]])
+    dec = L.sym_tridiagonal(arr.copy())
+    diag, off = dec.into_diagonals()
+    np.testing.assert_allclose(diag, [4, 10 / 3, -33 / 25, 149 / 75], atol=1e-5)
+    np.testing.assert_allclose(off, [3, 5 / 3, 68 / 75], atol=1e-5)
+    dec = L.sym_tridiagonal(arr.copy())
+    q = dec.generate_q(); tri = dec.into_tridiag_matrix()
+    np.testing.assert_allclose(q @ tri @ q.T, arr, atol=1e-9)
+    np.testing.assert_allclose(q @ q.T, np.eye(4), atol=1e-9)
+    one = L.sym_tridiagonal(np.array([[1.1]]))
+    d, o = one.into_diagonals()
+    assert d[0] == 1.1 and o.size == 0
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [2, 3, 10, 33, 100, 257])
+def test_tridiagonal_parity(L, n, dt):
+    g = rnd((n, n), np.float64, seed=n, lo=-1, hi=1)
+    a0 = ((g + g.T) / 2).astype(dt)
+    ref = a0.copy(); offr = O.sym_tridiagonal(ref)
+    c = 64
+    for name, a in layouts(a0)[:4]:
+        dec = L.sym_tridiagonal(a)
+        assert np.max(np.abs(np.tril(a) - np.tril(ref))) <= tol(a0, c), name   # diag + reflectors (lower part)
+        assert np.max(np.abs(dec.off_diagonal - offr)) <= tol(a0, c), name
+    dec = L.sym_tridiagonal(a0.copy())
+    q = dec.generate_q().astype(np.float64); t = dec.into_tridiag_matrix().astype(np.float64)
+    assert np.all(np.abs(np.triu(t, 2)) == 0) and np.all(np.abs(np.tril(t, -2)) == 0)
+    assert np.linalg.norm(q @ t @ q.T - a0) <= c * n * EPS[dt] * np.linalg.norm(a0)
+    assert np.linalg.norm(q @ q.T - np.eye(n)) <= c * n * EPS[dt]
+    L.sym_tridiagonal(rnd((n, n), dt, seed=1)).generate_q()                    # non-symmetric must not crash
+
+
+# ---- bidiagonal ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(1, 1), (3, 4), (4, 3), (10, 10), (1, 7), (7, 1), (40, 23), (23, 40), (130, 70), (64, 200)])
+def test_bidiagonal_parity(L, shape, dt):
+    a0 = rnd(shape, dt, seed=shape[0] * 100 + shape[1], lo=-1, hi=1)
+    ref = a0.copy(); dr, er = O.bidiagonal(ref)
+    c = 64
+    for name, a in layouts(a0)[:4]:
+        dec = L.bidiagonal(a)
+        assert np.max(np.abs(a - ref)) <= tol(a0, c), name
+        assert np.max(np.abs(dec.diagonal - dr)) <= tol(a0, c), name
+        if er.size:
+            assert np.max(np.abs(dec.off_diagonal - er)) <= tol(a0, c), name
+    dec = L.bidiagonal(a0.copy())
+    u = dec.generate_u().astype(np.float64); vt = dec.generate_vt().astype(np.float64); b = dec.into_b().astype(np.float64)
+    md = min(shape)
+    assert u.shape == (shape[0], md) and vt.shape == (md, shape[1]) and b.shape == (md, md)
+    e = EPS[dt] * c * max(shape)
+    assert np.linalg.norm((u.T @ u if shape[0] >= shape[1] else u @ u.T) - np.eye(md)) <= e
+    assert np.linalg.norm(vt @ vt.T - np.eye(md)) <= e
+    assert np.linalg.norm(u @ b @ vt - a0) <= e * np.linalg.norm(a0)
+    assert np.all(b >= 0)
+
+
+# ---- batched -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("batch,m,n", [(1, 32, 32), (1000, 32, 32), (77, 16, 5), (300, 8, 8), (5, 32, 1), (64, 20, 20)])
+def test_qr_batched_parity(L, batch, m, n, dt):
+    a0 = rnd((batch, m, n), dt, seed=batch + m + n, lo=-1, hi=1)
+    if batch > 3:
+        a0[1, :, 0] = 0          # a None column
+        a0[2] = 0                # an all-zero matrix
+    ref = a0.copy(); dref = O.qr_batched(ref)
+    a = a0.copy(); d = L.qr_batched(a)
+    t = 16 * m * EPS[dt] * np.sqrt(m)
+    assert np.max(np.abs(a - ref)) <= t
+    assert np.max(np.abs(d - dref)) <= t
+    assert np.array_equal(d == 0, dref == 0)
+
+
+# ---- mid-size properties (no oracle: size-independent checks) -------------------------------------
+def test_qr_2048_properties(L):
+    m, n = 2304, 2048
+    a0 = rnd((m, n), seed=99, lo=-1, hi=1)
+    dec = L.qr(a0)
+    q, r = dec.into_decomp()
+    assert np.all(np.diag(r) >= 0)
+    assert np.linalg.norm(q.T @ q - np.eye(n)) <= 8 * m * EPS[np.float64]
+    assert np.linalg.norm(q @ r - a0) <= 8 * m * EPS[np.float64] * np.linalg.norm(a0)
+    import scipy.linalg as sl
+    rl = sl.qr(a0, mode="r")[0][:n]
+    rl = rl * np.sign(np.diag(rl))[:, None]      # LAPACK R with the reference's diag >= 0 convention
+    assert np.max(np.abs(r - rl)) <= 8 * m * EPS[np.float64] * np.linalg.norm(a0, 2)
+
+
+def test_cholesky_4096_properties(L):
+    n = 4096
+    g = rnd((n, n), seed=7, lo=-1, hi=1)
+    a0 = (g + g.T) / 2 + n * np.eye(n)
+    l = L.cholesky(a0)
+    assert np.linalg.norm(l @ l.T - a0) <= 8 * n * EPS[np.float64] * np.linalg.norm(a0)
+    assert np.max(np.abs(l - np.linalg.cholesky(a0))) <= 8 * n * EPS[np.float64] * np.linalg.norm(a0, 2)
