@@ -58,8 +58,10 @@ int lfb_create(lfb_handle **out, int device);
 int lfb_destroy(lfb_handle *h);
 /* Message of the last failure on this handle ("" if none).  Valid until the next call. */
 const char *lfb_last_error(lfb_handle *h);
-/* Run subsequent calls on a caller-owned cudaStream_t (NULL restores the handle's own stream). */
+/* Run subsequent calls on a caller-owned cudaStream_t, taken verbatim (NULL = the legacy default
+ * stream); lfb_use_own_stream restores the handle's own non-blocking stream. */
 int lfb_set_stream(lfb_handle *h, void *cuda_stream);
+int lfb_use_own_stream(lfb_handle *h);
 int lfb_synchronize(lfb_handle *h);
 /* Version / build string, and the number of kernels this handle has launched so far. */
 const char *lfb_version(void);

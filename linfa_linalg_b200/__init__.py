@@ -119,7 +119,11 @@ class Engine:
             raise ValueError(f"unknown option {key}")
 
     def set_stream(self, cuda_stream: int | None):
-        self.lib.lfb_set_stream(self.h, C.c_void_p(cuda_stream or 0))
+        """cuda_stream: a cudaStream_t handle as int (0 = legacy default stream); None = the engine's own stream."""
+        if cuda_stream is None:
+            self.lib.lfb_use_own_stream(self.h)
+        else:
+            self.lib.lfb_set_stream(self.h, C.c_void_p(int(cuda_stream)))
 
     def synchronize(self):
         self._check(self.lib.lfb_synchronize(self.h))

@@ -25,6 +25,7 @@ SIGNATURES = {
     "lfb_destroy": [_vp],
     "lfb_last_error": [_vp],
     "lfb_set_stream": [_vp, _vp],
+    "lfb_use_own_stream": [_vp],
     "lfb_synchronize": [_vp],
     "lfb_version": [],
     "lfb_launch_count": [_vp],

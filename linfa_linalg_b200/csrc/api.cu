@@ -299,7 +299,13 @@ const char *lfb_last_error(lfb_handle *h) { return h ? h->err.c_str() : "null ha
 
 int lfb_set_stream(lfb_handle *h, void *s) {
     if (!h) return LFB_INVALID_ARGUMENT;
-    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    h->stream = (cudaStream_t)s;   // verbatim: NULL is the legacy default stream
+    return LFB_OK;
+}
+
+int lfb_use_own_stream(lfb_handle *h) {
+    if (!h) return LFB_INVALID_ARGUMENT;
+    h->stream = h->own_stream;
     return LFB_OK;
 }
 

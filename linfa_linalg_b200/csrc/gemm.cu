@@ -207,8 +207,8 @@ struct SgemmP {
 
 __global__ void __launch_bounds__(256) sgemm_kernel(SgemmP p) {
     constexpr int TM = 64, TN = 64, TK = 16;
-    __shared__ float sA[TK][TM + 4];
-    __shared__ float sB[TK][TN + 4];
+    __shared__ __align__(16) float sA[TK][TM + 4];
+    __shared__ __align__(16) float sB[TK][TN + 4];
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
     if (p.lower_only && m0 + TM <= n0) return;

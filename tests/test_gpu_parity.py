@@ -84,8 +84,9 @@ def test_gemm_f32(L):
         ref = (A.t() if ta else A).double() @ (B.t() if tb else B).double()
         torch.cuda.synchronize()
         e.set_stream(torch.cuda.current_stream().cuda_stream)
-        st = e.call("lfb_gemm_dev_f32", ta, tb, m, n, k, 1.0, C.c_void_p(A.t().contiguous().data_ptr()), A.shape[0],
-                    C.c_void_p(B.t().contiguous().data_ptr()), B.shape[0], 0.0, C.c_void_p(Ccm.data_ptr()), m)
+        Acm, Bcm = A.t().contiguous(), B.t().contiguous()   # keep alive: column-major storage of A, B
+        st = e.call("lfb_gemm_dev_f32", ta, tb, m, n, k, 1.0, C.c_void_p(Acm.data_ptr()), A.shape[0],
+                    C.c_void_p(Bcm.data_ptr()), B.shape[0], 0.0, C.c_void_p(Ccm.data_ptr()), m)
         e._check(st)
         torch.cuda.synchronize()
         e.set_stream(None)
@@ -262,7 +263,9 @@ def test_solvec_invc(L, n, k):
 def test_solve_triangular_parity(L, uplo, n, k):
     a0 = rnd((n, n), seed=n * 31 + uplo)
     d = np.diag(a0).copy(); d[np.abs(d) < 1.0] = 1.0                           # tests/triangular.rs:9-21
-    a0[np.arange(n), np.arange(n)] = d * 10
+    # keep the system well conditioned at n >> 10 (random triangular systems are exponentially
+    # ill-conditioned): diagonally dominant rows
+    a0[np.arange(n), np.arange(n)] = np.sign(d) * (np.abs(d) + 60.0 * n)
     tri = np.triu(a0) if uplo == L.UPPER else np.tril(a0)
     x = rnd((n, k), seed=n + k)
     b0 = tri @ x
