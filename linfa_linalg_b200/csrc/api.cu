@@ -323,8 +323,10 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     if (k == "qr_nb") h->opt.qr_nb = value;
     else if (k == "qr_sub") h->opt.qr_sub = value;
     else if (k == "chol_base") h->opt.chol_base = value;
+    else if (k == "chol_nb") h->opt.chol_nb = value;
     else if (k == "gemm_tma") h->opt.gemm_tma = value;
     else if (k == "gemm_splitk") h->opt.gemm_splitk = value;
+    else if (k == "gemm_v2") h->opt.gemm_v2 = value;
     else if (k == "panel_cluster") h->opt.panel_cluster = value;
     else return LFB_INVALID_ARGUMENT;
     return LFB_OK;

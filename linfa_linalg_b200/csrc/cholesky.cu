@@ -1,11 +1,14 @@
-// Recursive blocked Cholesky (lower, column-major) and triangular solves.
+// Blocked Cholesky (lower, column-major) and triangular solves.
 //
 // Replaces src/cholesky.rs:51-83 (cholesky_inplace_dirty / cholesky_inplace) and
 // src/triangular.rs:95-144 (solve_triangular_system).  The reference's row-by-row triple loop is
-// restructured as  potrf(A) = { potrf(A11); A21 <- A21 L11^-T; A22 -= A21 A21^T (lower); potrf(A22) }
-// so that almost all flops are large-K tensor-core GEMMs; only <=64x64 diagonal blocks run in a
-// single CTA.  Only the lower triangle is read or written (the `dirty` contract, cholesky.rs:17-19).
-// A row-major ndarray lower factor is the transpose of this layout; api.cu handles that.
+// restructured right-looking with panels of `chol_nb` columns:
+//     L_kk = potrf(A_kk)  (recursive down to 64x64 single-CTA blocks)
+//     P    = A[k+nb:, k:k+nb] L_kk^-T          (recursive TRSM: 64-wide substitutions + GEMM)
+//     A22 -= P P^T  (lower triangle only)       (one large-K tensor-core GEMM per panel)
+// so that ~95 % of the flops are DMMA GEMMs with K = chol_nb.  Only the lower triangle is read or
+// written (the `dirty` contract, cholesky.rs:17-19).  A row-major ndarray lower factor is the
+// transpose of this layout; api.cu handles that.
 #include "common.cuh"
 
 namespace lfb {
@@ -17,63 +20,70 @@ template <typename T> __device__ __forceinline__ T t_sqrt(T x);
 template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
 template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
 
-// Unblocked right-looking Cholesky of an n x n (n <= 64) lower block held in shared memory.
+// Unblocked right-looking Cholesky of an n x n (n <= 64) lower block: two warps, thread r keeps
+// row r in registers, column j is broadcast through shared memory.
 // info[0]: 0 = ok so far, else (failing global row + 1).  cholesky.rs:69-71: pivot <= 0 fails,
-// NaN pivots are NOT reported.
+// NaN pivots are NOT reported.  On failure the block is written back partially factored.
 template <typename T>
-__global__ void __launch_bounds__(256) potf2_kernel(T *A, int64_t ld, int n, int64_t row0, int64_t *info) {
-    __shared__ T s[CB][CB + 1];
-    __shared__ int failed;
+__global__ void __launch_bounds__(64) potf2_kernel(T *A, int64_t ld, int n, int64_t row0, int64_t *info) {
+    __shared__ T col[CB];
+    __shared__ T sdj;
+    __shared__ int sfail;
     if (*info != 0) return;
-    const int tid = threadIdx.x;
-    for (int e = tid; e < n * n; e += blockDim.x) {
-        int i = e % n, j = e / n;
-        if (i >= j) s[i][j] = A[i + (int64_t)j * ld];
-    }
-    if (tid == 0) failed = -1;
+    const int r = threadIdx.x;
+    T a[CB];
+#pragma unroll
+    for (int k = 0; k < CB; ++k) a[k] = (r < n && k <= r) ? A[r + (int64_t)k * ld] : T(0);
+    if (r == 0) sfail = 0;
     __syncthreads();
-    int ncols_done = n;
-    for (int j = 0; j < n; ++j) {
-        T d = s[j][j];
-        if (d <= T(0)) {  // uniform: every thread reads the same value
-            if (tid == 0) { failed = j; *info = row0 + j + 1; }
-            ncols_done = j;
-            break;
+#pragma unroll
+    for (int j = 0; j < CB; ++j) {
+        if (j < n) {
+            if (r == j) {
+                T d = a[j];
+                if (d <= T(0)) {
+                    sfail = j + 1;
+                } else {
+                    T dj = t_sqrt(d);
+                    a[j] = dj;
+                    sdj = dj;
+                }
+            }
+            __syncthreads();
+            if (sfail) break;
+            T l = T(0);
+            if (r > j) {
+                l = a[j] / sdj;
+                a[j] = l;
+                col[r] = l;
+            }
+            __syncthreads();
+            if (r > j) {
+#pragma unroll
+                for (int k = j + 1; k < CB; ++k)
+                    if (k <= r) a[k] -= l * col[k];
+            }
         }
-        T dj = t_sqrt(d);
-        __syncthreads();
-        if (tid == 0) s[j][j] = dj;
-        for (int i = j + 1 + tid; i < n; i += blockDim.x) s[i][j] /= dj;
-        __syncthreads();
-        // trailing lower update: s[i][k] -= s[i][j] * s[k][j], j < k <= i
-        const int rem = n - j - 1;
-        for (int e = tid; e < rem * rem; e += blockDim.x) {
-            int i = j + 1 + e % rem, k = j + 1 + e / rem;
-            if (i >= k) s[i][k] -= s[i][j] * s[k][j];
-        }
-        __syncthreads();
     }
-    __syncthreads();
-    // write back the factored columns (and the partially updated rest, like the reference leaves it)
-    (void)ncols_done;
-    for (int e = tid; e < n * n; e += blockDim.x) {
-        int i = e % n, j = e / n;
-        if (i >= j) A[i + (int64_t)j * ld] = s[i][j];
-    }
+    if (r == 0 && sfail) *info = row0 + sfail;
+#pragma unroll
+    for (int k = 0; k < CB; ++k)
+        if (r < n && k <= r) A[r + (int64_t)k * ld] = a[k];
 }
 
-// Base triangular solve for NV independent vectors against an nb x nb (nb <= 64) coefficient
-// matrix: for j in order: x_j = (b_j - sum_{i solved} x_i * M(j,i)) / D(j).
+// Base triangular solve for independent vectors against an nb x nb (nb <= 64) coefficient matrix,
+// one vector per thread, right-looking (axpy) form so that the 63-k updates after each unknown are
+// independent FMAs:   x_k = acc_k / M(k,k);  acc_i -= M(i,k) x_k  for the unsolved equations i.
 //   M(j,i) = tri[j*sj + i*si]   (caller encodes lower/upper and transposition in the strides)
-//   vector element j of vector v lives at B[v*sv + j*sb]
-//   FORWARD: j ascending, uses i < j ; else j descending, uses i > j.
+//   element j of vector v lives at B[v*sv + j*sb]
+//   FORWARD: k ascending (uses i > k) ; else k descending (uses i < k).
 template <typename T, bool FORWARD>
 __global__ void __launch_bounds__(128) trsv_block_kernel(const T *__restrict__ tri, int64_t sj, int64_t si, int nb,
                                                          const T *__restrict__ ext_diag, T *B, int64_t sv, int64_t sb,
                                                          int64_t nvec, const int64_t *info) {
-    extern __shared__ unsigned char smem_raw[];
-    T *sM = reinterpret_cast<T *>(smem_raw);  // [CB][CB+1]
-    T *sB = sM + CB * (CB + 1);               // [CB][129]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sMT = reinterpret_cast<T *>(smem_raw);  // [CB][CB]: sMT[k*CB + i] = M(i,k)
+    T *sB = sMT + CB * CB;                     // [CB][129]
     constexpr int LDB = 129;
     if (info && *info != 0) return;
     const int tid = threadIdx.x;
@@ -81,7 +91,7 @@ __global__ void __launch_bounds__(128) trsv_block_kernel(const T *__restrict__ t
     const int64_t nleft = nvec - v0;
     const int nv = nleft < 128 ? (int)nleft : 128;
     for (int e = tid; e < CB * CB; e += 128) {
-        int j, i;
+        int j, i;  // equation j, unknown i
         if (si == 1) { i = e % CB; j = e / CB; } else { j = e % CB; i = e / CB; }
         T val = (i == j) ? T(1) : T(0);
         if (i < nb && j < nb) {
@@ -90,9 +100,8 @@ __global__ void __launch_bounds__(128) trsv_block_kernel(const T *__restrict__ t
             else if (i == j) val = ext_diag ? ext_diag[j] : tri[j * sj + i * si];
             else val = T(0);
         }
-        sM[j * (CB + 1) + i] = val;
+        sMT[i * CB + j] = val;
     }
-    // load B tile -> sB[j][v]
     for (int e = tid; e < CB * 128; e += 128) {
         int j, v;
         if (sb == 1) { j = e % CB; v = e / CB; } else { v = e % 128; j = e / 128; }
@@ -102,26 +111,28 @@ __global__ void __launch_bounds__(128) trsv_block_kernel(const T *__restrict__ t
     }
     __syncthreads();
     if (tid < nv) {
-        T x[CB];
+        T acc[CB];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) acc[j] = sB[j * LDB + tid];
         if (FORWARD) {
 #pragma unroll
-            for (int j = 0; j < CB; ++j) {
-                T acc = sB[j * LDB + tid];
+            for (int k = 0; k < CB; ++k) {
+                const T x = acc[k] / sMT[k * CB + k];
+                acc[k] = x;
 #pragma unroll
-                for (int i = 0; i < j; ++i) acc -= x[i] * sM[j * (CB + 1) + i];
-                x[j] = acc / sM[j * (CB + 1) + j];
+                for (int i = k + 1; i < CB; ++i) acc[i] -= sMT[k * CB + i] * x;
             }
         } else {
 #pragma unroll
-            for (int j = CB - 1; j >= 0; --j) {
-                T acc = sB[j * LDB + tid];
+            for (int k = CB - 1; k >= 0; --k) {
+                const T x = acc[k] / sMT[k * CB + k];
+                acc[k] = x;
 #pragma unroll
-                for (int i = CB - 1; i > j; --i) acc -= x[i] * sM[j * (CB + 1) + i];
-                x[j] = acc / sM[j * (CB + 1) + j];
+                for (int i = 0; i < k; ++i) acc[i] -= sMT[k * CB + i] * x;
             }
         }
 #pragma unroll
-        for (int j = 0; j < CB; ++j) sB[j * LDB + tid] = x[j];
+        for (int j = 0; j < CB; ++j) sB[j * LDB + tid] = acc[j];
     }
     __syncthreads();
     for (int e = tid; e < CB * 128; e += 128) {
@@ -135,7 +146,7 @@ template <typename T>
 void trsv_block(lfb_handle &h, bool forward, const T *tri, int64_t sj, int64_t si, int nb, const T *ext_diag, T *B,
                 int64_t sv, int64_t sb, int64_t nvec, const int64_t *info) {
     if (nvec <= 0 || nb <= 0) return;
-    size_t smem = sizeof(T) * (CB * (CB + 1) + CB * 129);
+    size_t smem = sizeof(T) * (CB * CB + CB * 129);
     static bool cfg = false;
     if (!cfg) {
         LFB_CUDA(cudaFuncSetAttribute(trsv_block_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -165,8 +176,7 @@ void trsm_right_lt(lfb_handle &h, int64_t rows, int64_t n, const T *L, int64_t l
     }
     int64_t n1 = split_point(n), n2 = n - n1;
     trsm_right_lt<T>(h, rows, n1, L, ldl, B, ldb, info);
-    // B2 -= X1 L21^T
-    gemm<T>(h, 0, 1, rows, n2, n1, T(-1), B, ldb, L + n1, ldl, T(1), B + n1 * ldb, ldb);
+    gemm<T>(h, 0, 1, rows, n2, n1, T(-1), B, ldb, L + n1, ldl, T(1), B + n1 * ldb, ldb);   // B2 -= X1 L21^T
     trsm_right_lt<T>(h, rows, n2, L + n1 + n1 * ldl, ldl, B + n1 * ldb, ldb, info);
 }
 
@@ -174,7 +184,7 @@ template <typename T>
 void potrf_rec(lfb_handle &h, T *A, int64_t n, int64_t ld, int64_t row0, int64_t *info) {
     if (n <= 0) return;
     if (n <= CB) {
-        potf2_kernel<T><<<1, 256, 0, h.stream>>>(A, ld, (int)n, row0, info);
+        potf2_kernel<T><<<1, 64, 0, h.stream>>>(A, ld, (int)n, row0, info);
         LFB_LAUNCH_CHECK(h);
         return;
     }
@@ -191,7 +201,18 @@ template <typename T>
 void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64_t *d_info) {
     LFB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int64_t), h.stream));
     if (n <= 0) return;
-    potrf_rec<T>(h, A, n, ld, 0, d_info);
+    const int64_t NB = std::max<int64_t>(CB, round_up(h.opt.chol_nb, CB));
+    for (int64_t k0 = 0; k0 < n; k0 += NB) {
+        const int64_t nb = std::min<int64_t>(NB, n - k0);
+        T *Akk = A + k0 + k0 * ld;
+        potrf_rec<T>(h, Akk, nb, ld, k0, d_info);
+        const int64_t rows = n - k0 - nb;
+        if (rows > 0) {
+            T *P = Akk + nb;
+            trsm_right_lt<T>(h, rows, nb, Akk, ld, P, ld, d_info);
+            gemm<T>(h, 0, 1, rows, rows, nb, T(-1), P, ld, P, ld, T(1), A + (k0 + nb) + (k0 + nb) * ld, ld, /*lower_only=*/1);
+        }
+    }
     if (clean) triangular_zero<T>(h, A, n, ld, /*keep_lower=*/1);
 }
 

@@ -195,6 +195,164 @@ __global__ void __launch_bounds__(256) dgemm_kernel(GemmP p) {
     }
 }
 
+// ---- f64 v2: 16 warps (4 per scheduler), 4-stage cp.async pipeline -----------------------------
+// ncu on the 8-warp kernel above (profiles/r1_dgemm_v1.md): DMMA pipe 77 % active, top stalls "wait"
+// and short scoreboard with only 2 warps per scheduler.  This variant keeps the 128x128x16 CTA tile
+// but runs 16 warps (warp tile 32x32, <= 128 registers) and feeds shared memory with 16-byte
+// cp.async (zero-filled at the edges), one barrier per k-tile.  Needs 16-byte aligned operands.
+constexpr int V2_STAGES = 4;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+template <int AMODE, int BMODE>
+__global__ void __launch_bounds__(512, 1) dgemm_v2_kernel(GemmP p) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int A_LD = AMODE == 0 ? BM + 4 : BK + 4;
+    constexpr int A_SZ = AMODE == 0 ? BK * (BM + 4) : BM * (BK + 4);
+    constexpr int B_LD = BMODE == 0 ? BK + 4 : BN + 4;
+    constexpr int B_SZ = BMODE == 0 ? BN * (BK + 4) : BK * (BN + 4);
+    double *sA = smem;
+    double *sB = smem + V2_STAGES * A_SZ;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (p.lower_only && m0 + BM <= n0) return;
+    const int kbeg = blockIdx.z * p.ksplit;
+    const int kend = min(p.K, kbeg + p.ksplit);
+    if (kbeg >= kend) return;
+    const int KT = (kend - kbeg + BK - 1) / BK;
+
+    const double *__restrict__ A = static_cast<const double *>(p.A);
+    const double *__restrict__ B = static_cast<const double *>(p.B);
+
+    auto issue = [&](int kt, int slot) {
+        const int k0 = kbeg + kt * BK;
+        double *a = sA + slot * A_SZ, *b = sB + slot * B_SZ;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            {
+                int gm, gk, nval;
+                double *dst;
+                const double *src;
+                if (AMODE == 0) {
+                    int k = (tid >> 6) + 8 * i, m = 2 * (tid & 63);
+                    gm = m0 + m; gk = k0 + k;
+                    nval = gk < kend ? max(0, min(2, p.M - gm)) : 0;
+                    dst = a + k * A_LD + m;
+                    src = A + gm + (int64_t)gk * p.lda;
+                } else {
+                    int m = (tid >> 3) + 64 * i, k = 2 * (tid & 7);
+                    gm = m0 + m; gk = k0 + k;
+                    nval = gm < p.M ? max(0, min(2, kend - gk)) : 0;
+                    dst = a + m * A_LD + k;
+                    src = A + gk + (int64_t)gm * p.lda;
+                }
+                cp_async16(dst, nval ? src : A, nval * 8);
+            }
+            {
+                int gn, gk, nval;
+                double *dst;
+                const double *src;
+                if (BMODE == 0) {
+                    int n = (tid >> 3) + 64 * i, k = 2 * (tid & 7);
+                    gn = n0 + n; gk = k0 + k;
+                    nval = gn < p.N ? max(0, min(2, kend - gk)) : 0;
+                    dst = b + n * B_LD + k;
+                    src = B + gk + (int64_t)gn * p.ldb;
+                } else {
+                    int k = (tid >> 6) + 8 * i, n = 2 * (tid & 63);
+                    gn = n0 + n; gk = k0 + k;
+                    nval = gk < kend ? max(0, min(2, p.N - gn)) : 0;
+                    dst = b + k * B_LD + n;
+                    src = B + gn + (int64_t)gk * p.ldb;
+                }
+                cp_async16(dst, nval ? src : B, nval * 8);
+            }
+        }
+    };
+
+    const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;
+    double acc[4][4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i][0] = acc[j][i][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < V2_STAGES - 1; ++s) {
+        if (s < KT) issue(s, s);
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<V2_STAGES - 2>();   // k-tile kt has landed (for this thread's copies)
+        __syncthreads();                  // ... and for everyone's; slot (kt-1)%S is free again
+        {
+            const int nk = kt + V2_STAGES - 1;
+            if (nk < KT) issue(nk, nk % V2_STAGES);
+            cp_async_commit();
+        }
+        const int slot = kt % V2_STAGES;
+        const double *a = sA + slot * A_SZ, *b = sB + slot * B_SZ;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            double fa[4], fb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                fa[i] = AMODE == 0 ? a[(ks * 4 + tig) * A_LD + wm0 + 8 * i + gid]
+                                   : a[(wm0 + 8 * i + gid) * A_LD + ks * 4 + tig];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                fb[j] = BMODE == 0 ? b[(wn0 + 8 * j + gid) * B_LD + ks * 4 + tig]
+                                   : b[(ks * 4 + tig) * B_LD + wn0 + 8 * j + gid];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dmma884(acc[j][i][0], acc[j][i][1], fb[j], fa[i]);
+        }
+    }
+    cp_async_wait<0>();
+
+    double *__restrict__ C = static_cast<double *>(p.C);
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + wn0 + 8 * j + gid;
+        if (n >= p.N) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + wm0 + 8 * i + 2 * tig;
+            if (m >= p.M) continue;
+            double *c = C + m + (int64_t)n * p.ldc;
+            bool w0 = !p.lower_only || m >= n;
+            bool w1 = (m + 1 < p.M) && (!p.lower_only || m + 1 >= n);
+            double v0 = alpha * acc[j][i][0], v1 = alpha * acc[j][i][1];
+            if (p.atomic) {
+                if (w0) atomicAdd(c, v0);
+                if (w1) atomicAdd(c + 1, v1);
+            } else if (p.vecC && w0 && w1) {
+                double2 o = make_double2(v0, v1);
+                if (beta != 0.0) {
+                    double2 old = *reinterpret_cast<double2 *>(c);
+                    o.x += beta * old.x;
+                    o.y += beta * old.y;
+                }
+                *reinterpret_cast<double2 *>(c) = o;
+            } else {
+                if (w0) c[0] = v0 + (beta != 0.0 ? beta * c[0] : 0.0);
+                if (w1) c[1] = v1 + (beta != 0.0 ? beta * c[1] : 0.0);
+            }
+        }
+    }
+}
+
 // ---- f32: 64x64x16 tile, 256 threads, 4x4 micro-tile, exact FFMA ------------------------------
 struct SgemmP {
     int M, N, K;
@@ -276,12 +434,18 @@ void launch_dgemm(lfb_handle &h, const GemmP &p, dim3 grid) {
     constexpr int A_SZ = AM == 0 ? BK * (BM + 4) : BM * (BK + 4);
     constexpr int B_SZ = BMo == 0 ? BN * (BK + 4) : BK * (BN + 4);
     constexpr size_t smem = sizeof(double) * 2 * (A_SZ + B_SZ);
+    constexpr size_t smem2 = sizeof(double) * V2_STAGES * (A_SZ + B_SZ);
     static bool configured = false;
     if (!configured) {
         LFB_CUDA(cudaFuncSetAttribute(dgemm_kernel<AM, BMo>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LFB_CUDA(cudaFuncSetAttribute(dgemm_v2_kernel<AM, BMo>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
         configured = true;
     }
-    dgemm_kernel<AM, BMo><<<grid, 256, smem, h.stream>>>(p);
+    if (p.vecA && p.vecB && h.opt.gemm_v2) {
+        dgemm_v2_kernel<AM, BMo><<<grid, 512, smem2, h.stream>>>(p);
+    } else {
+        dgemm_kernel<AM, BMo><<<grid, 256, smem, h.stream>>>(p);
+    }
     LFB_LAUNCH_CHECK(h);
 }
 

@@ -1,11 +1,326 @@
-// TMA-fed FP64 GEMM fast path (filled in after the generic path is validated on hardware).
+// TMA-fed, warp-specialised FP64 GEMM (the aligned fast path of lfb::gemm<double>).
+//
+//   * one producer warp: cp.async.bulk.tensor (TMA, SASS UTMALDG) into a 5-stage 128B-swizzled
+//     shared-memory ring, completion on `full` mbarriers (expect_tx);
+//   * sixteen consumer warps (4 per scheduler, warp tile 32x32): DMMA.8x8x4 straight from the
+//     swizzled tiles, release a stage with one `empty` mbarrier arrive per warp.
+// There is NO CTA-wide barrier in the main loop: the ncu profile of the barrier-per-k-tile kernels
+// (profiles/) shows the restart bubble after each __syncthreads as their main loss; here warps
+// drift apart and the FP64 tensor pipe always has a ready warp.
+//
+// Bank-conflict-free fragment loads from the TMA layout (no padding is possible with TMA): the MMA
+// does not care which physical row a fragment lane holds as long as the epilogue agrees, so rows
+// are permuted inside each 16-row group:
+//   K-major tile  (box 16k x 128 rows, 128B rows):  row = 16*grp + 2*gid + parity
+//   MN-major tile (8 boxes of 16 rows(mn) x 16 k):  row = 16*grp + perm(gid) + 4*parity,
+//                                                   perm(g) = g0 | g2<<1 | g1<<3
+// which makes the 16 lanes of each 64-bit shared-load phase hit 16 distinct 8-byte slots under the
+// 128B swizzle (chunk index ^= row%8).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace lfb {
+namespace {
 
-bool dgemm_tma_try(lfb_handle &, int, int, int64_t, int64_t, int64_t, double, const double *, int64_t, const double *,
-                   int64_t, double, double *, int64_t, int) {
-    return false;
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int STAGES = 5;
+constexpr int TILE_BYTES = BM * BK * 8;           // 16 KB per operand per stage
+constexpr int STAGE_BYTES = 2 * TILE_BYTES;       // 32 KB
+constexpr int NCONS = 16;                         // consumer warps
+constexpr int NTHREADS = (NCONS + 1) * 32;
+
+struct TmaP {
+    int M, N, K;
+    int64_t ldc;
+    double *C;
+    double alpha, beta;
+    int lower_only, ksplit, atomic;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done) {   // never hang the GPU on a protocol bug: trap after ~2 s
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 4000000000LL) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+        "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ int perm8(int g) { return (g & 1) | (((g >> 2) & 1) << 1) | (((g >> 1) & 1) << 3); }
+
+// physical row (0..31 inside the warp tile) held by lane-group g of fragment f
+template <int KMAJOR>
+__device__ __forceinline__ int frag_row(int f, int g) {
+    return KMAJOR ? 16 * (f >> 1) + 2 * g + (f & 1) : 16 * (f >> 1) + perm8(g) + 4 * (f & 1);
+}
+
+// AK / BKm: 1 if that operand's tile is K-major in shared memory.
+//   A: AMODE 1 (A stored K x M, k contiguous) -> K-major ; AMODE 0 (M x K) -> MN-major
+//   B: BMODE 0 (B stored K x N, k contiguous) -> K-major ; BMODE 1 (N x K) -> MN-major
+template <int AK, int BKm>
+__global__ void __launch_bounds__(NTHREADS, 1)
+dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TmaP p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // the 128B swizzle pattern is a function of the shared address: align the ring to 1024 bytes
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (p.lower_only && m0 + BM <= n0) return;
+    const int kbeg = blockIdx.z * p.ksplit;
+    const int kend = min(p.K, kbeg + p.ksplit);
+    if (kbeg >= kend) return;
+    const int KT = (kend - kbeg + BK - 1) / BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NCONS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == NCONS) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kt = 0; kt < KT; ++kt) {
+                const int slot = kt % STAGES;
+                const uint32_t phase = (kt / STAGES) & 1;
+                mbar_wait(&empty[slot], phase ^ 1);
+                mbar_expect_tx(&full[slot], STAGE_BYTES);
+                unsigned char *sa = smem + slot * STAGE_BYTES, *sb = sa + TILE_BYTES;
+                const int k0 = kbeg + kt * BK;
+                if (AK) {
+                    tma_load_2d(sa, &mapA, k0, m0, &full[slot]);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) tma_load_2d(sa + b * 2048, &mapA, m0 + 16 * b, k0, &full[slot]);
+                }
+                if (BKm) {
+                    tma_load_2d(sb, &mapB, k0, n0, &full[slot]);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) tma_load_2d(sb + b * 2048, &mapB, n0 + 16 * b, k0, &full[slot]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;
+    // per-fragment byte offsets: addr(ks) = base + ks*KS_STEP + (pre ^ ks-dependent constant)
+    uint32_t abase[4], apre[4], bbase[4], bpre[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        {
+            const int r = wm0 + frag_row<AK>(f, gid);
+            if (AK) {  // row*128 + ((2ks ^ pre) << 4) + (tig&1)*8,  pre = (r&7) ^ (tig>>1)
+                abase[f] = r * 128 + (tig & 1) * 8;
+                apre[f] = (uint32_t)(((r & 7) ^ (tig >> 1)) << 4);
+            } else {   // (r>>4)*2048 + (ks*4+tig)*128 + ((((r&15)>>1) ^ ((ks&1)<<2 | tig)) << 4) + (r&1)*8
+                abase[f] = (r >> 4) * 2048 + tig * 128 + (r & 1) * 8;
+                apre[f] = (uint32_t)(((((r & 15) >> 1) ^ tig)) << 4);
+            }
+        }
+        {
+            const int r = wn0 + frag_row<BKm>(f, gid);
+            if (BKm) {
+                bbase[f] = r * 128 + (tig & 1) * 8;
+                bpre[f] = (uint32_t)(((r & 7) ^ (tig >> 1)) << 4);
+            } else {
+                bbase[f] = (r >> 4) * 2048 + tig * 128 + (r & 1) * 8;
+                bpre[f] = (uint32_t)(((((r & 15) >> 1) ^ tig)) << 4);
+            }
+        }
+    }
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i][0] = acc[j][i][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int slot = kt % STAGES;
+        const uint32_t phase = (kt / STAGES) & 1;
+        mbar_wait(&full[slot], phase);
+        const unsigned char *sa = smem + slot * STAGE_BYTES, *sb = sa + TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            double fa[4], fb[4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const uint32_t oa = AK ? abase[f] + (apre[f] ^ (uint32_t)(ks << 5))
+                                       : abase[f] + ks * 512 + (apre[f] ^ (uint32_t)((ks & 1) << 6));
+                fa[f] = *reinterpret_cast<const double *>(sa + oa);
+                const uint32_t ob = BKm ? bbase[f] + (bpre[f] ^ (uint32_t)(ks << 5))
+                                        : bbase[f] + ks * 512 + (bpre[f] ^ (uint32_t)((ks & 1) << 6));
+                fb[f] = *reinterpret_cast<const double *>(sb + ob);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dmma884(acc[j][i][0], acc[j][i][1], fb[j], fa[i]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+    }
+
+    // epilogue: acc[j][i][e] is C[m = A-row(i, 2*tig+e)][n = B-row(j, gid)]
+    double *__restrict__ C = p.C;
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + wn0 + frag_row<BKm>(j, gid);
+        if (n >= p.N) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int m = m0 + wm0 + frag_row<AK>(i, 2 * tig + e);
+                if (m >= p.M) continue;
+                if (p.lower_only && m < n) continue;
+                double *c = C + m + (int64_t)n * p.ldc;
+                const double v = alpha * acc[j][i][e];
+                if (p.atomic) atomicAdd(c, v);
+                else *c = v + (beta != 0.0 ? beta * *c : 0.0);
+            }
+        }
+    }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                             const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// 2-D f64 tensor map over a column-major buffer: dim0 = contiguous extent d0, dim1 = d1 (stride ld).
+bool make_map(CUtensorMap *map, const double *ptr, int64_t d0, int64_t d1, int64_t ld, int box0, int box1) {
+    EncodeFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <typename K>
+__global__ void scale_kernel_d(K *C, int64_t M, int64_t N, int64_t ldc, K beta, int lower_only) {
+    int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    for (int64_t n = blockIdx.y; n < N; n += gridDim.y) {
+        if (lower_only && m < n) continue;
+        K *c = C + m + n * ldc;
+        *c = beta == K(0) ? K(0) : beta * *c;
+    }
+}
+
+template <int AK, int BKm>
+void launch(lfb_handle &h, const CUtensorMap &ma, const CUtensorMap &mb, const TmaP &p, dim3 grid) {
+    constexpr size_t smem = STAGES * STAGE_BYTES + 2 * STAGES * sizeof(uint64_t) + 1024;
+    static bool cfg = false;
+    if (!cfg) {
+        LFB_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BKm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cfg = true;
+    }
+    dgemm_tma_kernel<AK, BKm><<<grid, NTHREADS, smem, h.stream>>>(ma, mb, p);
+    LFB_LAUNCH_CHECK(h);
+}
+
+}  // namespace
+
+bool dgemm_tma_try(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
+                   int64_t lda, const double *B, int64_t ldb, double beta, double *C, int64_t ldc, int lower_only) {
+    // TMA needs 16-byte aligned bases and strides; tiny problems stay on the cp.async kernel.
+    if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 1) || (ldb & 1)) return false;
+    if (M < 64 || N < 32 || K < 64) return false;
+    if (M >= (1LL << 31) || N >= (1LL << 31) || K >= (1LL << 31)) return false;
+    alignas(64) CUtensorMap ma, mb;
+    const int AK = ta ? 1 : 0;   // A stored K x M -> K-major tile
+    const int BKm = tb ? 0 : 1;  // B stored K x N -> K-major tile
+    bool ok = AK ? make_map(&ma, A, K, M, lda, BK, BM) : make_map(&ma, A, M, K, lda, 16, BK);
+    ok = ok && (BKm ? make_map(&mb, B, K, N, ldb, BK, BN) : make_map(&mb, B, N, K, ldb, 16, BK));
+    if (!ok) return false;
+
+    TmaP p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.ldc = ldc; p.C = C; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only;
+    const int64_t tm = cdiv(M, BM), tn = cdiv(N, BN);
+    int splits = 1;
+    if (h.opt.gemm_splitk && tm * tn < h.sm_count) {
+        int64_t want = cdiv(2 * h.sm_count, tm * tn), maxs = std::max<int64_t>(1, K / (8 * BK));
+        splits = (int)std::min(want, maxs);
+    }
+    p.ksplit = (int)round_up(cdiv(K, splits), BK);
+    splits = (int)cdiv(K, p.ksplit);
+    p.atomic = splits > 1;
+    if (p.atomic && beta != 1.0) {
+        dim3 g((unsigned)cdiv(M, 256), (unsigned)(N < 65535 ? N : 65535));
+        scale_kernel_d<double><<<g, 256, 0, h.stream>>>(C, M, N, ldc, beta, lower_only);
+        LFB_LAUNCH_CHECK(h);
+    }
+    dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)splits);
+    if (AK && BKm) launch<1, 1>(h, ma, mb, p, grid);
+    else if (AK && !BKm) launch<1, 0>(h, ma, mb, p, grid);
+    else if (!AK && BKm) launch<0, 1>(h, ma, mb, p, grid);
+    else launch<0, 0>(h, ma, mb, p, grid);
+    return true;
 }
 
 }  // namespace lfb
