@@ -41,7 +41,7 @@ struct Options {
     int64_t qr_nb = 128;     // outer panel width of blocked compact-WY QR
     int64_t qr_sub = 32;     // inner BLAS-2 sub-panel width (<= 32)
     int64_t chol_base = 64;  // recursion base of Cholesky / TRSM (<= 64)
-    int64_t chol_nb = 256;   // right-looking panel width of Cholesky (K of the trailing SYRK)
+    int64_t chol_nb = 512;   // right-looking panel width of Cholesky (K of the trailing SYRK)
     int64_t gemm_tma = 1;    // use the TMA-fed DGEMM when operands are 16-byte aligned
     int64_t gemm_splitk = 1; // allow split-K for skinny-output GEMMs
     int64_t gemm_v2 = 1;     // 16-warp cp.async DGEMM when operands are 16-byte aligned
