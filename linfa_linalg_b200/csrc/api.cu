@@ -328,6 +328,7 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     else if (k == "gemm_splitk") h->opt.gemm_splitk = value;
     else if (k == "gemm_v2") h->opt.gemm_v2 = value;
     else if (k == "panel_cluster") h->opt.panel_cluster = value;
+    else if (k == "panel_cluster_max") h->opt.panel_cluster_max = value;
     else return LFB_INVALID_ARGUMENT;
     return LFB_OK;
 }

@@ -46,6 +46,7 @@ struct Options {
     int64_t gemm_splitk = 1; // allow split-K for skinny-output GEMMs
     int64_t gemm_v2 = 1;     // 16-warp cp.async DGEMM when operands are 16-byte aligned
     int64_t panel_cluster = 1; // use the cluster/DSMEM panel kernel when the panel fits
+    int64_t panel_cluster_max = 16; // largest cluster size tried (16 is non-portable but supported on B200)
 };
 
 }  // namespace lfb

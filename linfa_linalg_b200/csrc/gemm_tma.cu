@@ -35,7 +35,7 @@ struct TmaP {
     int64_t ldc;
     double *C;
     double alpha, beta;
-    int lower_only, ksplit, atomic;
+    int lower_only, ksplit, atomic, vecC;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -205,24 +205,66 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
 
     // epilogue: acc[j][i][e] is C[m = A-row(i, 2*tig+e)][n = B-row(j, gid)]
-    double *__restrict__ C = p.C;
+    // Stage the tile through the (now idle) pipeline ring so that C is read and written with
+    // coalesced 16-byte accesses and all loads of a thread are in flight together: with K = nb = 128
+    // (the QR trailing update) the epilogue is a third of the tile's time.
+    constexpr int LDT = BM + 2;
+    double *tile = reinterpret_cast<double *>(smem);   // [BN][LDT], element (m, n) at n*LDT + m
+    asm volatile("bar.sync 1, %0;" ::"n"(NCONS * 32) : "memory");   // every consumer is done with the ring
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int n = n0 + wn0 + frag_row<BKm>(j, gid);
-        if (n >= p.N) continue;
+        const int nl = wn0 + frag_row<BKm>(j, gid);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int m = m0 + wm0 + frag_row<AK>(i, 2 * tig + e);
-                if (m >= p.M) continue;
-                if (p.lower_only && m < n) continue;
-                double *c = C + m + (int64_t)n * p.ldc;
-                const double v = alpha * acc[j][i][e];
-                if (p.atomic) atomicAdd(c, v);
-                else *c = v + (beta != 0.0 ? beta * *c : 0.0);
+            for (int e = 0; e < 2; ++e) tile[nl * LDT + wm0 + frag_row<AK>(i, 2 * tig + e)] = alpha * acc[j][i][e];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NCONS * 32) : "memory");
+    double *__restrict__ C = p.C;
+    if (p.vecC && !p.atomic) {
+        constexpr int PER = 8;   // double2 chunks in flight per thread (2 rounds of 8 cover the tile)
+        for (int round = 0; round < (BM / 2) * BN / (NCONS * 32 * PER); ++round) {
+        double2 old[PER];
+        bool ok[PER];
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int idx = tid + (round * PER + it) * NCONS * 32;
+            const int nl = idx / (BM / 2), ml = (idx % (BM / 2)) * 2;
+            const int m = m0 + ml, n = n0 + nl;
+            ok[it] = m < p.M && n < p.N && (!p.lower_only || m + 1 >= n);
+            old[it] = make_double2(0.0, 0.0);
+            if (ok[it] && beta != 0.0) {
+                if (m + 1 < p.M) old[it] = *reinterpret_cast<const double2 *>(C + m + (int64_t)n * p.ldc);
+                else old[it].x = C[m + (int64_t)n * p.ldc];
             }
+        }
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            if (!ok[it]) continue;
+            const int idx = tid + (round * PER + it) * NCONS * 32;
+            const int nl = idx / (BM / 2), ml = (idx % (BM / 2)) * 2;
+            const int m = m0 + ml, n = n0 + nl;
+            const double2 t = *reinterpret_cast<const double2 *>(tile + nl * LDT + ml);
+            double2 o = make_double2(t.x + beta * old[it].x, t.y + beta * old[it].y);
+            double *c = C + m + (int64_t)n * p.ldc;
+            const bool w0 = !p.lower_only || m >= n, w1 = m + 1 < p.M;
+            if (w0 && w1) *reinterpret_cast<double2 *>(c) = o;
+            else {
+                if (w0) c[0] = o.x;
+                if (w1) c[1] = o.y;
+            }
+        }
+        }  // round
+    } else {
+        for (int idx = tid; idx < BM * BN; idx += NCONS * 32) {
+            const int nl = idx / BM, ml = idx % BM;
+            const int m = m0 + ml, n = n0 + nl;
+            if (m >= p.M || n >= p.N || (p.lower_only && m < n)) continue;
+            double *c = C + m + (int64_t)n * p.ldc;
+            const double v = tile[nl * LDT + ml];
+            if (p.atomic) atomicAdd(c, v);
+            else *c = v + (beta != 0.0 ? beta * *c : 0.0);
         }
     }
 }
@@ -301,6 +343,7 @@ bool dgemm_tma_try(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int64_t 
     TmaP p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.ldc = ldc; p.C = C; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only;
+    p.vecC = (((uintptr_t)C & 15) == 0) && ((ldc & 1) == 0);
     const int64_t tm = cdiv(M, BM), tn = cdiv(N, BN);
     int splits = 1;
     if (h.opt.gemm_splitk && tm * tn < h.sm_count) {

@@ -13,7 +13,11 @@
 // the reflector, update the sub-panel, and accumulate the NEXT column's Gram row in the same pass,
 // so a column costs one launch and one pass over the sub-panel), compact-WY block reflectors
 // I - V T V^T with T = (striu(V^T V) + I/2)^-1 (tau = 2 for unit-norm v), and GEMM trailing updates.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace lfb {
 namespace {
@@ -26,6 +30,22 @@ template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqr
 template <typename T> __device__ __forceinline__ T t_abs(T x) { return x < T(0) ? -x : x; }
 // Rust signum: +1 for +0.0, -1 for -0.0
 template <typename T> __device__ __forceinline__ T t_signum(T x) { return signbit(x) ? T(-1) : T(1); }
+
+// 1/sqrt(d): f32 seed + 2 Newton steps (full f64 accuracy for d inside the f32 range)
+template <typename T> __device__ __forceinline__ T fast_rsqrt(T d);
+template <> __device__ __forceinline__ float fast_rsqrt<float>(float d) { return rsqrtf(d); }
+template <> __device__ __forceinline__ double fast_rsqrt<double>(double d) {
+    if (d > 1e-30 && d < 1e30) {
+        double y = (double)rsqrtf((float)d);
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const double r = fma(-d * y, y, 1.0);
+            y = fma(0.5 * y, r, y);
+        }
+        return y;
+    }
+    return rsqrt(d);
+}
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
@@ -140,6 +160,208 @@ __global__ void __launch_bounds__(256) hh_col_step(T *__restrict__ A, int64_t ld
     if (nrem > 0) block_reduce_add<T, 256>(part, nrem, gram_next, sred);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cluster panel kernel: a whole sub-panel (rows x w, w <= 32) lives in the distributed shared memory
+// of ONE thread-block cluster (<= 16 CTAs, each owning a slab of rows).  Per column: one pass over
+// the slab (scale reflector, update the remaining columns, accumulate the full Gram row of the NEXT
+// column against all w columns), one deterministic cluster-wide reduction through DSMEM, one
+// cluster barrier.  That replaces one kernel launch per column (14.7 us measured) by ~1 us.
+// The same Gram rows give v_i . v_j for free, so the kernel also emits the compact-WY factor
+// T = (striu(V^T V) + I/2)^-1 of the sub-panel and the staged V (zero above the diagonal, zero for
+// `None` columns) that the trailing GEMMs consume.
+template <typename T>
+struct PanelArgs {
+    T *A; int64_t ld, m, c0;
+    int w, rpc;
+    T *beta;
+    T *V; int64_t ldv, vrow0; int vcol0;   // V workspace of the enclosing panel (rows from the panel's first row)
+    T *Tout; int ldt;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(512, 1) hh_panel_cluster(PanelArgs<T> p) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int nc = (int)cluster.num_blocks();
+    const int b = (int)cluster.block_rank();
+    extern __shared__ __align__(16) unsigned char panel_smem[];
+    const int w = p.w, rpc = p.rpc;
+    T *S = reinterpret_cast<T *>(panel_smem);  // [w][rpc]
+    T *exq = S + (size_t)w * rpc;              // [2][W] partial Gram rows (read remotely)
+    T *exh = exq + 2 * W;                      // [2][W] head row (valid in the owner CTA)
+    T *red = exh + 2 * W;                      // [16][W]
+    T *G = red + 16 * W;                       // [W][W]  G[k*W + j] = v_k . v_j (k < j)
+    T *fac = G + W * W;                        // [W]
+    T *qv = fac + W;                           // [W]
+    T *hv = qv + W;                            // [W]
+    T *somef = hv + W;                         // [W]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t grow0 = p.c0 + (int64_t)b * rpc;
+    const int nrows = (int)max((int64_t)0, min((int64_t)rpc, p.m - grow0));
+
+    for (int k = 0; k < w; ++k)
+        for (int lr = tid; lr < rpc; lr += 512)
+            S[(size_t)k * rpc + lr] = lr < nrows ? p.A[(grow0 + lr) + (p.c0 + k) * p.ld] : T(0);
+    for (int e = tid; e < W * W; e += 512) G[e] = T(0);
+    __syncthreads();
+
+    T part[W];
+    // warp-transposed reduction of part[] + cross-warp sum; result for column k lands in dst[k]
+    auto reduce_to = [&](T *dst) {
+#pragma unroll
+        for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (i < n) {
+                    const bool up = (lane & off) != 0;
+                    const T send = up ? part[i] : part[i + n];
+                    const T keep = up ? part[i + n] : part[i];
+                    part[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+        }
+        red[warp * W + lane] = part[0];
+        __syncthreads();
+        if (tid < W) {
+            T s = T(0);
+#pragma unroll
+            for (int wv = 0; wv < 16; ++wv) s += red[wv * W + tid];
+            dst[tid] = s;
+        }
+    };
+
+    // Gram row of column 0 and its head row
+#pragma unroll
+    for (int k = 0; k < W; ++k) part[k] = T(0);
+    for (int lr = tid; lr < nrows; lr += 512) {
+        const T x = S[lr];
+#pragma unroll
+        for (int k = 0; k < W; ++k)
+            if (k < w) part[k] += S[(size_t)k * rpc + lr] * x;
+    }
+    reduce_to(exq);
+    if (b == 0 && tid < w) exh[tid] = S[(size_t)tid * rpc];
+    cluster.sync();
+
+    for (int j = 0; j < w; ++j) {
+        const int par = j & 1;
+        const int64_t c = p.c0 + j;
+        // ---- gather the cluster-wide Gram row (fixed order => deterministic) and the head row ----
+        // one remote (DSMEM) load per thread: thread (bb, k) fetches CTA bb's partial for column k
+        {
+            const int bb = tid >> 5, k = tid & 31;   // 16 x 32 = 512 threads
+            red[bb * W + k] = bb < nc ? cluster.map_shared_rank(exq, bb)[par * W + k] : T(0);
+            if (bb == 0) hv[k] = cluster.map_shared_rank(exh, j / rpc)[par * W + k];
+        }
+        __syncthreads();
+        if (tid < W) {
+            T q = T(0);
+#pragma unroll
+            for (int bb = 0; bb < 16; ++bb) q += red[bb * W + tid];
+            qv[tid] = q;
+        }
+        __syncthreads();
+        const T nsq = qv[j], f = hv[j];
+        // householder.rs:13-23 with the two square roots taken as x*rsqrt(x) (f32 seed + Newton, then one
+        // correction step): the per-column latency chain is what bounds this kernel.
+        const T rn = nsq > T(0) ? fast_rsqrt(nsq) : T(0);
+        T nrm = nsq * rn;
+        nrm = fma(T(0.5) * rn, fma(-nrm, nrm, nsq), nrm);
+        const T s = t_signum(f) * nrm;                   // :16
+        const T newsq = (nsq + t_abs(f) * nrm) * T(2);   // :19-20
+        const bool some = newsq != T(0);                 // :22
+        const T rd = some ? fast_rsqrt(newsq) : T(0);    // 1 / sqrt(new_norm_sq)
+        if (tid < W) {
+            const int k = tid;
+            const T dotv = some ? (qv[k] + s * hv[k]) * rd : T(0);   // v_j . (column k)
+            fac[k] = (k > j && k < w) ? T(-2) * dotv : T(0);        // reflection.rs:29
+            if (k < j) G[k * W + j] = (somef[k] != T(0)) ? dotv : T(0);
+            if (k == j) somef[j] = some ? T(1) : T(0);
+            if (k == 0 && b == 0) p.beta[c] = some ? -s : T(0);     // householder.rs:24/26
+        }
+        __syncthreads();
+        // ---- one pass over the slab ----
+#pragma unroll
+        for (int k = 0; k < W; ++k) part[k] = T(0);
+        const bool has_next = j + 1 < w;
+        const int lr_min = (int)max((int64_t)0, c - grow0);
+        for (int lr = lr_min + tid; lr < nrows; lr += 512) {
+            const int64_t gr = grow0 + lr;
+            T v = S[(size_t)j * rpc + lr];
+            if (some) {
+                v = ((gr == c) ? v + s : v) * rd;        // householder.rs:17,23
+                S[(size_t)j * rpc + lr] = v;
+            }
+            T a1 = T(0);
+            if (has_next) {
+                a1 = S[(size_t)(j + 1) * rpc + lr];
+                if (some) {
+                    a1 += fac[j + 1] * v;                // reflection.rs:30
+                    S[(size_t)(j + 1) * rpc + lr] = a1;
+                }
+            }
+            const bool nxt = has_next && gr > c;
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+                if (k < w) {
+                    T a;
+                    if (k == j) a = v;
+                    else if (k == j + 1) a = a1;
+                    else {
+                        a = S[(size_t)k * rpc + lr];
+                        if (k > j && some) {
+                            a += fac[k] * v;
+                            S[(size_t)k * rpc + lr] = a;
+                        }
+                    }
+                    if (nxt) part[k] += a * a1;
+                }
+            }
+        }
+        if (has_next) {
+            reduce_to(exq + (par ^ 1) * W);
+            __syncthreads();
+            const int owner = (j + 1) / rpc, lrh = (j + 1) % rpc;
+            if (b == owner && tid < w) exh[(par ^ 1) * W + tid] = S[(size_t)tid * rpc + lrh];
+        }
+        cluster.sync();
+    }
+
+    // ---- write back: A (in place), staged V, and T (CTA 0) ----
+    for (int k = 0; k < w; ++k) {
+        const bool sk = somef[k] != T(0);
+        for (int lr = tid; lr < nrows; lr += 512) {
+            const T val = S[(size_t)k * rpc + lr];
+            const int64_t gr = grow0 + lr;
+            p.A[gr + (p.c0 + k) * p.ld] = val;
+            p.V[(p.vrow0 + (gr - p.c0)) + (int64_t)(p.vcol0 + k) * p.ldv] = (sk && gr >= p.c0 + k) ? val : T(0);
+        }
+    }
+    if (b == 0) {
+        for (int64_t e = tid; e < p.vrow0 * w; e += 512) p.V[(e % p.vrow0) + (p.vcol0 + e / p.vrow0) * p.ldv] = T(0);
+        // T = (striu(G) + I/2)^-1, one thread per column (w <= 32)
+        if (tid < w) {
+            const int jc = tid;
+            T tcol[W];
+#pragma unroll
+            for (int i = 0; i < W; ++i) tcol[i] = T(0);
+#pragma unroll
+            for (int i = W - 1; i >= 0; --i) {
+                if (i == jc) tcol[i] = T(2);
+                else if (i < jc) {
+                    T sum = T(0);
+#pragma unroll
+                    for (int k = 0; k < W; ++k)
+                        if (k > i && k <= jc) sum += G[i * W + k] * tcol[k];
+                    tcol[i] = T(-2) * sum;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < W; ++i)
+                if (i < w) p.Tout[i + jc * p.ldt] = tcol[i];
+        }
+    }
+}
+
 // Vout (rows x w, ldv) = V part of A[r0:, c0:c0+w): element (i, j) is zero for i < j ("upper" part
 // holds R), and whole column j is zeroed when beta != nullptr and beta[c0+j] == 0 (a `None` column:
 // the reference applies no reflection there).
@@ -157,25 +379,47 @@ __global__ void copy_v_kernel(const T *__restrict__ A, int64_t ld, int64_t r0, i
 
 // T = (striu(G) + I/2)^-1 for an nb x nb Gram matrix G = V^T V (single CTA, nb <= 128).
 // Column j of T solves U t = e_j by back substitution; one thread per column.
+// In-place recursive doubling (6-7 levels, each two small block products) instead of one
+// back-substitution per column: inv([A B; 0 C]) = [A^-1, -A^-1 B C^-1; 0, C^-1].
 template <typename T>
-__global__ void tinv_kernel(const T *__restrict__ G, int64_t ldg, int nb, T *__restrict__ Tm, int64_t ldt) {
-    extern __shared__ unsigned char smem_raw[];
-    T *U = reinterpret_cast<T *>(smem_raw);  // nb x (nb+1), U[i*(nb+1)+k] = U(i,k), i<k
-    const int lds = nb + 1;
-    for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
-        int i = e % nb, k = e / nb;
-        U[i * lds + k] = (i < k) ? G[i + (int64_t)k * ldg] : T(0);
+__global__ void __launch_bounds__(512) tinv_kernel(const T *__restrict__ G, int64_t ldg, int nb, T *__restrict__ Tm, int64_t ldt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int P = 1;
+    while (P < nb) P <<= 1;                   // padded size (<= 128)
+    const int lds = P + 1;
+    T *X = reinterpret_cast<T *>(smem_raw);   // [P][P+1]  starts as U, ends as U^-1
+    T *tmp = X + P * lds;                     // [P/2][P+1]
+    const int tid = threadIdx.x;
+    for (int e = tid; e < P * P; e += 512) {
+        const int i = e % P, k = e / P;
+        T v = T(0);
+        if (i == k) v = T(2);                                       // 1 / U_ii, U_ii = 1/2
+        else if (i < k && k < nb) v = G[i + (int64_t)k * ldg];      // striu(V^T V)
+        X[i * lds + k] = v;
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
-        T *tcol = Tm + (int64_t)j * ldt;
-        for (int i = j + 1; i < nb; ++i) tcol[i] = T(0);
-        tcol[j] = T(2);
-        for (int i = j - 1; i >= 0; --i) {
-            T sum = T(0);
-            for (int k = i + 1; k <= j; ++k) sum += U[i * lds + k] * tcol[k];
-            tcol[i] = T(-2) * sum;
+    for (int b = 1; b < P; b <<= 1) {
+        const int npair = P / (2 * b), per = b * b;
+        // tmp = B * C^-1   (B = X[o.., o+b..) original, C^-1 = X[o+b.., o+b..) upper)
+        for (int e = tid; e < npair * per; e += 512) {
+            const int p = e / per, i = (e % per) / b, j = e % b, o = p * 2 * b;
+            T acc = T(0);
+            for (int k = 0; k <= j; ++k) acc += X[(o + i) * lds + o + b + k] * X[(o + b + k) * lds + o + b + j];
+            tmp[(p * b + i) * lds + j] = acc;
         }
+        __syncthreads();
+        // X12 = -A^-1 * tmp   (A^-1 = X[o.., o..) upper)
+        for (int e = tid; e < npair * per; e += 512) {
+            const int p = e / per, i = (e % per) / b, j = e % b, o = p * 2 * b;
+            T acc = T(0);
+            for (int k = i; k < b; ++k) acc += X[(o + i) * lds + o + k] * tmp[(p * b + k) * lds + j];
+            X[(o + i) * lds + o + b + j] = -acc;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < nb * nb; e += 512) {
+        const int i = e % nb, k = e / nb;
+        Tm[i + (int64_t)k * ldt] = (i <= k) ? X[i * lds + k] : T(0);
     }
 }
 
@@ -254,13 +498,16 @@ void copy_v(lfb_handle &h, const T *A, int64_t ld, int64_t r0, int64_t c0, int64
 template <typename T>
 void build_t(lfb_handle &h, const T *V, int64_t ldv, int64_t rows, int nb, T *G, T *Tm, int64_t ldt) {
     gemm<T>(h, 1, 0, nb, nb, rows, T(1), V, ldv, V, ldv, T(0), G, nb);
-    size_t smem = sizeof(T) * nb * (nb + 1);
+    int P = 1;
+    while (P < nb) P <<= 1;
+    size_t smem = sizeof(T) * (size_t)(P * (P + 1) + (P / 2 + 1) * (P + 1));
     static bool cfg = false;
     if (!cfg) {
-        LFB_CUDA(cudaFuncSetAttribute(tinv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(T) * 128 * 129)));
+        LFB_CUDA(cudaFuncSetAttribute(tinv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(T) * (128 * 129 + 65 * 129))));
         cfg = true;
     }
-    tinv_kernel<T><<<1, 128, smem, h.stream>>>(G, nb, nb, Tm, ldt);
+    tinv_kernel<T><<<1, 512, smem, h.stream>>>(G, nb, nb, Tm, ldt);
     LFB_LAUNCH_CHECK(h);
 }
 
@@ -296,6 +543,58 @@ void factor_subpanel(lfb_handle &h, T *A, int64_t ld, int64_t m, int64_t c0, int
     }
 }
 
+// Picks (cluster size, sub-panel width, rows per CTA) so that the sub-panel fits the cluster's
+// distributed shared memory; returns false if it cannot (very tall panels) or clusters are off.
+template <typename T>
+bool plan_cluster(lfb_handle &h, int64_t rows, int wmax, int *nc, int *w, int *rpc, size_t *smem) {
+    if (!h.opt.panel_cluster || rows <= 0) return false;
+    const size_t extra = sizeof(T) * (size_t)(24 * W + W * W);
+    if (h.smem_optin <= extra + 4096) return false;
+    const int64_t cap = (int64_t)((h.smem_optin - extra - 1024) / sizeof(T));   // elements of S per CTA
+    int c = rows > 2048 ? 16 : rows > 1024 ? 8 : rows > 512 ? 4 : rows > 256 ? 2 : 1;
+    if (c > h.opt.panel_cluster_max) c = (int)h.opt.panel_cluster_max;
+    int64_t r = round_up(cdiv(rows, c), 32);
+    int ww = wmax;
+    while (ww > 8 && r * ww > cap) ww -= 8;
+    if (r * ww > cap) return false;
+    *nc = c; *w = ww; *rpc = (int)r;
+    *smem = sizeof(T) * (size_t)(r * ww) + extra;
+    return true;
+}
+
+template <typename T>
+bool factor_subpanel_cluster(lfb_handle &h, T *A, int64_t ld, int64_t m, int64_t c0, int nc, int w, int rpc, size_t smem,
+                             T *beta, T *V, int64_t ldv, int64_t vrow0, int vcol0, T *Tout, int ldt) {
+    static bool cfg = false;
+    if (!cfg) {
+        LFB_CUDA(cudaFuncSetAttribute(hh_panel_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem_optin));
+        LFB_CUDA(cudaFuncSetAttribute(hh_panel_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cfg = true;
+    }
+    PanelArgs<T> p;
+    p.A = A; p.ld = ld; p.m = m; p.c0 = c0; p.w = w; p.rpc = rpc; p.beta = beta;
+    p.V = V; p.ldv = ldv; p.vrow0 = vrow0; p.vcol0 = vcol0; p.Tout = Tout; p.ldt = ldt;
+    cudaLaunchConfig_t cfgl = {};
+    cfgl.gridDim = dim3((unsigned)nc);
+    cfgl.blockDim = dim3(512);
+    cfgl.dynamicSmemBytes = smem;
+    cfgl.stream = h.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)nc;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfgl.attrs = attr;
+    cfgl.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfgl, hh_panel_cluster<T>, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;   // e.g. the cluster cannot be co-scheduled: caller falls back
+    }
+    h.launches++;
+    return true;
+}
+
 }  // namespace
 
 // Standard (unscaled) blocked Householder QR of A (m x n, m >= n); beta[n] on device.
@@ -305,28 +604,44 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
     const int SUB = (int)std::max<int64_t>(1, std::min<int64_t>(h.opt.qr_sub, W));
     const int64_t ldv = round_up(m, 2);
     DevBuf<T> V(h, (size_t)ldv * NB);
-    DevBuf<T> Tm(h, (size_t)NB * NB), G(h, (size_t)NB * NB);
+    DevBuf<T> Tm(h, (size_t)NB * NB), G(h, (size_t)NB * NB), Ts(h, (size_t)W * W);
     DevBuf<T> W1(h, (size_t)NB * std::max<int64_t>(n, 1)), W2(h, (size_t)NB * std::max<int64_t>(n, 1));
     DevBuf<T> scratch(h, 5 * W);
 
     for (int64_t k0 = 0; k0 < n; k0 += NB) {
         const int nb = (int)std::min<int64_t>(NB, n - k0);
-        for (int s0 = 0; s0 < nb; s0 += SUB) {
-            const int w = std::min(SUB, nb - s0);
+        bool v_staged = true;   // the cluster kernels stage V (rows from k0) as they go
+        for (int s0 = 0; s0 < nb;) {
             const int64_t c0 = k0 + s0;
-            factor_subpanel<T>(h, A, ld, m, c0, w, beta, scratch);
-            const int64_t rest = (k0 + nb) - (c0 + w);  // remaining columns of this panel
-            if (rest > 0) {
-                const int64_t rows = m - c0;
-                copy_v<T>(h, A, ld, c0, c0, rows, w, beta, V, ldv);
-                build_t<T>(h, V, ldv, rows, w, G, Tm, NB);
-                apply_block_reflector<T>(h, V, ldv, rows, w, Tm, NB, /*trans_t=*/1, A + c0 + (c0 + w) * ld, ld, rest, W1, W2);
+            const int64_t rows = m - c0;
+            int w = std::min(SUB, nb - s0);
+            int nc = 0, wc = 0, rpc = 0;
+            size_t smem = 0;
+            bool done = false;
+            if (plan_cluster<T>(h, rows, w, &nc, &wc, &rpc, &smem)) {
+                done = factor_subpanel_cluster<T>(h, A, ld, m, c0, nc, wc, rpc, smem, beta, V, ldv, c0 - k0, s0, Ts, W);
+                if (done) w = wc;
+                else h.opt.panel_cluster = 0;   // launch refused once: stay on the per-column path
             }
+            const int64_t rest = (k0 + nb) - (c0 + w);  // remaining columns of this panel
+            if (!done) {
+                v_staged = false;
+                factor_subpanel<T>(h, A, ld, m, c0, w, beta, scratch);
+                if (rest > 0) {
+                    copy_v<T>(h, A, ld, c0, c0, rows, w, beta, V, ldv);
+                    build_t<T>(h, V, ldv, rows, w, G, Ts, W);
+                }
+            }
+            if (rest > 0) {
+                const T *Vs = done ? V.get() + (c0 - k0) + (int64_t)s0 * ldv : V.get();
+                apply_block_reflector<T>(h, Vs, ldv, rows, w, Ts, W, /*trans_t=*/1, A + c0 + (c0 + w) * ld, ld, rest, W1, W2);
+            }
+            s0 += w;
         }
         const int64_t trail = n - (k0 + nb);
         if (trail > 0) {
             const int64_t rows = m - k0;
-            copy_v<T>(h, A, ld, k0, k0, rows, nb, beta, V, ldv);
+            if (!v_staged) copy_v<T>(h, A, ld, k0, k0, rows, nb, beta, V, ldv);
             build_t<T>(h, V, ldv, rows, nb, G, Tm, NB);
             apply_block_reflector<T>(h, V, ldv, rows, nb, Tm, NB, /*trans_t=*/1, A + k0 + (k0 + nb) * ld, ld, trail, W1, W2);
         }
