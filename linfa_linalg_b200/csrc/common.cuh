@@ -45,7 +45,7 @@ struct Options {
     int64_t gemm_tma = 1;    // use the TMA-fed DGEMM when operands are 16-byte aligned
     int64_t gemm_splitk = 1; // allow split-K for skinny-output GEMMs
     int64_t gemm_v2 = 1;     // 16-warp cp.async DGEMM when operands are 16-byte aligned
-    int64_t panel_cluster = 1; // use the cluster/DSMEM panel kernel when the panel fits
+    int64_t panel_cluster = 2; // cluster/DSMEM panel kernel: 2 = second generation, 1 = first, 0 = per-column launches
     int64_t panel_cluster_max = 16; // largest cluster size tried (16 is non-portable but supported on B200)
 };
 

@@ -20,6 +20,12 @@
 namespace cg = cooperative_groups;
 
 namespace lfb {
+
+// panel_cluster.cu
+template <typename T>
+bool factor_subpanel_cluster2(lfb_handle &h, T *A, int64_t ld, int64_t m, int64_t c0, int wmax, int *w_out, T *beta, T *V,
+                              int64_t ldv, int64_t vrow0, int vcol0, T *Tout, int ldt);
+
 namespace {
 
 constexpr int W = 32;  // max sub-panel width
@@ -618,7 +624,12 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
             int nc = 0, wc = 0, rpc = 0;
             size_t smem = 0;
             bool done = false;
-            if (plan_cluster<T>(h, rows, w, &nc, &wc, &rpc, &smem)) {
+            if (h.opt.panel_cluster >= 2) {
+                done = factor_subpanel_cluster2<T>(h, A, ld, m, c0, w, &wc, beta, V, ldv, c0 - k0, s0, Ts, W);
+                if (done) w = wc;
+                else h.opt.panel_cluster = 1;   // refused once: try the first-generation kernel
+            }
+            if (!done && plan_cluster<T>(h, rows, w, &nc, &wc, &rpc, &smem)) {
                 done = factor_subpanel_cluster<T>(h, A, ld, m, c0, nc, wc, rpc, smem, beta, V, ldv, c0 - k0, s0, Ts, W);
                 if (done) w = wc;
                 else h.opt.panel_cluster = 0;   // launch refused once: stay on the per-column path
