@@ -272,6 +272,10 @@ int lfb_create(lfb_handle **out, int device) {
         LFB_CUDA(cudaSetDevice(device));
         LFB_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         h->stream = h->own_stream;
+        int lo = 0, hi = 0;
+        LFB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        LFB_CUDA(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi));
+        for (auto &e : h->ev) LFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         cudaDeviceProp prop;
         LFB_CUDA(cudaGetDeviceProperties(&prop, device));
         h->sm_count = prop.multiProcessorCount;
@@ -291,6 +295,8 @@ int lfb_destroy(lfb_handle *h) {
     for (auto &b : h->blocks) cudaFree(b.p);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     delete h;
     return LFB_OK;
 }
@@ -329,6 +335,7 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     else if (k == "gemm_v2") h->opt.gemm_v2 = value;
     else if (k == "panel_cluster") h->opt.panel_cluster = value;
     else if (k == "panel_cluster_max") h->opt.panel_cluster_max = value;
+    else if (k == "lookahead") h->opt.lookahead = value;
     else return LFB_INVALID_ARGUMENT;
     return LFB_OK;
 }

@@ -46,6 +46,7 @@ struct Options {
     int64_t gemm_splitk = 1; // allow split-K for skinny-output GEMMs
     int64_t gemm_v2 = 1;     // 16-warp cp.async DGEMM when operands are 16-byte aligned
     int64_t panel_cluster = 2; // cluster/DSMEM panel kernel: 2 = second generation, 1 = first, 0 = per-column launches
+    int64_t lookahead = 1;     // factor the next panel on a side stream while the trailing update runs
     int64_t panel_cluster_max = 16; // largest cluster size tried (16 is non-portable but supported on B200)
 };
 
@@ -56,6 +57,8 @@ struct lfb_handle {
     int device = 0;
     cudaStream_t stream = nullptr;      // stream in use
     cudaStream_t own_stream = nullptr;  // created by lfb_create
+    cudaStream_t aux_stream = nullptr;  // high-priority side stream for look-ahead panel factorisation
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
     size_t smem_optin = 0;
     std::string err;

@@ -609,14 +609,20 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
     const int NB = (int)std::max<int64_t>(W, std::min<int64_t>(h.opt.qr_nb, 128));
     const int SUB = (int)std::max<int64_t>(1, std::min<int64_t>(h.opt.qr_sub, W));
     const int64_t ldv = round_up(m, 2);
-    DevBuf<T> V(h, (size_t)ldv * NB);
-    DevBuf<T> Tm(h, (size_t)NB * NB), G(h, (size_t)NB * NB), Ts(h, (size_t)W * W);
+    // two generations of the panel workspaces (V, T): with look-ahead panel k+1 is factored while the
+    // trailing update of panel k still reads V_k / T_k
+    DevBuf<T> Vb0(h, (size_t)ldv * NB), Vb1(h, (size_t)ldv * NB);
+    DevBuf<T> Tb0(h, (size_t)NB * NB), Tb1(h, (size_t)NB * NB);
+    T *Vbuf[2] = {Vb0.get(), Vb1.get()}, *Tbuf[2] = {Tb0.get(), Tb1.get()};
+    DevBuf<T> G(h, (size_t)NB * NB), Ts(h, (size_t)W * W);
+    DevBuf<T> W1p(h, (size_t)NB * NB), W2p(h, (size_t)NB * NB);   // panel-internal applies (<= NB columns)
     DevBuf<T> W1(h, (size_t)NB * std::max<int64_t>(n, 1)), W2(h, (size_t)NB * std::max<int64_t>(n, 1));
     DevBuf<T> scratch(h, 5 * W);
 
-    for (int64_t k0 = 0; k0 < n; k0 += NB) {
-        const int nb = (int)std::min<int64_t>(NB, n - k0);
-        bool v_staged = true;   // the cluster kernels stage V (rows from k0) as they go
+    // Factors panel [k0, k0+nb) on the handle's current stream; stages V (rows from k0) and, if the
+    // panel has a trailing matrix, builds its compact-WY T.
+    auto factor_panel = [&](int64_t k0, int nb, T *V, T *Tm) {
+        bool v_staged = true;   // the cluster kernels stage V as they go
         for (int s0 = 0; s0 < nb;) {
             const int64_t c0 = k0 + s0;
             const int64_t rows = m - c0;
@@ -644,17 +650,50 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
                 }
             }
             if (rest > 0) {
-                const T *Vs = done ? V.get() + (c0 - k0) + (int64_t)s0 * ldv : V.get();
-                apply_block_reflector<T>(h, Vs, ldv, rows, w, Ts, W, /*trans_t=*/1, A + c0 + (c0 + w) * ld, ld, rest, W1, W2);
+                const T *Vs = done ? V + (c0 - k0) + (int64_t)s0 * ldv : V;
+                apply_block_reflector<T>(h, Vs, ldv, rows, w, Ts, W, /*trans_t=*/1, A + c0 + (c0 + w) * ld, ld, rest, W1p, W2p);
             }
             s0 += w;
         }
-        const int64_t trail = n - (k0 + nb);
-        if (trail > 0) {
+        if (n - (k0 + nb) > 0) {
             const int64_t rows = m - k0;
             if (!v_staged) copy_v<T>(h, A, ld, k0, k0, rows, nb, beta, V, ldv);
             build_t<T>(h, V, ldv, rows, nb, G, Tm, NB);
-            apply_block_reflector<T>(h, V, ldv, rows, nb, Tm, NB, /*trans_t=*/1, A + k0 + (k0 + nb) * ld, ld, trail, W1, W2);
+        }
+    };
+
+    cudaStream_t sm = h.stream, sp = h.aux_stream;
+    const bool la = h.opt.lookahead && sp != nullptr && !h.prof_on && n >= 4 * NB;
+    factor_panel(0, (int)std::min<int64_t>(NB, n), Vbuf[0], Tbuf[0]);
+    int cur = 0;
+    for (int64_t k0 = 0; k0 < n; k0 += NB, cur ^= 1) {
+        const int nb = (int)std::min<int64_t>(NB, n - k0);
+        const int64_t trail = n - (k0 + nb);
+        if (trail <= 0) break;
+        const int64_t rows = m - k0;
+        const int nbn = (int)std::min<int64_t>(NB, trail);
+        T *C = A + k0 + (k0 + nb) * ld;
+        if (la) {
+            // trailing update of the NEXT panel's columns first, then factor that panel on the side
+            // stream while the rest of the trailing matrix is updated here
+            apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C, ld, nbn, W1, W2);
+            LFB_CUDA(cudaEventRecord(h.ev[2], sm));
+            LFB_CUDA(cudaStreamWaitEvent(sp, h.ev[2], 0));
+            h.stream = sp;
+            try {
+                factor_panel(k0 + nb, nbn, Vbuf[cur ^ 1], Tbuf[cur ^ 1]);
+            } catch (...) {
+                h.stream = sm;
+                throw;
+            }
+            LFB_CUDA(cudaEventRecord(h.ev[3], sp));
+            h.stream = sm;
+            if (trail > nbn)
+                apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C + (int64_t)nbn * ld, ld, trail - nbn, W1, W2);
+            LFB_CUDA(cudaStreamWaitEvent(sm, h.ev[3], 0));
+        } else {
+            apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C, ld, trail, W1, W2);
+            factor_panel(k0 + nb, nbn, Vbuf[cur ^ 1], Tbuf[cur ^ 1]);
         }
     }
 }

@@ -191,9 +191,9 @@ void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64
     }
     DevBuf<T> Linv(h, CB * CB);
     const int64_t NB = std::max<int64_t>(CB, round_up(h.opt.chol_nb, CB));
-    for (int64_t k0 = 0; k0 < n; k0 += NB) {
-        const int64_t nb = std::min<int64_t>(NB, n - k0);
-        const int64_t pend = k0 + nb;   // first column after this panel
+    // panel [k0, k0+nb): 64-column blocks, everything on the handle's current stream
+    auto factor_panel = [&](int64_t k0, int64_t nb) {
+        const int64_t pend = k0 + nb;
         for (int64_t j0 = k0; j0 < pend; j0 += CB) {
             const int jb = (int)std::min<int64_t>(CB, pend - j0);
             T *Ajj = A + j0 + j0 * ld;
@@ -208,10 +208,42 @@ void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64
             if (rem > 0)   // A[j0+jb.., j0+jb..pend) -= Bp * Bp[0:rem, :]^T   (lower part only)
                 gemm<T>(h, 0, 1, below, rem, jb, T(-1), Bp, ld, Bp, ld, T(1), A + (j0 + jb) + (j0 + jb) * ld, ld, /*lower_only=*/1);
         }
+    };
+    // Look-ahead: the trailing SYRK of panel k is split into the block column of panel k+1 (done
+    // first) and the rest; panel k+1 is factored on a high-priority side stream while the rest of
+    // the SYRK runs, so the latency-bound diagonal kernels leave the critical path.
+    cudaStream_t sm = h.stream, sp = h.aux_stream;
+    const bool la = h.opt.lookahead && sp != nullptr && !h.prof_on && n >= 4 * NB;
+    factor_panel(0, std::min<int64_t>(NB, n));
+    for (int64_t k0 = 0; k0 < n; k0 += NB) {
+        const int64_t nb = std::min<int64_t>(NB, n - k0);
+        const int64_t pend = k0 + nb;
         const int64_t rows = n - pend;
-        if (rows > 0) {
-            T *P = A + pend + k0 * ld;
+        if (rows <= 0) break;
+        const int64_t nbn = std::min<int64_t>(NB, rows);
+        T *P = A + pend + k0 * ld;
+        if (la) {
+            gemm<T>(h, 0, 1, rows, nbn, nb, T(-1), P, ld, P, ld, T(1), A + pend + pend * ld, ld, /*lower_only=*/1);
+            LFB_CUDA(cudaEventRecord(h.ev[0], sm));
+            LFB_CUDA(cudaStreamWaitEvent(sp, h.ev[0], 0));
+            h.stream = sp;
+            try {
+                factor_panel(pend, nbn);
+            } catch (...) {
+                h.stream = sm;
+                throw;
+            }
+            LFB_CUDA(cudaEventRecord(h.ev[1], sp));
+            h.stream = sm;
+            const int64_t rows2 = rows - nbn;
+            if (rows2 > 0) {
+                T *P2 = P + nbn;
+                gemm<T>(h, 0, 1, rows2, rows2, nb, T(-1), P2, ld, P2, ld, T(1), A + (pend + nbn) + (pend + nbn) * ld, ld, /*lower_only=*/1);
+            }
+            LFB_CUDA(cudaStreamWaitEvent(sm, h.ev[1], 0));
+        } else {
             gemm<T>(h, 0, 1, rows, rows, nb, T(-1), P, ld, P, ld, T(1), A + pend + pend * ld, ld, /*lower_only=*/1);
+            factor_panel(pend, nbn);
         }
     }
     if (clean) triangular_zero<T>(h, A, n, ld, /*keep_lower=*/1);
