@@ -1,10 +1,18 @@
-// Batched thin QR of many small row-major matrices (m, n <= 32): one warp per matrix, lane = column.
+// Batched thin QR of many small row-major matrices (m, n <= 32): one warp per matrix.
 //
-// Each matrix is src/qr.rs:38-41 (clear_column per column, householder.rs:34-51) executed literally,
-// including the sign scaling, so the compact output is bit-for-bit in the reference's format.
-// HBM-bound by design: a matrix is read once (coalesced 128-byte rows), lives in registers
-// (lane j holds column j), and is written once.  The reflector is broadcast through a per-warp
-// shared-memory slab (one LDS.128 per 4 elements instead of 32 shuffles).
+// Each matrix is src/qr.rs:38-41 (clear_column per column, householder.rs:34-51).  HBM-bound by
+// design: a matrix is read once (coalesced 128-byte rows), lives on chip, and is written once.
+//
+// Layout of the work (second generation; the first kept everything in 250 registers with 32 fully
+// unrolled column steps and was instruction-fetch / latency bound at 7 % of the HBM roofline):
+//   * lane t keeps COLUMN t in registers (static indexing only);
+//   * per column step j the owner lane publishes its column through a per-warp shared slab, the
+//     norm is then a 5-step shuffle reduction with lane = row, every lane computes the scalars,
+//     the unit reflector v goes back through shared memory (one float per lane out, 16-byte
+//     broadcast loads in) and lanes t > j do dot + axpy on their register column;
+//   * rows above the current 8-row segment are skipped statically (4 code segments);
+//   * the reference's per-column sign scaling (householder.rs:45-48) is applied once at the end:
+//     R[i, t>i] *= P_i, v_j *= P_{j-1}, diag_j = P_{j-1} beta_j with P_j = sgn(beta_j).
 #include "common.cuh"
 
 namespace lfb {
@@ -16,62 +24,126 @@ template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqr
 template <typename T> __device__ __forceinline__ T t_abs(T x) { return x < T(0) ? -x : x; }
 template <typename T> __device__ __forceinline__ T t_signum(T x) { return signbit(x) ? T(-1) : T(1); }
 
-constexpr int WPB = 8;  // warps (matrices) per CTA
+// 1/sqrt(x): f32 = MUFU.RSQ; f64 = f32 seed + 2 Newton steps (full accuracy inside the f32 range)
+template <typename T> __device__ __forceinline__ T fast_rsqrt(T d);
+template <> __device__ __forceinline__ float fast_rsqrt<float>(float d) { return rsqrtf(d); }
+template <> __device__ __forceinline__ double fast_rsqrt<double>(double d) {
+    if (d > 1e-30 && d < 1e30) {
+        double y = (double)rsqrtf((float)d);
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const double r = fma(-d * y, y, 1.0);
+            y = fma(0.5 * y, r, y);
+        }
+        return y;
+    }
+    return rsqrt(d);
+}
+
+template <typename T> constexpr int wpb() { return sizeof(T) == 8 ? 4 : 8; }   // warps (matrices in flight) per CTA
+constexpr int VP = 36;    // pitch of the per-warp reflector store (16-byte aligned rows)
+
+template <typename T, int RS>
+__device__ __forceinline__ void column_steps(T (&a)[32], T *colbuf, T *vstore, int lane, int n, int jend, T &dg) {
+    for (int j = RS; j < jend; ++j) {
+        // 1. the owner lane publishes rows RS.. of its column
+        if (lane == j) {   // 16-byte stores
+            if constexpr (sizeof(T) == 4) {
+#pragma unroll
+                for (int r = RS; r < 32; r += 4)
+                    *reinterpret_cast<float4 *>(colbuf + r) = make_float4(a[r], a[r + 1], a[r + 2], a[r + 3]);
+            } else {
+#pragma unroll
+                for (int r = RS; r < 32; r += 2) *reinterpret_cast<double2 *>(colbuf + r) = make_double2(a[r], a[r + 1]);
+            }
+        }
+        __syncwarp();
+        const T x = colbuf[lane];                                   // lane = row
+        const T xa = lane >= j ? x : T(0);
+        T nsq = xa * xa;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nsq += __shfl_xor_sync(0xffffffffu, nsq, o);
+        const T f = __shfl_sync(0xffffffffu, x, j);
+        // householder.rs:13-23; sqrt(x) = x * rsqrt(x) (+ one correction step) and the division by
+        // sqrt(new_norm_sq) is a multiplication: the 32 column steps of a matrix are one latency chain
+        const T rn = nsq > T(0) ? fast_rsqrt(nsq) : T(0);
+        T nrm = nsq * rn;
+        nrm = fma(T(0.5) * rn, fma(-nrm, nrm, nsq), nrm);
+        const T s = t_signum(f) * nrm;                              // :16
+        const T newsq = (nsq + t_abs(f) * nrm) * T(2);              // :19-20
+        const bool some = newsq != T(0);                            // :22
+        const T rd = some ? fast_rsqrt(newsq) : T(0);
+        const T v = some ? ((lane == j ? x + s : xa) * rd) : T(0);  // :17,23 (zero above the pivot row)
+        vstore[j * VP + lane] = some ? v : x;   // a `None` column is left untouched
+        if (lane == j) dg = some ? -s : T(0);                       // :24/26
+        __syncwarp();
+        // 2./3. lanes right of the pivot column: dot + axpy on their register column (reflection.rs:29-30)
+        if (some && lane > j && lane < n) {
+            T vr[32 - RS];
+            if constexpr (sizeof(T) == 4) {   // 16-byte broadcast loads
+#pragma unroll
+                for (int r = RS; r < 32; r += 4) {
+                    const float4 q = *reinterpret_cast<const float4 *>(vstore + j * VP + r);
+                    vr[r - RS] = q.x; vr[r + 1 - RS] = q.y; vr[r + 2 - RS] = q.z; vr[r + 3 - RS] = q.w;
+                }
+            } else {
+#pragma unroll
+                for (int r = RS; r < 32; r += 2) {
+                    const double2 q = *reinterpret_cast<const double2 *>(vstore + j * VP + r);
+                    vr[r - RS] = q.x; vr[r + 1 - RS] = q.y;
+                }
+            }
+            T d0 = T(0), d1 = T(0), d2 = T(0), d3 = T(0);           // four chains: the dot is latency bound
+#pragma unroll
+            for (int r = RS; r < 32; r += 4) {
+                d0 += vr[r - RS] * a[r];
+                d1 += vr[r + 1 - RS] * a[r + 1];
+                d2 += vr[r + 2 - RS] * a[r + 2];
+                d3 += vr[r + 3 - RS] * a[r + 3];
+            }
+            const T fac = T(-2) * ((d0 + d1) + (d2 + d3));
+#pragma unroll
+            for (int r = RS; r < 32; ++r) a[r] += fac * vr[r - RS];
+        }
+    }
+}
 
 template <typename T>
-__global__ void __launch_bounds__(WPB * 32) qr_batched_kernel(T *__restrict__ A, int64_t batch, int m, int n,
-                                                              T *__restrict__ diag) {
-    __shared__ __align__(16) T sv[WPB][32];
+__global__ void __launch_bounds__(wpb<T>() * 32, 2) qr_batched_kernel(T *__restrict__ A, int64_t batch, int m, int n,
+                                                                 T *__restrict__ diag) {
+    constexpr int WPB = wpb<T>();
+    __shared__ __align__(16) T s_col[WPB][32];
+    __shared__ __align__(16) T s_v[WPB][32 * VP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T *colbuf = s_col[warp], *vstore = s_v[warp];
     for (int64_t b = (int64_t)blockIdx.x * WPB + warp; b < batch; b += (int64_t)gridDim.x * WPB) {
         T *mat = A + b * (int64_t)m * n;
         T a[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) a[i] = (i < m && lane < n) ? mat[i * n + lane] : T(0);
-        T mydiag = T(0);
+        T dg = T(0);
+        column_steps<T, 0>(a, colbuf, vstore, lane, n, min(8, n), dg);
+        if (n > 8) column_steps<T, 8>(a, colbuf, vstore, lane, n, min(16, n), dg);
+        if (n > 16) column_steps<T, 16>(a, colbuf, vstore, lane, n, min(24, n), dg);
+        if (n > 24) column_steps<T, 24>(a, colbuf, vstore, lane, n, min(32, n), dg);
+        // sign convention of the reference, applied once: running sign P_r (every lane scans all pivots)
+        T p = T(1), prevp = T(1);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (j < n) {
-                // lane j: reflector of its own column, rows j.. (householder.rs:9-28)
-                T s = T(0), d = T(1);
-                int some = 0;
-                if (lane == j) {
-                    T nsq = T(0);
-#pragma unroll
-                    for (int i = j; i < 32; ++i) nsq += a[i] * a[i];
-                    T nrm = t_sqrt(nsq);
-                    T f = a[j];
-                    s = t_signum(f) * nrm;
-                    T newsq = (nsq + t_abs(f) * nrm) * T(2);
-                    some = newsq != T(0);
-                    d = t_sqrt(newsq);
-                    if (some) {
-                        a[j] = f + s;
-#pragma unroll
-                        for (int i = j; i < 32; ++i) a[i] = a[i] / d;
-                        mydiag = -s;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) sv[warp][i] = (i >= j && i < m) ? a[i] : T(0);
-                }
-                __syncwarp();
-                some = __shfl_sync(0xffffffffu, some, j);
-                const T sg = t_signum(-__shfl_sync(0xffffffffu, s, j));   // signum of the returned pivot
-                if (some && lane > j && lane < n) {
-                    T dot = T(0);
-#pragma unroll
-                    for (int i = j; i < 32; ++i) dot += sv[warp][i] * a[i];
-                    const T fac = T(-2) * dot;                             // reflection.rs:29
-#pragma unroll
-                    for (int i = j; i < 32; ++i) a[i] = sg * (a[i] + fac * sv[warp][i]);   // :30 + householder.rs:48
-                }
-                __syncwarp();
-            }
+        for (int r = 0; r < 32; ++r) {
+            if (lane == r) prevp = p;                               // P_{lane-1}
+            const T br = __shfl_sync(0xffffffffu, dg, r);
+            if (br != T(0)) p = t_signum(br);
+            if (r < lane) a[r] *= p;                                // R[r, lane] *= P_r
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (i < m && lane < n) mat[i * n + lane] = a[i];
-        if (lane < n) diag[b * n + lane] = mydiag;
+        for (int i = 0; i < 32; ++i) {
+            if (i < m && lane < n) {
+                const T val = (i < lane) ? a[i] : prevp * vstore[lane * VP + i];
+                mat[i * n + lane] = val;
+            }
+        }
+        if (lane < n) diag[b * n + lane] = prevp * dg;
+        __syncwarp();
     }
 }
 
@@ -80,7 +152,8 @@ __global__ void __launch_bounds__(WPB * 32) qr_batched_kernel(T *__restrict__ A,
 template <typename T>
 void qr_batched(lfb_handle &h, T *A, int64_t batch, int64_t m, int64_t n, T *diag) {
     if (batch <= 0 || n <= 0) return;
-    int64_t blocks = std::min<int64_t>(cdiv(batch, WPB), (int64_t)h.sm_count * 8);
+    constexpr int WPB = wpb<T>();
+    int64_t blocks = std::min<int64_t>(cdiv(batch, WPB), (int64_t)h.sm_count * 16);
     qr_batched_kernel<T><<<(unsigned)blocks, WPB * 32, 0, h.stream>>>(A, batch, (int)m, (int)n, diag);
     LFB_LAUNCH_CHECK(h);
 }
