@@ -292,6 +292,8 @@ int lfb_destroy(lfb_handle *h) {
     if (!h) return LFB_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    for (auto *s : h->subs) lfb_destroy(s);
+    h->subs.clear();
     for (auto &b : h->blocks) cudaFree(b.p);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -300,6 +302,21 @@ int lfb_destroy(lfb_handle *h) {
     delete h;
     return LFB_OK;
 }
+
+}  // extern "C"
+
+void lfb::lfb_ensure_subs(lfb_handle &h, int n) {
+    while ((int)h.subs.size() < n) {
+        lfb_handle *s = nullptr;
+        if (lfb_create(&s, h.device) != LFB_OK || !s) throw lfb::CudaError(LFB_ERR_CUDA, "could not create a worker handle");
+        s->is_sub = true;
+        s->opt = h.opt;
+        h.subs.push_back(s);
+    }
+    for (auto *s : h.subs) s->opt = h.opt;
+}
+
+extern "C" {
 
 const char *lfb_last_error(lfb_handle *h) { return h ? h->err.c_str() : "null handle"; }
 
@@ -336,6 +353,8 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     else if (k == "panel_cluster") h->opt.panel_cluster = value;
     else if (k == "panel_cluster_max") h->opt.panel_cluster_max = value;
     else if (k == "lookahead") h->opt.lookahead = value;
+    else if (k == "tsqr_chunk") h->opt.tsqr_chunk = value;
+    else if (k == "tsqr_streams") h->opt.tsqr_streams = value;
     else return LFB_INVALID_ARGUMENT;
     return LFB_OK;
 }

@@ -48,6 +48,8 @@ struct Options {
     int64_t panel_cluster = 2; // cluster/DSMEM panel kernel: 2 = second generation, 1 = first, 0 = per-column launches
     int64_t lookahead = 1;     // factor the next panel on a side stream while the trailing update runs
     int64_t panel_cluster_max = 16; // largest cluster size tried (16 is non-portable but supported on B200)
+    int64_t tsqr_chunk = 16384;     // rows per concurrently factored chunk of a tall-skinny block
+    int64_t tsqr_streams = 8;       // chunks in flight (each panel kernel occupies one 16-SM cluster)
 };
 
 }  // namespace lfb
@@ -59,6 +61,8 @@ struct lfb_handle {
     cudaStream_t own_stream = nullptr;  // created by lfb_create
     cudaStream_t aux_stream = nullptr;  // high-priority side stream for look-ahead panel factorisation
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool is_sub = false;                // a worker handle owned by another handle (TSQR chunk pool)
+    std::vector<lfb_handle *> subs;     // created on demand by lfb_ensure_subs
     int sm_count = 148;
     size_t smem_optin = 0;
     std::string err;
@@ -139,6 +143,9 @@ struct DevBuf {
     T *get() const { return p; }
     operator T *() const { return p; }
 };
+
+// Makes sure h.subs holds at least n worker handles (own streams, events, workspace pools).
+void lfb_ensure_subs(lfb_handle &h, int n);
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }

@@ -723,14 +723,45 @@ __global__ void extract_r_kernel(const T *__restrict__ A, int64_t ld, int64_t n,
     }
 }
 
+// Local stage of TSQR.  A tall block is cut into row chunks that fit the cluster panel kernel
+// (tsqr_chunk rows); the chunks are factored CONCURRENTLY on a pool of sub-handles (each chunk's
+// panel kernel occupies one 16-SM cluster, so ~8 chunks fill the GPU), their R factors are stacked
+// and the stack is reduced the same way (a tree inside the GPU).  R of the stack == R of the block.
 template <typename T>
 void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *R, int64_t ldr) {
     if (cols <= 0) return;
-    DevBuf<T> diag(h, cols);
-    qr_factor<T>(h, A, rows, cols, ld, diag);
-    dim3 grid((unsigned)cdiv(cols, 256), ycap(cols));
-    extract_r_kernel<T><<<grid, 256, 0, h.stream>>>(A, ld, cols, diag, R, ldr);
-    LFB_LAUNCH_CHECK(h);
+    const int64_t CH = std::max<int64_t>(h.opt.tsqr_chunk, 2 * cols);
+    if (rows < 2 * CH || h.is_sub) {
+        DevBuf<T> diag(h, cols);
+        qr_factor<T>(h, A, rows, cols, ld, diag);
+        dim3 grid((unsigned)cdiv(cols, 256), ycap(cols));
+        extract_r_kernel<T><<<grid, 256, 0, h.stream>>>(A, ld, cols, diag, R, ldr);
+        LFB_LAUNCH_CHECK(h);
+        return;
+    }
+    const int64_t nch = rows / CH;   // the last chunk absorbs the remainder (< 2 CH rows)
+    const int64_t lds = nch * cols;
+    DevBuf<T> Rstack(h, (size_t)lds * cols);
+    const int NS = (int)std::min<int64_t>(std::max<int64_t>(h.opt.tsqr_streams, 1), nch);
+    lfb_ensure_subs(h, NS);
+    LFB_CUDA(cudaEventRecord(h.ev[4], h.stream));
+    for (int s = 0; s < NS; ++s) LFB_CUDA(cudaStreamWaitEvent(h.subs[s]->stream, h.ev[4], 0));
+    for (int64_t i = 0; i < nch; ++i) {
+        lfb_handle &sub = *h.subs[i % NS];
+        const int64_t r0 = i * CH, nr = (i == nch - 1) ? rows - r0 : CH;
+        DevBuf<T> diag(sub, cols);
+        qr_factor<T>(sub, A + r0, nr, cols, ld, diag);
+        dim3 grid((unsigned)cdiv(cols, 256), ycap(cols));
+        extract_r_kernel<T><<<grid, 256, 0, sub.stream>>>(A + r0, ld, cols, diag, Rstack.get() + i * cols, lds);
+        LFB_LAUNCH_CHECK(sub);
+    }
+    for (int s = 0; s < NS; ++s) {
+        LFB_CUDA(cudaEventRecord(h.subs[s]->ev[5], h.subs[s]->stream));
+        LFB_CUDA(cudaStreamWaitEvent(h.stream, h.subs[s]->ev[5], 0));
+        h.launches += h.subs[s]->launches;
+        h.subs[s]->launches = 0;
+    }
+    tsqr_local_r<T>(h, Rstack, lds, cols, lds, R, ldr);
 }
 
 template <typename T>

@@ -396,3 +396,25 @@ def test_cholesky_4096_properties(L):
     l = L.cholesky(a0)
     assert np.linalg.norm(l @ l.T - a0) <= 8 * n * EPS[np.float64] * np.linalg.norm(a0)
     assert np.max(np.abs(l - np.linalg.cholesky(a0))) <= 8 * n * EPS[np.float64] * np.linalg.norm(a0, 2)
+
+
+# ---- TSQR local stage (device API): chunked tree inside the GPU vs the oracle's R -------------------
+@pytest.mark.parametrize("rows,cols,chunk", [(5000, 32, 1024), (40000, 64, 4096), (70000, 256, 16384), (3000, 48, 16384)])
+def test_tsqr_local_r(L, rows, cols, chunk):
+    import ctypes as C
+    import torch
+    e = L.Engine(0)
+    e.set_option("tsqr_chunk", chunk)
+    a0 = rnd((rows, cols), seed=rows + cols, lo=-1, hi=1)
+    ref = a0.copy(); dref = O.qr(ref); r_ref = O.qr_into_r(ref, dref)
+    A = torch.from_numpy(np.ascontiguousarray(a0.T)).cuda()        # row-major (cols, rows) == column-major rows x cols
+    R = torch.zeros((cols, cols), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    e.set_stream(torch.cuda.current_stream().cuda_stream)
+    st = e.call("lfb_tsqr_local_r_dev_f64", C.c_void_p(A.data_ptr()), rows, cols, rows, C.c_void_p(R.data_ptr()), cols)
+    e._check(st)
+    torch.cuda.synchronize()
+    r = R.t().cpu().numpy()                                          # column-major cols x cols
+    assert np.all(np.diag(r) >= 0) and np.all(np.tril(r, -1) == 0)
+    assert np.max(np.abs(r - r_ref)) <= 64 * cols * EPS[np.float64] * np.linalg.norm(a0, 2) * 8
+    e.close()
