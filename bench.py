@@ -365,25 +365,14 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         # column-major rows x cols block == row-major (cols, rows) tensor
         T0 = torch.rand((cols, rows), dtype=torch.float64, device=dev, generator=gen).mul_(2).sub_(1)
         Tw = torch.empty_like(T0)
-        R = torch.zeros((cols, cols), dtype=torch.float64, device=dev)
-        Rall = torch.zeros((world * cols, cols), dtype=torch.float64, device=dev) if world > 1 else None
-        stack = torch.zeros((cols, world * cols), dtype=torch.float64, device=dev) if world > 1 else None
-        diag = torch.zeros(cols, dtype=torch.float64, device=dev)
+        from linfa_linalg_b200 import dist as D
+        local_r = D.gpu_local_r(eng, Tw, rows, cols)
+        final_r = D.gpu_final_r(eng, cols)
 
         def tsqr_step():
             Tw.copy_(T0)
-            st = lib.lfb_tsqr_local_r_dev_f64(eng.h, C.c_void_p(Tw.data_ptr()), rows, cols, rows, C.c_void_p(R.data_ptr()), cols)
-            if st != 0:
-                raise RuntimeError(f"lfb_tsqr_local_r_dev_f64 status {st}")
-            if world > 1:
-                # R is column-major (cols x cols) == row-major R^T; gather R^T blocks, stack rows of R
-                dist.all_gather_into_tensor(Rall, R)
-                # Rall[g] = R_g^T (row-major).  Column-major stacked matrix [R_0; R_1; ...] (world*cols x cols)
-                # is the row-major tensor of shape (cols, world*cols) whose [:, g*cols:(g+1)*cols] = R_g^T.
-                stack.copy_(Rall.view(world, cols, cols).permute(1, 0, 2).reshape(cols, world * cols))
-                st = lib.lfb_qr_dev_f64(eng.h, C.c_void_p(stack.data_ptr()), world * cols, cols, world * cols, C.c_void_p(diag.data_ptr()))
-                if st != 0:
-                    raise RuntimeError(f"lfb_qr_dev_f64 (stacked R) status {st}")
+            # local R per rank -> one NCCL all_gather of the 256x256 factors -> R of the stack (replicated)
+            D.tsqr_r(local_r, final_r, cols)
         ms = timed(tsqr_step, 2, 1)
         fl = 2.0 * rows_total * cols * cols - 2.0 / 3.0 * cols ** 3
         out["tsqr_f64"] = {"workload": f"TSQR {rows_total}x{cols} f64, {rows} rows per GPU (C4)", "gflops": fl * 2 / (ms * 1e-3) / 1e9,

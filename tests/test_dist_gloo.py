@@ -1,0 +1,86 @@
+"""CPU, world_size 2, gloo: the host-side sharding logic of the two sharded paths.
+The local arithmetic is the oracle here (tests may use it); on the GPU box the same dist.py code path
+runs with the CUDA callables (bench.py extras)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from linfa_linalg_b200 import dist as D
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_shard_range_covers_everything():
+    for total in (0, 1, 7, 262144, 4194304):
+        for world in (1, 2, 3, 8):
+            spans = [D.shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _oracle_r_cm(a):
+    """column-major R (as a row-major torch tensor: R^T) of the numpy matrix a"""
+    import oracle as O
+    w = np.array(a, dtype=np.float64, order="C")
+    d = O.qr(w)
+    return torch.from_numpy(np.ascontiguousarray(O.qr_into_r(w, d).T))
+
+
+def _tsqr_worker(rank, world, port, rows, n, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = np.random.default_rng(7).uniform(-1, 1, (rows, n))
+    b, e = D.shard_range(rows, world, rank)
+    local = full[b:e]
+
+    def final_r(stack):  # stack: (n, world*n) row-major == column-major (world*n) x n
+        return _oracle_r_cm(stack.numpy().T)
+
+    r = D.tsqr_r(lambda: _oracle_r_cm(local), final_r, n)
+    out[rank] = r.numpy().T.copy()
+    # batched path: shards are disjoint and cover the batch
+    bb, be = D.shard_range(1000, world, rank)
+    cnt = torch.tensor([be - bb])
+    dist.all_reduce(cnt)
+    assert int(cnt) == 1000
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_tsqr_two_ranks_matches_single_qr():
+    import oracle as O
+    rows, n, world = 400, 12, 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_tsqr_worker, args=(world, _free_port(), rows, n, out), nprocs=world, join=True)
+    full = np.random.default_rng(7).uniform(-1, 1, (rows, n))
+    w = full.copy()
+    d = O.qr(w)
+    r_ref = O.qr_into_r(w, d)
+    for rank in range(world):
+        r = out[rank]
+        assert np.all(np.diag(r) >= 0) and np.all(np.tril(r, -1) == 0)
+        assert np.max(np.abs(r - r_ref)) <= 64 * n * 2.2e-16 * np.linalg.norm(full, 2)
+
+
+def test_stack_layout():
+    world, n = 3, 4
+    rs = [torch.arange(n * n, dtype=torch.float64).reshape(n, n) + 100 * g for g in range(world)]   # row-major views R_g^T
+    stack = D.stack_r_factors(torch.cat(rs, 0), world, n)
+    # column-major stacked matrix X = [R_0; R_1; R_2]: X[g*n + r, c] == R_g[r, c] == rs[g][c, r]
+    X = stack.t()
+    for g in range(world):
+        assert torch.equal(X[g * n:(g + 1) * n, :], rs[g].t())
