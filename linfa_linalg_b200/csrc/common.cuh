@@ -44,6 +44,7 @@ struct Options {
     int64_t chol_nb = 512;   // right-looking panel width of Cholesky (K of the trailing SYRK)
     int64_t gemm_tma = 1;    // use the TMA-fed DGEMM when operands are 16-byte aligned
     int64_t gemm_splitk = 1; // allow split-K for skinny-output GEMMs
+    int64_t gemm_split_waves = 6; // target waves of (tile, split-K) work items for skinny outputs
     int64_t gemm_v2 = 1;     // 16-warp cp.async DGEMM when operands are 16-byte aligned
     int64_t panel_cluster = 2; // cluster/DSMEM panel kernel: 2 = second generation, 1 = first, 0 = per-column launches
     int64_t lookahead = 1;     // factor the next panel on a side stream while the trailing update runs

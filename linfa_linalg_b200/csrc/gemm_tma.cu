@@ -347,7 +347,9 @@ bool dgemm_tma_try(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int64_t 
     const int64_t tm = cdiv(M, BM), tn = cdiv(N, BN);
     int splits = 1;
     if (h.opt.gemm_splitk && tm * tn < h.sm_count) {
-        int64_t want = cdiv(2 * h.sm_count, tm * tn), maxs = std::max<int64_t>(1, K / (8 * BK));
+        // enough (tile, split) work items for `gemm_split_waves` waves: with one row of tiles (W = V^T C) two
+        // waves of 128 CTAs on 148 SMs waste 14 % to wave quantisation
+        int64_t want = cdiv(h.opt.gemm_split_waves * h.sm_count, tm * tn), maxs = std::max<int64_t>(1, K / (8 * BK));
         splits = (int)std::min(want, maxs);
     }
     p.ksplit = (int)round_up(cdiv(K, splits), BK);

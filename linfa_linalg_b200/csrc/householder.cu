@@ -513,8 +513,26 @@ void build_t(lfb_handle &h, const T *V, int64_t ldv, int64_t rows, int nb, T *G,
                                       (int)(sizeof(T) * (128 * 129 + 65 * 129))));
         cfg = true;
     }
-    tinv_kernel<T><<<1, 512, smem, h.stream>>>(G, nb, nb, Tm, ldt);
+    if (nb <= 128) {
+        tinv_kernel<T><<<1, 512, smem, h.stream>>>(G, nb, nb, Tm, ldt);
+        LFB_LAUNCH_CHECK(h);
+        return;
+    }
+    // nb in (128, 256]: T = [T1, -T1 G12 T2; 0, T2] with T1, T2 from the two diagonal blocks of G
+    const int n1 = 128, n2 = nb - 128;
+    smem = sizeof(T) * (size_t)(128 * 129 + 65 * 129);
+    tinv_kernel<T><<<1, 512, smem, h.stream>>>(G, nb, n1, Tm, ldt);
     LFB_LAUNCH_CHECK(h);
+    tinv_kernel<T><<<1, 512, smem, h.stream>>>(G + n1 + (int64_t)n1 * nb, nb, n2, Tm + n1 + (int64_t)n1 * ldt, ldt);
+    LFB_LAUNCH_CHECK(h);
+    fill<T>(h, Tm + n1, n2, n1, ldt, T(0), T(0));                                                   // T21 = 0
+    T *X = G + n1;   // the (unused) lower-left block of G as scratch: n2 x n1 region holds n1 x n2? no: use rows n1.., cols 0..n1
+    // X (n1 x n2) = T1 * G12 ; stored in a separate column block of G is not possible without clobbering G12,
+    // so write it over G21 (n2 x n1) transposed-free: use ldg = nb with the n1 x n2 product placed at G[0:n1, 0:n2]
+    // (G11 is no longer needed once T1 exists).
+    X = G;
+    gemm<T>(h, 0, 0, n1, n2, n1, T(1), Tm, ldt, G + (int64_t)n1 * nb, nb, T(0), X, nb);                // X = T1 G12
+    gemm<T>(h, 0, 0, n1, n2, n2, T(-1), X, nb, Tm + n1 + (int64_t)n1 * ldt, ldt, T(0), Tm + (int64_t)n1 * ldt, ldt);   // T12 = -X T2
 }
 
 // C (rows x ncols, ldc) <- (I - V op(T) V^T) C,  op(T) = T^T if trans_t.  W1/W2: nb x ncols scratch.
@@ -606,7 +624,7 @@ bool factor_subpanel_cluster(lfb_handle &h, T *A, int64_t ld, int64_t m, int64_t
 // Standard (unscaled) blocked Householder QR of A (m x n, m >= n); beta[n] on device.
 template <typename T>
 static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld, T *beta) {
-    const int NB = (int)std::max<int64_t>(W, std::min<int64_t>(h.opt.qr_nb, 128));
+    const int NB = (int)std::max<int64_t>(W, std::min<int64_t>(h.opt.qr_nb, 256));
     const int SUB = (int)std::max<int64_t>(1, std::min<int64_t>(h.opt.qr_sub, W));
     const int64_t ldv = round_up(m, 2);
     // two generations of the panel workspaces (V, T): with look-ahead panel k+1 is factored while the
