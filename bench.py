@@ -381,6 +381,56 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
                            "ms_per_step": ms / 2, "scaling": "strong", "exchange": "NCCL all_gather of 256x256 R per rank" if world > 1 else "none"}
     except Exception as ex:
         out["tsqr_f64"] = {"error": str(ex)[:200]}
+    # ---- C5a / C5b: phase 1 of eigh (tridiagonalisation + Q) and of SVD (bidiagonalisation); replicas ----
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        n = 8192
+        gen = torch.Generator(device=dev).manual_seed(0x1F2E3D4C + 5 + rank)
+        S0 = torch.rand((n, n), dtype=torch.float64, device=dev, generator=gen).mul_(2).sub_(1)
+        S0 = S0.add_(S0.t().clone()).mul_(0.5)
+        Sw = torch.empty_like(S0)
+        Q = torch.empty_like(S0)
+        off = torch.zeros(n, dtype=torch.float64, device=dev)
+
+        def trd_step():
+            Sw.copy_(S0)
+            st = lib.lfb_sym_tridiagonal_dev_f64(eng.h, C.c_void_p(Sw.data_ptr()), n, n, C.c_void_p(off.data_ptr()))
+            if st != 0:
+                raise RuntimeError(f"lfb_sym_tridiagonal_dev_f64 status {st}")
+
+        def q_step():
+            st = lib.lfb_assemble_q_dev_f64(eng.h, C.c_void_p(Sw.data_ptr()), n, n, n, 1, C.c_void_p(off.data_ptr()), C.c_void_p(Q.data_ptr()), n)
+            if st != 0:
+                raise RuntimeError(f"lfb_assemble_q_dev_f64 status {st}")
+        ms_t = timed(trd_step, 1, 1)
+        ms_q = timed(q_step, 1, 1)
+        fl = 4.0 / 3.0 * n ** 3
+        gemv_bytes = 8.0 * n ** 3 / 3.0       # one full read of the trailing matrix per column
+        out["tridiag_f64"] = {"workload": f"sym_tridiagonal {n}x{n} f64 (C5a phase 1)", "ms": ms_t, "gflops": fl / (ms_t * 1e-3) / 1e9,
+                              "gemv_GBps_lower_bound": gemv_bytes / (ms_t * 1e-3) / 1e9, "hbm_peak_GBps": hbm,
+                              "frac_of_hbm_lower_bound": gemv_bytes / (ms_t * 1e-3) / 1e9 / hbm,
+                              "generate_q_ms": ms_q, "generate_q_gflops": fl / (ms_q * 1e-3) / 1e9}
+        del S0, Sw, Q
+        torch.cuda.empty_cache()
+        m2, n2 = 16384, 4096
+        B0 = torch.rand((n2, m2), dtype=torch.float64, device=dev, generator=gen).mul_(2).sub_(1)   # column-major m2 x n2
+        Bw = torch.empty_like(B0)
+        dd = torch.zeros(n2, dtype=torch.float64, device=dev)
+        ee = torch.zeros(n2, dtype=torch.float64, device=dev)
+
+        def bd_step():
+            Bw.copy_(B0)
+            st = lib.lfb_bidiagonal_dev_f64(eng.h, C.c_void_p(Bw.data_ptr()), m2, n2, m2, C.c_void_p(dd.data_ptr()), C.c_void_p(ee.data_ptr()))
+            if st != 0:
+                raise RuntimeError(f"lfb_bidiagonal_dev_f64 status {st}")
+        ms_b = timed(bd_step, 1, 0)
+        flb = 4.0 * m2 * n2 * n2 - 4.0 / 3.0 * n2 ** 3
+        out["bidiag_f64"] = {"workload": f"bidiagonal {m2}x{n2} f64 (C5b phase 1, BLAS-2 generation)", "ms": ms_b,
+                             "gflops": flb / (ms_b * 1e-3) / 1e9}
+        del B0, Bw
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["tridiag_bidiag"] = {"error": str(ex)[:200]}
     return out
 
 

@@ -1,5 +1,5 @@
-// Two-sided Householder reductions, first (BLAS-2) generation: symmetric tridiagonalisation and
-// Golub-Kahan bidiagonalisation with fused GPU kernels, one reflector at a time, HBM-bound.
+// Golub-Kahan bidiagonalisation, first (BLAS-2) generation: fused GPU kernels, one reflector at a
+// time, HBM-bound.  (The symmetric tridiagonalisation moved to tridiag.cu, blocked.)
 //
 // Replaces src/tridiagonal.rs:31-66 (sym_tridiagonal hot loop :40-60) and src/bidiagonal.rs:27-59
 // (alternating clear_column / clear_row, householder.rs:34-63).  The arithmetic follows the
@@ -156,7 +156,7 @@ void launch_gemv_n(lfb_handle &h, const T *M, int64_t ld, int64_t rows, int64_t 
                    const StepState<T> *st) {
     if (rows <= 0 || cols <= 0) return;
     int64_t rb = cdiv(rows, 128);
-    int64_t splits = std::max<int64_t>(1, std::min<int64_t>(cdiv(4 * h.sm_count, rb), cdiv(cols, 64)));
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>(cdiv(16 * h.sm_count, rb), cdiv(cols, 64)));
     int64_t csplit = cdiv(cols, splits);
     dim3 grid((unsigned)rb, (unsigned)cdiv(cols, csplit));
     gemv_n_kernel<T><<<grid, 128, 0, h.stream>>>(M, ld, rows, cols, x, alpha, y, csplit, st);
@@ -164,26 +164,6 @@ void launch_gemv_n(lfb_handle &h, const T *M, int64_t ld, int64_t rows, int64_t 
 }
 
 }  // namespace
-
-template <typename T>
-void sym_tridiagonal(lfb_handle &h, T *A, int64_t n, int64_t ld, T *off) {
-    if (n <= 1) return;
-    DevBuf<T> v(h, n), p(h, n), w(h, n);
-    DevBuf<StepState<T>> st(h, 1);
-    for (int64_t i = 0; i + 1 < n; ++i) {
-        const int64_t L = n - i - 1;
-        T *x = A + (i + 1) + i * ld;          // axis = A[i+1.., i]
-        T *M = A + (i + 1) + (i + 1) * ld;    // A[i+1.., i+1..]
-        reflector_kernel<T><<<1, 1024, 0, h.stream>>>(x, L, 1, v.get(), off + i, st.get(), p.get(), L);
-        LFB_LAUNCH_CHECK(h);
-        launch_gemv_n<T>(h, M, ld, L, L, v.get(), T(2), p.get(), st.get());          // p = 2 M v  (:49)
-        tri_w_kernel<T><<<1, 1024, 0, h.stream>>>(v.get(), p.get(), w.get(), L, st.get());
-        LFB_LAUNCH_CHECK(h);
-        dim3 grid((unsigned)cdiv(L, 256), ycap(L, 2048));
-        syr2_kernel<T><<<grid, 256, 0, h.stream>>>(M, ld, L, v.get(), w.get(), st.get());
-        LFB_LAUNCH_CHECK(h);
-    }
-}
 
 // One clear_column on the column-major matrix (householder.rs:34-51).
 template <typename T>
@@ -245,7 +225,6 @@ void bidiagonal(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *
 }
 
 #define INST(T)                                                                       \
-    template void sym_tridiagonal<T>(lfb_handle &, T *, int64_t, int64_t, T *);       \
     template void bidiagonal<T>(lfb_handle &, T *, int64_t, int64_t, int64_t, T *, T *);
 INST(float)
 INST(double)
