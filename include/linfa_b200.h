@@ -159,6 +159,10 @@ int lfb_gemm_dev_f32(lfb_handle *h, int ta, int tb, int64_t m, int64_t n, int64_
 int lfb_profile_begin(lfb_handle *h);
 int lfb_profile_end(lfb_handle *h, double *gemm_ms, double *gemm_flops, int64_t *gemm_calls);
 
+/* Debug: first call arms per-phase cycle counters in the cluster panel kernel, later calls read the
+ * counters of the most recent launch (gather, scalars, row pass, reduce+push+barrier). */
+int lfb_debug_panel_phases(lfb_handle *h, long long *out4);
+
 /* ---- micro-benchmarks used by bench.py to measure the FP64 pipe ceiling in the same run ------- */
 /* kind: 0 = DFMA register chain, 1 = DMMA.8x8x4 (mma.sync f64).  Returns achieved GFLOP/s. */
 int lfb_microbench_fp64(lfb_handle *h, int kind, double *gflops);

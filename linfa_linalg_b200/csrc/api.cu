@@ -524,6 +524,17 @@ int lfb_profile_end(lfb_handle *h, double *gemm_ms, double *gemm_flops, int64_t 
     if (gemm_calls) *gemm_calls = (int64_t)(h->prof_used / 2);
     LFB_API_END(h)
 }
+int lfb_debug_panel_phases(lfb_handle *h, long long *out4) {
+    LFB_API_BEGIN(h)
+    if (!h->panel_dbg) {
+        LFB_CUDA(cudaMalloc(&h->panel_dbg, 8 * sizeof(long long)));
+        LFB_CUDA(cudaMemset(h->panel_dbg, 0, 8 * sizeof(long long)));
+    }
+    LFB_CUDA(cudaStreamSynchronize(h->stream));
+    LFB_CUDA(cudaDeviceSynchronize());
+    if (out4) LFB_CUDA(cudaMemcpy(out4, h->panel_dbg, 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+    LFB_API_END(h)
+}
 int lfb_microbench_fp64(lfb_handle *h, int kind, double *gflops) {
     if (!gflops) return LFB_INVALID_ARGUMENT;
     LFB_API_BEGIN(h)

@@ -62,6 +62,7 @@ struct lfb_handle {
     cudaStream_t own_stream = nullptr;  // created by lfb_create
     cudaStream_t aux_stream = nullptr;  // high-priority side stream for look-ahead panel factorisation
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *panel_dbg = nullptr;          // device buffer for the panel kernel's phase counters (debug)
     bool is_sub = false;                // a worker handle owned by another handle (TSQR chunk pool)
     std::vector<lfb_handle *> subs;     // created on demand by lfb_ensure_subs
     int sm_count = 148;

@@ -67,6 +67,7 @@ struct PanelArgs2 {
     T *beta;
     T *V; int64_t ldv, vrow0; int vcol0;
     T *Tout; int ldt;
+    long long *dbg;   // optional: per-phase cycle counters (CTA 0, thread 0), see tools/panel_phases.py
 };
 
 // part[0..32) per lane -> lane l ends with the warp-wide sum of part[l]
@@ -122,9 +123,14 @@ __global__ void __launch_bounds__(NT, 1) hh_panel_cluster3(PanelArgs2<T> p) {
         const T r = warp_transposed_reduce(part, lane);
         red[warp * WMAX + lane] = r;
         __syncthreads();   // also orders this column's slab updates before the head-row read below
-        T s = T(0);
+        T sb[NW];
 #pragma unroll
-        for (int wv = 0; wv < NW; ++wv) s += red[wv * WMAX + lane];
+        for (int wv = 0; wv < NW; ++wv) sb[wv] = red[wv * WMAX + lane];
+#pragma unroll
+        for (int st = 1; st < NW; st <<= 1)
+#pragma unroll
+            for (int wv = 0; wv < NW; wv += 2 * st) sb[wv] += sb[wv + st];
+        const T s = sb[0];
         const int owner = jn / rpc, lrh = jn % rpc;
         const T hval = (b == owner && lane < WD) ? S[(size_t)lane * rpc + lrh] : T(0);
         for (int dst = warp; dst < nc; dst += NW) {   // warp w serves CTAs w, w+8
@@ -145,14 +151,23 @@ __global__ void __launch_bounds__(NT, 1) hh_panel_cluster3(PanelArgs2<T> p) {
     reduce_and_push(0, 0);
 
     unsigned somemask = 0;   // bit k: column k produced a reflection (identical in every thread)
+    long long tph[5] = {0, 0, 0, 0, 0};
+    const bool dbg = p.dbg != nullptr && b == 0 && tid == 0;
     for (int j = 0; j < WD; ++j) {
         const int par = j & 1;
         const int64_t c = p.c0 + j;
+        long long tq0 = dbg ? clock64() : 0;
         // every warp reduces the 16 pushed partials from its own shared memory, in a fixed order
-        T q = T(0);
+        T qb[MAXC];
 #pragma unroll
-        for (int bb = 0; bb < MAXC; ++bb) q += inbox[(par * MAXC + bb) * WMAX + lane];
+        for (int bb = 0; bb < MAXC; ++bb) qb[bb] = inbox[(par * MAXC + bb) * WMAX + lane];
+#pragma unroll
+        for (int st = 1; st < MAXC; st <<= 1)   // fixed pairwise tree: 4 dependent adds instead of 16
+#pragma unroll
+            for (int bb = 0; bb < MAXC; bb += 2 * st) qb[bb] += qb[bb + st];
+        const T q = qb[0];
         const T hd = inhead[par * WMAX + lane];
+        if (dbg) { long long t = clock64(); tph[0] += t - tq0; tq0 = t; }
         const T nsq = __shfl_sync(0xffffffffu, q, j), f = __shfl_sync(0xffffffffu, hd, j);
         const T rn = nsq > T(0) ? fast_rsqrt(nsq) : T(0);
         T nrm = nsq * rn;                                   // householder.rs:13
@@ -169,6 +184,7 @@ __global__ void __launch_bounds__(NT, 1) hh_panel_cluster3(PanelArgs2<T> p) {
         }
         if (some) somemask |= 1u << j;
         __syncwarp();
+        if (dbg) { long long t = clock64(); tph[1] += t - tq0; tq0 = t; }
         const T *fac = facw + warp * WMAX;
         // ---- one pass over the slab, two consecutive rows per lane ----
 #pragma unroll
@@ -196,24 +212,44 @@ __global__ void __launch_bounds__(NT, 1) hh_panel_cluster3(PanelArgs2<T> p) {
             }
             const T mx = (has_next && gr > c) ? n1.x : T(0);
             const T my = (has_next && gr + 1 > c && lr + 1 < nrows) ? n1.y : T(0);
+            // Chunks of 8 columns: ALL loads of a chunk are issued before any store.  (Interleaving
+            // "load column k, update, store column k" serialises on the store->load ordering of the
+            // same shared array: measured 3800 cycles per pass instead of ~500.)
 #pragma unroll
-            for (int k = 0; k < WD; ++k) {
-                V2 a;
-                if (k == j) { a.x = v.x; a.y = v.y; }
-                else if (k == j + 1) a = n1;
-                else {
-                    a = *reinterpret_cast<const V2 *>(S + (size_t)k * rpc + lr);
-                    if (k > j && some) {
-                        a.x += fac[k] * vx;
-                        a.y += fac[k] * vy;
-                        *reinterpret_cast<V2 *>(S + (size_t)k * rpc + lr) = a;
+            for (int k0 = 0; k0 < WD; k0 += 8) {
+                V2 a[8];
+                T fk[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k = k0 + q;
+                    a[q] = *reinterpret_cast<const V2 *>(S + (size_t)k * rpc + lr);
+                    fk[q] = fac[k];
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k = k0 + q;
+                    if (k == j) { a[q].x = v.x; a[q].y = v.y; }
+                    else if (k == j + 1) a[q] = n1;
+                    else if (k > j && some) {
+                        a[q].x += fk[q] * vx;
+                        a[q].y += fk[q] * vy;
+                    }
+                    part[k] += a[q].x * mx + a[q].y * my;
+                }
+                if (some) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int k = k0 + q;
+                        if (k > j + 1) *reinterpret_cast<V2 *>(S + (size_t)k * rpc + lr) = a[q];
                     }
                 }
-                part[k] += a.x * mx + a.y * my;
             }
         }
+        if (dbg) { long long t = clock64(); tph[2] += t - tq0; tq0 = t; }
         if (has_next) reduce_and_push(par ^ 1, j + 1);
+        if (dbg) { long long t = clock64(); tph[3] += t - tq0; tq0 = t; }
     }
+    if (dbg) for (int q = 0; q < 4; ++q) p.dbg[q] = tph[q];
     __syncthreads();
 
     // ---- write back: A (in place), staged V, and T (CTA 0) ----
@@ -306,6 +342,7 @@ bool factor_subpanel_cluster2(lfb_handle &h, T *A, int64_t ld, int64_t m, int64_
     PanelArgs2<T> p;
     p.A = A; p.ld = ld; p.m = m; p.c0 = c0; p.rpc = (int)rpc; p.beta = beta;
     p.V = V; p.ldv = ldv; p.vrow0 = vrow0; p.vcol0 = vcol0; p.Tout = Tout; p.ldt = ldt;
+    p.dbg = (long long *)h.panel_dbg;
     const size_t smem = sizeof(T) * (size_t)(rpc * w) + extra;
     bool ok = false;
     switch (w) {
