@@ -395,6 +395,7 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     else if (k == "panel_cluster_max") h->opt.panel_cluster_max = value;
     else if (k == "lookahead") h->opt.lookahead = value;
     else if (k == "tsqr_chunk") h->opt.tsqr_chunk = value;
+    else if (k == "batched_quad") h->opt.batched_quad = value;
     else if (k == "tsqr_streams") h->opt.tsqr_streams = value;
     else return LFB_INVALID_ARGUMENT;
     return LFB_OK;

@@ -147,11 +147,148 @@ __global__ void __launch_bounds__(wpb<T>() * 32, 2) qr_batched_kernel(T *__restr
     }
 }
 
+
+// ---- f32, four matrices per warp ------------------------------------------------------------------
+// ncu on the one-matrix-per-warp kernel: issue bound, 5.2k warp instructions per matrix of which only
+// 1.3k are FMAs -- the per-column overhead (publish, reduce, scalars, broadcast) is paid by a whole
+// warp for one matrix.  Here a matrix belongs to 8 lanes; lane g keeps columns g, g+8, g+16, g+24 in
+// registers (interleaved so the triangular work stays balanced), so every overhead instruction serves
+// four matrices and the FMA share rises to ~60 %.
+template <int Q>   // column slot of the pivot column: j = 8*Q + jj, rows RS = 8*Q .. 31 are live
+__device__ __forceinline__ void column_steps4(float (&a)[4][32], float *colbuf, float *vbuf, int g, int n, float (&dg)[4]) {
+    constexpr int RS = 8 * Q;
+    const unsigned gmask = 0xffu << (threadIdx.x & 24);   // the 8 lanes of this matrix
+    for (int jj = 0; jj < 8; ++jj) {
+        const int j = RS + jj;
+        if (j >= n) break;   // n is matrix-uniform and warp-uniform
+        if (g == jj) {
+#pragma unroll
+            for (int r = RS; r < 32; r += 4)
+                *reinterpret_cast<float4 *>(colbuf + r) = make_float4(a[Q][r], a[Q][r + 1], a[Q][r + 2], a[Q][r + 3]);
+        }
+        __syncwarp();
+        // norm over rows >= j: lane g sums rows g, g+8, g+16, g+24
+        float nsq = 0.f, xs[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int r = g + 8 * t;
+            xs[t] = (r >= RS) ? colbuf[r] : 0.f;
+            if (r >= j) nsq += xs[t] * xs[t];
+        }
+        nsq += __shfl_xor_sync(gmask, nsq, 1);
+        nsq += __shfl_xor_sync(gmask, nsq, 2);
+        nsq += __shfl_xor_sync(gmask, nsq, 4);
+        const float f = colbuf[j];
+        const float rn = nsq > 0.f ? rsqrtf(nsq) : 0.f;
+        float nrm = nsq * rn;                                        // householder.rs:13
+        nrm = fmaf(0.5f * rn, fmaf(-nrm, nrm, nsq), nrm);
+        const float s = (signbit(f) ? -1.f : 1.f) * nrm;             // :16
+        const float newsq = (nsq + fabsf(f) * nrm) * 2.f;            // :19-20
+        const bool some = newsq != 0.f;                              // :22
+        const float rd = some ? rsqrtf(newsq) : 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int r = g + 8 * t;
+            if (r >= RS) vbuf[r] = (some && r >= j) ? ((r == j ? xs[t] + s : xs[t]) * rd) : 0.f;   // :17,23
+        }
+        if (g == jj) dg[Q] = some ? -s : 0.f;                        // :24/26
+        __syncwarp();
+        if (some) {
+            float vr[32 - RS];
+#pragma unroll
+            for (int r = RS; r < 32; r += 4) {
+                const float4 q4 = *reinterpret_cast<const float4 *>(vbuf + r);
+                vr[r - RS] = q4.x; vr[r + 1 - RS] = q4.y; vr[r + 2 - RS] = q4.z; vr[r + 3 - RS] = q4.w;
+            }
+#pragma unroll
+            for (int qq = Q; qq < 4; ++qq) {
+                const int c = 8 * qq + g;
+                if (c == j) {                    // the pivot column keeps v (rows >= j), R entries above stay
+#pragma unroll
+                    for (int r = RS; r < 32; ++r) a[qq][r] = (r >= j) ? vr[r - RS] : a[qq][r];
+                } else if (c > j && c < n) {     // reflection.rs:29-30
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                    for (int r = RS; r < 32; r += 4) {
+                        d0 += vr[r - RS] * a[qq][r];
+                        d1 += vr[r + 1 - RS] * a[qq][r + 1];
+                        d2 += vr[r + 2 - RS] * a[qq][r + 2];
+                        d3 += vr[r + 3 - RS] * a[qq][r + 3];
+                    }
+                    const float fac = -2.f * ((d0 + d1) + (d2 + d3));
+#pragma unroll
+                    for (int r = RS; r < 32; ++r) a[qq][r] += fac * vr[r - RS];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128, 2) qr_batched4_kernel(float *__restrict__ A, int64_t batch, int m, int n, float *__restrict__ diag) {
+    __shared__ __align__(16) float s_col[4][4][32];
+    __shared__ __align__(16) float s_v[4][4][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane & 7, grp = lane >> 3;
+    float *colbuf = s_col[warp][grp], *vbuf = s_v[warp][grp];
+    const unsigned gmask = 0xffu << (lane & 24);
+    const int64_t nquads = (batch + 3) / 4;
+    for (int64_t qd = (int64_t)blockIdx.x * 4 + warp; qd < nquads; qd += (int64_t)gridDim.x * 4) {
+        const int64_t b = qd * 4 + grp;
+        const bool live = b < batch;
+        float *mat = A + (live ? b : 0) * (int64_t)m * n;
+        float a[4][32];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[q][i] = (live && i < m && 8 * q + g < n) ? mat[i * n + 8 * q + g] : 0.f;
+        float dg[4] = {0.f, 0.f, 0.f, 0.f};
+        column_steps4<0>(a, colbuf, vbuf, g, n, dg);
+        if (n > 8) column_steps4<1>(a, colbuf, vbuf, g, n, dg);
+        if (n > 16) column_steps4<2>(a, colbuf, vbuf, g, n, dg);
+        if (n > 24) column_steps4<3>(a, colbuf, vbuf, g, n, dg);
+        // reference sign convention, applied once: running sign P_r over the pivots of this matrix
+        float p = 1.f, prev[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (8 * q + g == r) prev[q] = p;                                 // P_{c-1}
+            const float br = __shfl_sync(gmask, dg[r >> 3], (lane & 24) + (r & 7));
+            if (br != 0.f) p = signbit(br) ? -1.f : 1.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (r < 8 * q + g) a[q][r] *= p;                                 // R[r, c] *= P_r
+        }
+        if (live) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = 8 * q + g;
+                if (c < n) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < m) mat[i * n + c] = (i < c) ? a[q][i] : prev[q] * a[q][i];
+                    diag[b * n + c] = prev[q] * dg[q];
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 template <typename T>
 void qr_batched(lfb_handle &h, T *A, int64_t batch, int64_t m, int64_t n, T *diag) {
     if (batch <= 0 || n <= 0) return;
+    if constexpr (sizeof(T) == 4) {
+        if (h.opt.batched_quad) {
+            int64_t blocks4 = std::min<int64_t>(cdiv(cdiv(batch, 4), 4), (int64_t)h.sm_count * 16);
+            qr_batched4_kernel<<<(unsigned)blocks4, 128, 0, h.stream>>>(A, batch, (int)m, (int)n, diag);
+            LFB_LAUNCH_CHECK(h);
+            return;
+        }
+    }
     constexpr int WPB = wpb<T>();
     int64_t blocks = std::min<int64_t>(cdiv(batch, WPB), (int64_t)h.sm_count * 16);
     qr_batched_kernel<T><<<(unsigned)blocks, WPB * 32, 0, h.stream>>>(A, batch, (int)m, (int)n, diag);

@@ -49,6 +49,7 @@ struct Options {
     int64_t panel_cluster = 2; // cluster/DSMEM panel kernel: 2 = second generation, 1 = first, 0 = per-column launches
     int64_t lookahead = 1;     // factor the next panel on a side stream while the trailing update runs
     int64_t panel_cluster_max = 16; // largest cluster size tried (16 is non-portable but supported on B200)
+    int64_t batched_quad = 1;       // f32 batched QR: four matrices per warp
     int64_t tsqr_chunk = 16384;     // rows per concurrently factored chunk of a tall-skinny block
     int64_t tsqr_streams = 8;       // chunks in flight (each panel kernel occupies one 16-SM cluster)
 };
