@@ -31,6 +31,7 @@ SIGNATURES = {
     "lfb_launch_count": [_vp],
     "lfb_set_option": [_vp, C.c_char_p, _i64],
     "lfb_microbench_fp64": [_vp, _int, C.POINTER(_dbl)],
+    "lfb_microbench_kernel": [_vp, C.c_char_p, _i64, _int, C.POINTER(_dbl)],
     "lfb_debug_panel_phases": [_vp, C.POINTER(C.c_longlong)],
     "lfb_profile_begin": [_vp],
     "lfb_profile_end": [_vp, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_i64)],

@@ -397,6 +397,10 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     else if (k == "tsqr_chunk") h->opt.tsqr_chunk = value;
     else if (k == "batched_quad") h->opt.batched_quad = value;
     else if (k == "tsqr_streams") h->opt.tsqr_streams = value;
+    else if (k == "trd_fused") h->opt.trd_fused = value;
+    else if (k == "bd_blocked") h->opt.bd_blocked = value;
+    else if (k == "trd_profile") h->opt.trd_profile = value;
+    else if (k == "trd_symv_async") h->opt.trd_symv_async = value;
     else return LFB_INVALID_ARGUMENT;
     return LFB_OK;
 }
@@ -540,6 +544,16 @@ int lfb_microbench_fp64(lfb_handle *h, int kind, double *gflops) {
     if (!gflops) return LFB_INVALID_ARGUMENT;
     LFB_API_BEGIN(h)
     *gflops = microbench_fp64(*h, kind);
+    LFB_API_END(h)
+}
+
+int lfb_microbench_kernel(lfb_handle *h, const char *name, int64_t n, int reps, double *us_per_launch) {
+    if (!us_per_launch || !name || n < 2 || reps < 1) return LFB_INVALID_ARGUMENT;
+    LFB_API_BEGIN(h)
+    const std::string k(name);
+    if (k == "trd_symv") *us_per_launch = microbench_trd(*h, 0, n, reps);
+    else if (k == "trd_head") *us_per_launch = microbench_trd(*h, 1, n, reps);
+    else return fail(h, LFB_INVALID_ARGUMENT, "unknown kernel name");
     LFB_API_END(h)
 }
 

@@ -203,7 +203,7 @@ static void clear_row_dev(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64
 }
 
 template <typename T>
-void bidiagonal(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *d, T *e) {
+void bidiagonal_unblocked(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *d, T *e) {
     const int64_t md = std::min(rows, cols);
     if (md <= 0) return;
     const int64_t mx = std::max(rows, cols);
@@ -225,7 +225,7 @@ void bidiagonal(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *
 }
 
 #define INST(T)                                                                       \
-    template void bidiagonal<T>(lfb_handle &, T *, int64_t, int64_t, int64_t, T *, T *);
+    template void bidiagonal_unblocked<T>(lfb_handle &, T *, int64_t, int64_t, int64_t, T *, T *);
 INST(float)
 INST(double)
 #undef INST

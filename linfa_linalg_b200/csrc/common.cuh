@@ -51,6 +51,10 @@ struct Options {
     int64_t panel_cluster_max = 16; // largest cluster size tried (16 is non-portable but supported on B200)
     int64_t batched_quad = 1;       // f32 batched QR: four matrices per warp
     int64_t tsqr_chunk = 16384;     // rows per concurrently factored chunk of a tall-skinny block
+    int64_t trd_fused = 1;          // tridiagonalisation: cluster head kernel + lower-triangle SYMV (0 = first generation)
+    int64_t trd_symv_async = 1;     // SYMV tiles staged through shared memory with cp.async (0 = direct register loads)
+    int64_t trd_profile = 0;        // debug: events around every tridiagonalisation launch, summary on stderr
+    int64_t bd_blocked = 1;         // bidiagonalisation: blocked (deferred rank-1 updates); 0 = one reflector at a time
     int64_t tsqr_streams = 8;       // chunks in flight (each panel kernel occupies one 16-SM cluster)
 };
 
@@ -178,5 +182,6 @@ template <typename T> void qr_batched(lfb_handle &h, T *A, int64_t batch, int64_
 template <typename T> void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *R, int64_t ldr);
 template <typename T> void triangular_zero(lfb_handle &h, T *A, int64_t n, int64_t ld, int keep_lower);
 double microbench_fp64(lfb_handle &h, int kind);
+double microbench_trd(lfb_handle &h, int kind, int64_t n, int reps);
 
 }  // namespace lfb

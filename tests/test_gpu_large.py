@@ -50,3 +50,73 @@ def test_qr_lookahead_matches_no_lookahead():
     assert np.max(np.abs(a1 - a2)) <= 64 * m * EPS * np.linalg.norm(a0)
     assert np.max(np.abs(d1 - d2)) <= 64 * m * EPS * np.linalg.norm(a0)
     e1.close(); e2.close()
+
+
+@pytest.mark.parametrize("n", [777, 1100, 2500])
+def test_tridiagonal_large_vs_oracle_and_first_generation(n):
+    """The cluster head kernel + lower-triangle SYMV path (several 512-row cluster blocks, interior and
+    diagonal SYMV tiles, odd/even n) against the oracle (tridiagonal.rs:31-66) and the per-launch path."""
+    import linfa_linalg_b200 as L
+    import oracle as O
+    g = np.random.default_rng(n).uniform(-1, 1, (n, n))
+    a0 = (g + g.T) / 2
+    t = 64 * n * EPS * np.linalg.norm(a0)
+    a2 = a0.copy()
+    dec = L.sym_tridiagonal(a2)
+    e1 = L.Engine(0)
+    e1.set_option("trd_fused", 0)
+    a1 = a0.copy()
+    dec1 = L.sym_tridiagonal(a1, e1)
+    e1.close()
+    assert np.max(np.abs(np.tril(a2) - np.tril(a1))) <= t
+    assert np.max(np.abs(dec.off_diagonal - dec1.off_diagonal)) <= t
+    e3 = L.Engine(0)
+    e3.set_option("trd_symv_async", 0)           # register-staged SYMV tiles instead of cp.async
+    a3 = a0.copy()
+    dec3 = L.sym_tridiagonal(a3, e3)
+    e3.close()
+    assert np.max(np.abs(np.tril(a3) - np.tril(a1))) <= t
+    assert np.max(np.abs(dec3.off_diagonal - dec1.off_diagonal)) <= t
+    if n <= 1100:
+        ref = a0.copy(); offr = O.sym_tridiagonal(ref)
+        assert np.max(np.abs(np.tril(a2) - np.tril(ref))) <= t
+        assert np.max(np.abs(dec.off_diagonal - offr)) <= t
+    dec = L.sym_tridiagonal(a0.copy())
+    q = dec.generate_q(); tri = dec.into_tridiag_matrix()
+    assert np.linalg.norm(q @ tri @ q.T - a0) <= 64 * n * EPS * np.linalg.norm(a0)
+    assert np.linalg.norm(q @ q.T - np.eye(n)) <= 64 * n * EPS
+
+
+@pytest.mark.parametrize("shape", [(700, 300), (300, 700), (1500, 1101), (2600, 640)])
+def test_bidiagonal_blocked_vs_oracle_and_unblocked(shape):
+    """Blocked bidiagonalisation (cluster head kernels, cp.async GEMV tiles, deferred rank-1 updates, several
+    panels, odd sizes, the transposed wide case) against the oracle (bidiagonal.rs:27-59) and the one-reflector-
+    at-a-time path; the running sign of householder.rs:45-48 must come out elementwise."""
+    import linfa_linalg_b200 as L
+    import oracle as O
+    m, n = shape
+    a0 = np.random.default_rng(m * 7 + n).uniform(-1, 1, shape)
+    t = 64 * max(shape) * EPS * np.linalg.norm(a0)
+    a2 = a0.copy()
+    dec = L.bidiagonal(a2)
+    e1 = L.Engine(0)
+    e1.set_option("bd_blocked", 0)
+    a1 = a0.copy()
+    dec1 = L.bidiagonal(a1, e1)
+    e1.close()
+    assert np.max(np.abs(a2 - a1)) <= t
+    assert np.max(np.abs(dec.diagonal - dec1.diagonal)) <= t
+    assert np.max(np.abs(dec.off_diagonal - dec1.off_diagonal)) <= t
+    if max(shape) <= 1500:
+        ref = a0.copy(); dr, er = O.bidiagonal(ref)
+        assert np.max(np.abs(a2 - ref)) <= t
+        assert np.max(np.abs(dec.diagonal - dr)) <= t
+        assert np.max(np.abs(dec.off_diagonal - er)) <= t
+    dec = L.bidiagonal(a0.copy())
+    u = dec.generate_u(); vt = dec.generate_vt(); b = dec.into_b()
+    md = min(shape)
+    eb = 64 * max(shape) * EPS
+    assert np.linalg.norm((u.T @ u if m >= n else u @ u.T) - np.eye(md)) <= eb
+    assert np.linalg.norm(vt @ vt.T - np.eye(md)) <= eb
+    assert np.linalg.norm(u @ b @ vt - a0) <= eb * np.linalg.norm(a0)
+    assert np.all(b >= 0)
