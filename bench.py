@@ -426,7 +426,7 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
             Tw.copy_(T0)
             # local R per rank -> one NCCL all_gather of the 256x256 factors -> R of the stack (replicated)
             D.tsqr_r(local_r, final_r, cols)
-        ms = timed(tsqr_step, 2, 1)
+        ms = timed(tsqr_step, 2, 2)
         fl = 2.0 * rows_total * cols * cols - 2.0 / 3.0 * cols ** 3
         out["tsqr_f64"] = {"workload": f"TSQR {rows_total}x{cols} f64, {rows} rows per GPU (C4)", "gflops": fl * 2 / (ms * 1e-3) / 1e9,
                            "ms_per_step": ms / 2, "scaling": "strong", "exchange": "NCCL all_gather of 256x256 R per rank" if world > 1 else "none"}
@@ -456,10 +456,14 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         ms_t = timed(trd_step, 1, 1)
         ms_q = timed(q_step, 1, 1)
         fl = 4.0 / 3.0 * n ** 3
-        gemv_bytes = 8.0 * n ** 3 / 3.0       # one full read of the trailing matrix per column
+        symv_bytes = 4.0 * n ** 3 / 3.0       # ONE read of the lower triangle of the trailing matrix per column
+        us_symv = C.c_double(0)
+        lib.lfb_microbench_kernel(eng.h, b"trd_symv", n, 50, C.byref(us_symv))       # the SYMV alone, back to back, at the full size
         out["tridiag_f64"] = {"workload": f"sym_tridiagonal {n}x{n} f64 (C5a phase 1)", "ms": ms_t, "gflops": fl / (ms_t * 1e-3) / 1e9,
-                              "gemv_GBps_lower_bound": gemv_bytes / (ms_t * 1e-3) / 1e9, "hbm_peak_GBps": hbm,
-                              "frac_of_hbm_lower_bound": gemv_bytes / (ms_t * 1e-3) / 1e9 / hbm,
+                              "symv_GBps_lower_bound": symv_bytes / (ms_t * 1e-3) / 1e9, "hbm_peak_GBps": hbm,
+                              "frac_of_hbm_lower_bound": symv_bytes / (ms_t * 1e-3) / 1e9 / hbm,
+                              "symv_kernel_at_n": {"us": us_symv.value, "GBps": 4.0 * n * n / max(us_symv.value, 1e-9) / 1e3,
+                                                   "frac_of_hbm": 4.0 * n * n / max(us_symv.value, 1e-9) / 1e3 / hbm},
                               "generate_q_ms": ms_q, "generate_q_gflops": fl / (ms_q * 1e-3) / 1e9}
         del S0, Sw, Q
         torch.cuda.empty_cache()
@@ -476,8 +480,16 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
                 raise RuntimeError(f"lfb_bidiagonal_dev_f64 status {st}")
         ms_b = timed(bd_step, 1, 0)
         flb = 4.0 * m2 * n2 * n2 - 4.0 / 3.0 * n2 ** 3
-        out["bidiag_f64"] = {"workload": f"bidiagonal {m2}x{n2} f64 (C5b phase 1, BLAS-2 generation)", "ms": ms_b,
-                             "gflops": flb / (ms_b * 1e-3) / 1e9}
+        gemv_bytes = 16.0 * (m2 * n2 * n2 / 2.0 - n2 ** 3 / 6.0)   # two streaming passes per column/row pair
+        us_n, us_t = C.c_double(0), C.c_double(0)
+        lib.lfb_microbench_kernel(eng.h, b"bd_gemv_n", n2, 50, C.byref(us_n))     # the GEMVs alone at the full 16384 x 4096 size
+        lib.lfb_microbench_kernel(eng.h, b"bd_gemv_t", n2, 50, C.byref(us_t))
+        full = 8.0 * m2 * n2
+        out["bidiag_f64"] = {"workload": f"bidiagonal {m2}x{n2} f64 (C5b phase 1, blocked: deferred rank-1 updates)", "ms": ms_b,
+                             "gflops": flb / (ms_b * 1e-3) / 1e9, "gemv_GBps_lower_bound": gemv_bytes / (ms_b * 1e-3) / 1e9,
+                             "hbm_peak_GBps": hbm, "frac_of_hbm_lower_bound": gemv_bytes / (ms_b * 1e-3) / 1e9 / hbm,
+                             "gemv_kernels_at_full_size": {"n_us": us_n.value, "n_GBps": full / max(us_n.value, 1e-9) / 1e3,
+                                                           "t_us": us_t.value, "t_GBps": full / max(us_t.value, 1e-9) / 1e3}}
         del B0, Bw
         torch.cuda.empty_cache()
     except Exception as ex:

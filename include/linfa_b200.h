@@ -167,7 +167,8 @@ int lfb_debug_panel_phases(lfb_handle *h, long long *out4);
 /* kind: 0 = DFMA register chain, 1 = DMMA.8x8x4 (mma.sync f64).  Returns achieved GFLOP/s. */
 int lfb_microbench_fp64(lfb_handle *h, int kind, double *gflops);
 /* Device time (us per launch, CUDA events, back-to-back launches) of one internal kernel on an n x n f64
- * problem: "trd_symv" (lower-triangle SYMV of the tridiagonalisation), "trd_head" (its cluster kernel). */
+ * problem: "trd_symv" (lower-triangle SYMV of the tridiagonalisation), "trd_head" (its cluster kernel),
+ * "bd_gemv_n" / "bd_gemv_t" (streaming GEMVs of the bidiagonalisation on a 4n x n matrix). */
 int lfb_microbench_kernel(lfb_handle *h, const char *name, int64_t n, int reps, double *us_per_launch);
 
 #ifdef __cplusplus

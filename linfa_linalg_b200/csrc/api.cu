@@ -332,6 +332,8 @@ int lfb_destroy(lfb_handle *h) {
     if (!h) return LFB_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    h->drop_graphs();
+    for (auto &e : h->ev_graph) if (e) cudaEventDestroy(e);
     for (auto *s : h->subs) lfb_destroy(s);
     h->subs.clear();
     for (auto &b : h->blocks) cudaFree(b.p);
@@ -397,6 +399,7 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     else if (k == "tsqr_chunk") h->opt.tsqr_chunk = value;
     else if (k == "batched_quad") h->opt.batched_quad = value;
     else if (k == "tsqr_streams") h->opt.tsqr_streams = value;
+    else if (k == "tsqr_graph") h->opt.tsqr_graph = value;
     else if (k == "trd_fused") h->opt.trd_fused = value;
     else if (k == "bd_blocked") h->opt.bd_blocked = value;
     else if (k == "trd_profile") h->opt.trd_profile = value;
@@ -553,6 +556,8 @@ int lfb_microbench_kernel(lfb_handle *h, const char *name, int64_t n, int reps, 
     const std::string k(name);
     if (k == "trd_symv") *us_per_launch = microbench_trd(*h, 0, n, reps);
     else if (k == "trd_head") *us_per_launch = microbench_trd(*h, 1, n, reps);
+    else if (k == "bd_gemv_n") *us_per_launch = microbench_bd_gemv(*h, 0, 4 * n, n, reps);   // the 4:1 aspect of configs[4]
+    else if (k == "bd_gemv_t") *us_per_launch = microbench_bd_gemv(*h, 1, 4 * n, n, reps);
     else return fail(h, LFB_INVALID_ARGUMENT, "unknown kernel name");
     LFB_API_END(h)
 }

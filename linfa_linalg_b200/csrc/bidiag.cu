@@ -488,6 +488,40 @@ bool bidiagonal_tall(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld, T *d
 
 }  // namespace
 
+// Device time (us per launch, CUDA events, back to back) of the streaming GEMV of the bidiagonalisation on an
+// m x n matrix: kind 0 = x_raw = B u (row sums), 1 = y_raw = B^T v (column sums).
+double microbench_bd_gemv(lfb_handle &h, int kind, int64_t m, int64_t n, int reps) {
+    using T = double;
+    const int64_t ld = round_up(m, 2);
+    DevBuf<T> A(h, (size_t)ld * n), x(h, std::max(ld, n) + 2), y(h, std::max(ld, n) + 2);
+    DevBuf<BdState<T>> st(h, 1);
+    LFB_CUDA(cudaMemsetAsync(A.get(), 0, sizeof(T) * ld * n, h.stream));
+    LFB_CUDA(cudaMemsetAsync(x.get(), 0, sizeof(T) * (std::max(ld, n) + 2), h.stream));
+    LFB_CUDA(cudaMemsetAsync(y.get(), 0, sizeof(T) * (std::max(ld, n) + 2), h.stream));
+    BdState<T> hs;
+    memset(&hs, 0, sizeof hs);
+    hs.some = 1;
+    LFB_CUDA(cudaMemcpyAsync(st.get(), &hs, sizeof hs, cudaMemcpyHostToDevice, h.stream));
+    const int *some = reinterpret_cast<const int *>(reinterpret_cast<char *>(st.get()) + offsetof(BdState<T>, some));
+    cudaEvent_t e0, e1;
+    LFB_CUDA(cudaEventCreate(&e0));
+    LFB_CUDA(cudaEventCreate(&e1));
+    auto once = [&]() {
+        if (kind == 0) launch_gemv<T, 0>(h, A.get(), ld, m, n, 1, 1, x.get(), T(1), y.get(), some);
+        else launch_gemv<T, 1>(h, A.get(), ld, m, n, 0, 1, x.get(), T(1), y.get(), some);
+    };
+    for (int r = 0; r < 3; ++r) once();
+    LFB_CUDA(cudaEventRecord(e0, h.stream));
+    for (int r = 0; r < reps; ++r) once();
+    LFB_CUDA(cudaEventRecord(e1, h.stream));
+    LFB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    LFB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return (double)ms * 1e3 / reps;
+}
+
 // bidiagonal.rs:27-59.  A: rows x cols column-major; d (min(rows, cols)) and e (min - 1) get the signed
 // pivots, A the reflectors, exactly as the reference leaves them.
 template <typename T>

@@ -50,12 +50,14 @@ struct Options {
     int64_t lookahead = 1;     // factor the next panel on a side stream while the trailing update runs
     int64_t panel_cluster_max = 16; // largest cluster size tried (16 is non-portable but supported on B200)
     int64_t batched_quad = 1;       // f32 batched QR: four matrices per warp
-    int64_t tsqr_chunk = 16384;     // rows per concurrently factored chunk of a tall-skinny block
+    int64_t tsqr_chunk = 12288;     // rows per concurrently factored chunk (12288 x 32 f64 is the widest sub-panel a 16-CTA cluster holds)
     int64_t trd_fused = 1;          // tridiagonalisation: cluster head kernel + lower-triangle SYMV (0 = first generation)
     int64_t trd_symv_async = 1;     // SYMV tiles staged through shared memory with cp.async (0 = direct register loads)
     int64_t trd_profile = 0;        // debug: events around every tridiagonalisation launch, summary on stderr
     int64_t bd_blocked = 1;         // bidiagonalisation: blocked (deferred rank-1 updates); 0 = one reflector at a time
     int64_t tsqr_streams = 8;       // chunks in flight (each panel kernel occupies one 16-SM cluster)
+    int64_t tsqr_graph = 0;         // 1: replay the local TSQR stage of a (buffer, shape) seen before as one CUDA graph
+                                    // (measured: 145 vs 147 ms -- the stage is GPU bound, not launch bound -- so off by default)
 };
 
 }  // namespace lfb
@@ -80,6 +82,19 @@ struct lfb_handle {
     struct Block { void *p; size_t bytes; bool used; };
     std::vector<Block> blocks;
     void *pinned = nullptr; size_t pinned_bytes = 0;
+
+    // ---- CUDA graphs of launch-bound multi-stream stages (TSQR local stage), keyed by buffer and shape ----
+    struct GraphEntry {
+        const void *a; const void *r; int64_t rows, cols, ld, ldr, chunk, streams; size_t elem;
+        cudaGraphExec_t exec; int64_t launches;
+    };
+    std::vector<GraphEntry> graphs;
+    bool in_capture = false;
+    cudaEvent_t ev_graph[2] = {nullptr, nullptr};
+    void drop_graphs() {
+        for (auto &g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+        graphs.clear();
+    }
 
     // ---- optional GEMM profiler (bench.py roofline): CUDA events around every GEMM launch ----
     bool prof_on = false;
@@ -122,6 +137,8 @@ struct lfb_handle {
         for (auto &b : blocks) if (b.p == p) { b.used = false; return; }
     }
     void trim() {
+        drop_graphs();   // captured graphs hold pointers into the pool
+        for (auto *sub : subs) sub->trim();
         std::vector<Block> keep;
         for (auto &b : blocks) { if (b.used) keep.push_back(b); else cudaFree(b.p); }
         blocks.swap(keep);
@@ -183,5 +200,6 @@ template <typename T> void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64
 template <typename T> void triangular_zero(lfb_handle &h, T *A, int64_t n, int64_t ld, int keep_lower);
 double microbench_fp64(lfb_handle &h, int kind);
 double microbench_trd(lfb_handle &h, int kind, int64_t n, int reps);
+double microbench_bd_gemv(lfb_handle &h, int kind, int64_t m, int64_t n, int reps);
 
 }  // namespace lfb

@@ -746,17 +746,7 @@ __global__ void extract_r_kernel(const T *__restrict__ A, int64_t ld, int64_t n,
 // panel kernel occupies one 16-SM cluster, so ~8 chunks fill the GPU), their R factors are stacked
 // and the stack is reduced the same way (a tree inside the GPU).  R of the stack == R of the block.
 template <typename T>
-void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *R, int64_t ldr) {
-    if (cols <= 0) return;
-    const int64_t CH = std::max<int64_t>(h.opt.tsqr_chunk, 2 * cols);
-    if (rows < 2 * CH || h.is_sub) {
-        DevBuf<T> diag(h, cols);
-        qr_factor<T>(h, A, rows, cols, ld, diag);
-        dim3 grid((unsigned)cdiv(cols, 256), ycap(cols));
-        extract_r_kernel<T><<<grid, 256, 0, h.stream>>>(A, ld, cols, diag, R, ldr);
-        LFB_LAUNCH_CHECK(h);
-        return;
-    }
+static void tsqr_local_chunks(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *R, int64_t ldr, int64_t CH) {
     const int64_t nch = rows / CH;   // the last chunk absorbs the remainder (< 2 CH rows)
     const int64_t lds = nch * cols;
     DevBuf<T> Rstack(h, (size_t)lds * cols);
@@ -779,8 +769,97 @@ void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T
         h.launches += h.subs[s]->launches;
         h.subs[s]->launches = 0;
     }
-    tsqr_local_r<T>(h, Rstack, lds, cols, lds, R, ldr);
+    const bool prev = h.in_capture;   // the stacked R factors are an internal buffer: no graph cache entry for them
+    h.in_capture = true;
+    try {
+        tsqr_local_r<T>(h, Rstack, lds, cols, lds, R, ldr);
+    } catch (...) {
+        h.in_capture = prev;
+        throw;
+    }
+    h.in_capture = prev;
 }
+
+template <typename T>
+void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *R, int64_t ldr) {
+    if (cols <= 0) return;
+    const int64_t CH = std::max<int64_t>(h.opt.tsqr_chunk, 2 * cols);
+    if (rows < 2 * CH || h.is_sub) {
+        DevBuf<T> diag(h, cols);
+        qr_factor<T>(h, A, rows, cols, ld, diag);
+        dim3 grid((unsigned)cdiv(cols, 256), ycap(cols));
+        extract_r_kernel<T><<<grid, 256, 0, h.stream>>>(A, ld, cols, diag, R, ldr);
+        LFB_LAUNCH_CHECK(h);
+        return;
+    }
+    cudaStream_t user = h.stream;
+    if (!h.opt.tsqr_graph || h.in_capture || h.prof_on) {
+        tsqr_local_chunks<T>(h, A, rows, cols, ld, R, ldr, CH);
+        return;
+    }
+    // Option tsqr_graph: the chunked stage is thousands of short launches on several streams; the second call with
+    // the same buffers and shape captures it into a CUDA graph and later calls replay it (one launch from the
+    // host).  Measured on B200: 145 ms replayed vs 147 ms launched -- the stage is bound by the panel cluster
+    // kernels and the skinny GEMMs on the GPU, not by the host -- so the option is off by default.  A NULL
+    // (legacy) user stream cannot be captured: the graph then runs on the handle's own stream, fenced against
+    // the legacy stream on both sides.
+    lfb_handle::GraphEntry *ent = nullptr;
+    for (auto &g : h.graphs)
+        if (g.a == A && g.r == R && g.rows == rows && g.cols == cols && g.ld == ld && g.ldr == ldr && g.chunk == CH &&
+            g.streams == h.opt.tsqr_streams && g.elem == sizeof(T))
+            ent = &g;
+    if (!ent) {
+        h.graphs.push_back({A, R, rows, cols, ld, ldr, CH, h.opt.tsqr_streams, sizeof(T), nullptr, 0});
+        tsqr_local_chunks<T>(h, A, rows, cols, ld, R, ldr, CH);
+        return;
+    }
+    cudaStream_t cs = user ? user : h.own_stream;
+    if (!user) {
+        if (!h.ev_graph[0]) {
+            LFB_CUDA(cudaEventCreateWithFlags(&h.ev_graph[0], cudaEventDisableTiming));
+            LFB_CUDA(cudaEventCreateWithFlags(&h.ev_graph[1], cudaEventDisableTiming));
+        }
+        LFB_CUDA(cudaEventRecord(h.ev_graph[0], user));
+        LFB_CUDA(cudaStreamWaitEvent(cs, h.ev_graph[0], 0));
+    }
+    if (!ent->exec) {
+        const int64_t l0 = h.launches;
+        cudaGraph_t graph = nullptr;
+        h.stream = cs;
+        h.in_capture = true;
+        LFB_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+        try {
+            tsqr_local_chunks<T>(h, A, rows, cols, ld, R, ldr, CH);
+        } catch (...) {
+            cudaStreamEndCapture(cs, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            h.stream = user;
+            h.in_capture = false;
+            throw;
+        }
+        h.stream = user;
+        h.in_capture = false;
+        LFB_CUDA(cudaStreamEndCapture(cs, &graph));
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t ge = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ge != cudaSuccess) {
+            cudaGetLastError();
+            throw CudaError(LFB_ERR_CUDA, std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ge));
+        }
+        ent->exec = exec;
+        ent->launches = h.launches - l0;
+    } else {
+        h.launches += ent->launches;
+    }
+    LFB_CUDA(cudaGraphLaunch(ent->exec, cs));
+    if (!user) {
+        LFB_CUDA(cudaEventRecord(h.ev_graph[1], cs));
+        LFB_CUDA(cudaStreamWaitEvent(user, h.ev_graph[1], 0));
+    }
+}
+
 
 template <typename T>
 void assemble_q(lfb_handle &h, const T *M, int64_t rows, int64_t cols, int64_t ld, int64_t shift, const T *signs, T *Q,

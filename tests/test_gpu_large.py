@@ -120,3 +120,39 @@ def test_bidiagonal_blocked_vs_oracle_and_unblocked(shape):
     assert np.linalg.norm(vt @ vt.T - np.eye(md)) <= eb
     assert np.linalg.norm(u @ b @ vt - a0) <= eb * np.linalg.norm(a0)
     assert np.all(b >= 0)
+
+
+@pytest.mark.parametrize("use_stream", [False, True])
+def test_tsqr_local_graph_replay(use_stream):
+    """The chunked TSQR stage is captured into a CUDA graph on the second call with the same buffers and
+    replayed afterwards (legacy NULL stream: fenced onto the handle's own stream); every call must give the
+    oracle's R for the data that is in the buffer at that time."""
+    import ctypes as C
+    import torch
+    import linfa_linalg_b200 as L
+    import oracle as O
+    rows, cols, chunk = 36000, 64, 4096
+    e = L.Engine(0)
+    e.set_option("tsqr_chunk", chunk)
+    e.set_option("tsqr_graph", 1)
+    A = torch.empty((cols, rows), dtype=torch.float64, device="cuda")       # column-major rows x cols
+    R = torch.zeros((cols, cols), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.Stream() if use_stream else torch.cuda.current_stream()
+    e.set_stream(stream.cuda_stream)
+    l_prev = None
+    with torch.cuda.stream(stream):
+        for it in range(4):
+            a0 = np.random.default_rng(100 + it).uniform(-1, 1, (rows, cols))
+            A.copy_(torch.from_numpy(np.ascontiguousarray(a0.T)), non_blocking=False)
+            l0 = e.launch_count
+            st = e.call("lfb_tsqr_local_r_dev_f64", C.c_void_p(A.data_ptr()), rows, cols, rows, C.c_void_p(R.data_ptr()), cols)
+            e._check(st)
+            stream.synchronize()
+            nl = e.launch_count - l0
+            assert nl > 0 and (l_prev is None or nl == l_prev)
+            l_prev = nl
+            r = R.t().cpu().numpy()
+            ref = a0.copy(); dref = O.qr(ref); r_ref = O.qr_into_r(ref, dref)
+            assert np.all(np.diag(r) >= 0) and np.all(np.tril(r, -1) == 0)
+            assert np.max(np.abs(r - r_ref)) <= 64 * cols * EPS * np.linalg.norm(a0, 2) * 8
+    e.close()

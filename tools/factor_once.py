@@ -15,8 +15,12 @@ m = int(sys.argv[3]) if len(sys.argv) > 3 else n
 eng = L.Engine(0)
 lib = eng.lib
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
+warm = 1
 for k, v in (a.split("=") for a in sys.argv[4:]):
-    eng.set_option(k, int(v))
+    if k == "warm":
+        warm = int(v)
+    else:
+        eng.set_option(k, int(v))
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(1)
 p = lambda t: C.c_void_p(t.data_ptr())
@@ -58,7 +62,8 @@ elif kind == "batched":
     d = torch.zeros((n, 32), dtype=torch.float32, device=dev)
     step = lambda: (W.copy_(A), lib.lfb_qr_batched_dev_f32(eng.h, p(W), n, 32, 32, p(d)))
     flops = n * 43690.7
-step()
+for _ in range(warm):
+    step()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 l0 = eng.launch_count

@@ -18,4 +18,5 @@ us = C.c_double(0)
 st = eng.lib.lfb_microbench_kernel(eng.h, name.encode(), n, reps, C.byref(us))
 assert st == 0, eng.lib.lfb_last_error(eng.h)
 print(f"{name} n={n} {' '.join(a for a in sys.argv[3:] if '=' in a)}: {us.value:.2f} us per launch"
-      + (f", {4.0 * n * n / us.value / 1e3:.0f} GB/s of lower-triangle traffic" if name == "trd_symv" else ""))
+      + (f", {4.0 * n * n / us.value / 1e3:.0f} GB/s of lower-triangle traffic" if name == "trd_symv" else "")
+      + (f", {8.0 * 4 * n * n / us.value / 1e3:.0f} GB/s" if name.startswith("bd_gemv") else ""))
