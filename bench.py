@@ -465,7 +465,22 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
                               "symv_kernel_at_n": {"us": us_symv.value, "GBps": 4.0 * n * n / max(us_symv.value, 1e-9) / 1e3,
                                                    "frac_of_hbm": 4.0 * n * n / max(us_symv.value, 1e-9) / 1e3 / hbm},
                               "generate_q_ms": ms_q, "generate_q_gflops": fl / (ms_q * 1e-3) / 1e9}
-        del S0, Sw, Q
+        # eigh end to end (eigh.rs:10-129): scale, tridiagonalise, Q, implicit-QR Givens phase (host recurrence,
+        # rotations applied on the device 16 sweeps per pass); eigenvalues land in host memory
+        vals = np.zeros(n)
+
+        def eigh_step():
+            Sw.copy_(S0)
+            st = lib.lfb_eigh_dev_f64(eng.h, C.c_void_p(Sw.data_ptr()), n, n, C.c_void_p(vals.ctypes.data), C.c_void_p(Q.data_ptr()), n)
+            if st != 0:
+                raise RuntimeError(f"lfb_eigh_dev_f64 status {st}")
+        barrier()
+        t0 = time.perf_counter(); eigh_step(); torch.cuda.synchronize(); t_eigh = time.perf_counter() - t0
+        Qt = Q.t()                                  # torch sees the column-major Q transposed
+        resid = float((S0 @ Qt - Qt * torch.from_numpy(vals).to(dev)[None, :]).norm() / S0.norm())
+        out["eigh_f64"] = {"workload": f"eigh {n}x{n} f64, eigenvalues + eigenvectors (C5a end to end)", "ms": t_eigh * 1e3,
+                           "relative_residual": resid, "timing": "wall clock around one call (host recurrence inside)"}
+        del S0, Sw, Q, Qt
         torch.cuda.empty_cache()
         m2, n2 = 16384, 4096
         B0 = torch.rand((n2, m2), dtype=torch.float64, device=dev, generator=gen).mul_(2).sub_(1)   # column-major m2 x n2

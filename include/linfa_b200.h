@@ -114,6 +114,18 @@ int lfb_solve_triangular_f32(lfb_handle *h, const float *a, int64_t a_rows, int6
 int lfb_triangular_inplace_f64(lfb_handle *h, double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int uplo);
 int lfb_triangular_inplace_f32(lfb_handle *h, float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int uplo);
 
+/* ---- eigh.rs:202-268 EighInto / Eigh / EigValshInto / EigValsh (symmetric_eig, eigh.rs:10-129) ---------
+ * a: n x n view (only read; the reference consumes `self`, nothing of it is observable afterwards).
+ * vals: n contiguous entries, in the reference's own (unsorted) order -- EigSort stays host-side.
+ * vecs: n x n view that receives the eigenvectors as columns, or NULL for eigvalsh (no Q is formed).
+ * Scale by max|a|, tridiagonalise and generate Q on the device; the scalar implicit-QR recurrence of
+ * eigh.rs:51-128 runs on the host and its Givens rotations are applied to Q on the device, eight sweeps per
+ * pass.  Returns LFB_NOT_SQUARE like check_square (lib.rs:64-71); n = 0 is legal. */
+int lfb_eigh_f64(lfb_handle *h, const double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                 double *vals, double *vecs, int64_t vrs, int64_t vcs);
+int lfb_eigh_f32(lfb_handle *h, const float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                 float *vals, float *vecs, int64_t vrs, int64_t vcs);
+
 /* ---- tridiagonal.rs:31-66 sym_tridiagonal ---------------------------------------------------- */
 /* In place: diag(a) becomes the tridiagonal's diagonal, a[i+1.., i] the reflectors; off (n-1) gets
  * the SIGNED off-diagonal (TridiagonalDecomp, :71-77).  n == 0 -> LFB_EMPTY_MATRIX. */
@@ -141,6 +153,8 @@ int lfb_cholesky_dev_f32(lfb_handle *h, float *d_a, int64_t n, int64_t ld, int c
 int lfb_assemble_q_dev_f64(lfb_handle *h, const double *d_m, int64_t rows, int64_t cols, int64_t ld,
                            int64_t shift, const double *d_signs, double *d_q, int64_t ldq);
 int lfb_sym_tridiagonal_dev_f64(lfb_handle *h, double *d_a, int64_t n, int64_t ld, double *d_off);
+/* d_a (n x n column-major, consumed) -> vals_host (n, HOST memory), d_q (n x n device, or NULL). */
+int lfb_eigh_dev_f64(lfb_handle *h, double *d_a, int64_t n, int64_t ld, double *vals_host, double *d_q, int64_t ldq);
 int lfb_bidiagonal_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_d, double *d_e);
 /* batched: d_a is [batch][m][n] row-major packed (the ndarray layout), in place */
 int lfb_qr_batched_dev_f32(lfb_handle *h, float *d_a, int64_t batch, int64_t m, int64_t n, float *d_diag);

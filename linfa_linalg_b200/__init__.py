@@ -25,6 +25,7 @@ __all__ = [
     "solvec", "solvec_into", "solvec_inplace", "invc", "invc_inplace",
     "solve_triangular", "solve_triangular_into", "solve_triangular_inplace", "triangular_inplace", "into_triangular",
     "is_triangular", "sym_tridiagonal", "TridiagonalDecomp", "bidiagonal", "BidiagonalDecomp",
+    "eigh", "eigh_into", "eigvalsh", "eigvalsh_into", "sort_eig", "sort_eig_asc", "sort_eig_desc", "LARGEST", "SMALLEST",
 ]
 
 
@@ -427,6 +428,62 @@ def sym_tridiagonal(a: np.ndarray, eng=None) -> TridiagonalDecomp:
     st = e.call("lfb_sym_tridiagonal" + _sfx(a), *_view(a), _vecp(obuf))
     e._check(st)
     return TridiagonalDecomp(a, off, e)
+
+
+# ---- eigh: src/eigh.rs ------------------------------------------------------------------------------
+LARGEST, SMALLEST = "largest", "smallest"   # lib.rs:77-80 Order
+
+
+def _eigh(a: np.ndarray, vectors: bool, e: Engine):
+    n = _check_square(a)
+    vals = np.zeros(n, dtype=a.dtype)
+    vecs = np.zeros((n, n), dtype=a.dtype) if vectors else None
+    if n == 0:                                  # eigh.rs:16-25
+        return vals, vecs
+    vv = (_vecp(vecs), vecs.strides[0] // vecs.itemsize, vecs.strides[1] // vecs.itemsize) if vectors else (None, 0, 0)
+    st = e.call("lfb_eigh" + _sfx(a), *_view(a), _vecp(vals), *vv)
+    e._check(st)
+    return vals, vecs
+
+
+def eigh_into(a: np.ndarray, eng=None):
+    """eigh.rs:211-219 EighInto::eigh_into -> (eigenvalues in the reference's order, eigenvectors as columns)."""
+    return _eigh(a, True, eng or engine())
+
+
+def eigh(a, eng=None):
+    """eigh.rs:231-238 Eigh::eigh (works on a copy, like `to_owned()`)."""
+    return eigh_into(_owned(a), eng)
+
+
+def eigvalsh_into(a: np.ndarray, eng=None) -> np.ndarray:
+    """eigh.rs:249-255 EigValshInto::eigvalsh_into (no Q is formed)."""
+    return _eigh(a, False, eng or engine())[0]
+
+
+def eigvalsh(a, eng=None) -> np.ndarray:
+    """eigh.rs:266-272 EigValsh::eigvalsh."""
+    return eigvalsh_into(_owned(a), eng)
+
+
+def sort_eig(res, order=SMALLEST):
+    """eigh.rs:275-325 EigSort (host-side, as in the reference): a stable sort of the eigenvalues, columns of the
+    eigenvector matrix permuted alike.  `res` is an eigenvalue array or an (eigenvalues, eigenvectors) pair."""
+    vals, vecs = (res, None) if isinstance(res, np.ndarray) else res
+    if np.isnan(vals).any():
+        raise ValueError("NaN values in array")          # cmp_floats panics
+    idx = np.argsort(-vals if order == LARGEST else vals, kind="stable")
+    if vecs is None:
+        return vals[idx]
+    return vals[idx], np.ascontiguousarray(vecs[:, idx])
+
+
+def sort_eig_asc(res):
+    return sort_eig(res, SMALLEST)
+
+
+def sort_eig_desc(res):
+    return sort_eig(res, LARGEST)
 
 
 # ---- bidiagonal: src/bidiagonal.rs ---------------------------------------------------------------

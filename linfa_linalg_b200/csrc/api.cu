@@ -263,6 +263,22 @@ int sym_tridiagonal_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_
 }
 
 template <typename T>
+int eigh_host(lfb_handle *h, const T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *vals, T *vecs, int64_t vrs,
+              int64_t vcs) {
+    if (rows != cols) return fail(h, LFB_NOT_SQUARE, "Matrix is not square");                 // eigh.rs:15 (check_square)
+    if (rows > 0 && !vals) return fail(h, LFB_INVALID_ARGUMENT, "vals is null");
+    const int64_t n = rows;
+    if (n == 0) return LFB_OK;                                                                // :16-25
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(n, 2);
+    DevBuf<T> dA(*h, (size_t)ld * n), dQ(*h, vecs ? (size_t)ld * n : 1);
+    upload<T>(*h, a, n, n, rs, cs, dA, ld);
+    symmetric_eig<T>(*h, dA, n, ld, vals, vecs ? dQ.get() : nullptr, ld);
+    if (vecs) download<T>(*h, dQ, ld, vecs, n, n, vrs, vcs);
+    LFB_API_END(h)
+}
+
+template <typename T>
 int bidiagonal_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *d, T *e) {
     const int64_t md = std::min(rows, cols);
     if (md <= 0) return fail(h, LFB_EMPTY_MATRIX, "Matrix is empty");                         // bidiagonal.rs:30-32
@@ -401,6 +417,10 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     else if (k == "tsqr_streams") h->opt.tsqr_streams = value;
     else if (k == "tsqr_graph") h->opt.tsqr_graph = value;
     else if (k == "trd_fused") h->opt.trd_fused = value;
+    else if (k == "rot_staged") h->opt.rot_staged = value;
+    else if (k == "eigh_stable_2x2") h->opt.eigh_stable_2x2 = value;
+    else if (k == "rot_serial") h->opt.rot_serial = value;
+    else if (k == "fast_hypot") h->opt.fast_hypot = value;
     else if (k == "bd_blocked") h->opt.bd_blocked = value;
     else if (k == "trd_profile") h->opt.trd_profile = value;
     else if (k == "trd_symv_async") h->opt.trd_symv_async = value;
@@ -438,6 +458,8 @@ int lfb_triangular_inplace_f64(lfb_handle *h, double *a, int64_t r, int64_t c, i
 int lfb_triangular_inplace_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, int uplo) { return triangular_inplace_host<float>(h, a, r, c, rs, cs, uplo); }
 int lfb_sym_tridiagonal_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *off) { return sym_tridiagonal_host<double>(h, a, r, c, rs, cs, off); }
 int lfb_sym_tridiagonal_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *off) { return sym_tridiagonal_host<float>(h, a, r, c, rs, cs, off); }
+int lfb_eigh_f64(lfb_handle *h, const double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *vals, double *vecs, int64_t vrs, int64_t vcs) { return eigh_host<double>(h, a, r, c, rs, cs, vals, vecs, vrs, vcs); }
+int lfb_eigh_f32(lfb_handle *h, const float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *vals, float *vecs, int64_t vrs, int64_t vcs) { return eigh_host<float>(h, a, r, c, rs, cs, vals, vecs, vrs, vcs); }
 int lfb_bidiagonal_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *d, double *e) { return bidiagonal_host<double>(h, a, r, c, rs, cs, d, e); }
 int lfb_bidiagonal_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *d, float *e) { return bidiagonal_host<float>(h, a, r, c, rs, cs, d, e); }
 int lfb_qr_batched_f32(lfb_handle *h, float *a, int64_t batch, int64_t m, int64_t n, float *diag) { return qr_batched_host<float>(h, a, batch, m, n, diag); }
@@ -477,6 +499,12 @@ int lfb_sym_tridiagonal_dev_f64(lfb_handle *h, double *d_a, int64_t n, int64_t l
     if (n < 1) return fail(h, LFB_EMPTY_MATRIX, "Matrix is empty");
     LFB_API_BEGIN(h)
     sym_tridiagonal<double>(*h, d_a, n, ld, d_off);
+    LFB_API_END(h)
+}
+int lfb_eigh_dev_f64(lfb_handle *h, double *d_a, int64_t n, int64_t ld, double *vals_host, double *d_q, int64_t ldq) {
+    if (n < 0 || (n > 0 && !vals_host)) return fail(h, LFB_INVALID_ARGUMENT, "bad arguments");
+    LFB_API_BEGIN(h)
+    symmetric_eig<double>(*h, d_a, n, ld, vals_host, d_q, ldq);
     LFB_API_END(h)
 }
 int lfb_bidiagonal_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_d, double *d_e) {

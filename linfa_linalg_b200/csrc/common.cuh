@@ -55,6 +55,10 @@ struct Options {
     int64_t trd_symv_async = 1;     // SYMV tiles staged through shared memory with cp.async (0 = direct register loads)
     int64_t trd_profile = 0;        // debug: events around every tridiagonalisation launch, summary on stderr
     int64_t bd_blocked = 1;         // bidiagonalisation: blocked (deferred rank-1 updates); 0 = one reflector at a time
+    int64_t rot_staged = 1;         // Givens wavefront: coefficients staged through shared memory with cp.async
+    int64_t rot_serial = 0;         // debug: one chain per pass
+    int64_t eigh_stable_2x2 = 1;    // eigh.rs:111 basis without cancellation (0 = the reference's formula verbatim)
+    int64_t fast_hypot = 1;         // host recurrence: sqrt(x^2 + y^2) instead of hypot when far from underflow
     int64_t tsqr_streams = 8;       // chunks in flight (each panel kernel occupies one 16-SM cluster)
     int64_t tsqr_graph = 0;         // 1: replay the local TSQR stage of a (buffer, shape) seen before as one CUDA graph
                                     // (measured: 145 vs 147 ms -- the stage is GPU bound, not launch bound -- so off by default)
@@ -195,6 +199,8 @@ template <typename T> void trsm_left(lfb_handle &h, int lower, int trans, int64_
                                      const T *ext_diag, T *B, int64_t ldb);
 template <typename T> void sym_tridiagonal(lfb_handle &h, T *A, int64_t n, int64_t ld, T *off);
 template <typename T> void bidiagonal(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *d, T *e);
+// eigh.rs:10-129: dA consumed; vals is a HOST array (reference order); dQ device n x n or nullptr.
+template <typename T> void symmetric_eig(lfb_handle &h, T *dA, int64_t n, int64_t ld, T *vals, T *dQ, int64_t ldq);
 template <typename T> void qr_batched(lfb_handle &h, T *A, int64_t batch, int64_t m, int64_t n, T *diag);
 template <typename T> void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *R, int64_t ldr);
 template <typename T> void triangular_zero(lfb_handle &h, T *A, int64_t n, int64_t ld, int keep_lower);

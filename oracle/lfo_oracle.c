@@ -8,7 +8,8 @@
  * triangular hot path of rust-ml/linfa-linalg v0.2.1:
  *   src/householder.rs:9-93, src/reflection.rs:26-37, src/qr.rs:32-44,91-120,
  *   src/cholesky.rs:51-83, src/triangular.rs:37-53,95-144,
- *   src/tridiagonal.rs:31-66, src/bidiagonal.rs:27-59.
+ *   src/tridiagonal.rs:31-66, src/bidiagonal.rs:27-59, and (for the end-to-end eigh parity of the
+ *   Givens phase) src/eigh.rs:10-199 with src/givens.rs:12-106.
  * The Rust crate itself cannot be built in this image (no rustc/cargo), so
  * parity is PINNED against the reference's own known-answer tests instead
  * (tests/test_oracle_kat.py reproduces every KAT listed in SURVEY.md 8c) and
@@ -25,21 +26,25 @@
 #define SFX _f64
 #define SQRT sqrt
 #define FABS fabs
+#define HYPOT hypot
 #include "lfo_impl.inc"
 #undef T
 #undef SFX
 #undef SQRT
 #undef FABS
+#undef HYPOT
 
 #define T float
 #define SFX _f32
 #define SQRT sqrtf
 #define FABS fabsf
+#define HYPOT hypotf
 #include "lfo_impl.inc"
 #undef T
 #undef SFX
 #undef SQRT
 #undef FABS
+#undef HYPOT
 
 /* Batched thin QR over `batch` packed row-major m x n matrices (the reference has no batched
  * entry point: this is qr.rs:32-44 in a loop, as a caller would write it). */

@@ -219,3 +219,23 @@ def qr_batched(a: np.ndarray) -> np.ndarray:
     f.restype = None
     f(_p(a), _i(batch), _i(m), _i(n), _p(diag))
     return diag
+
+
+def symmetric_eig(a: np.ndarray, vectors: bool = True, eps=None):
+    """eigh.rs:10-129 (symmetric_eig): `a` is consumed; returns (vals, vecs or None) in the reference's own
+    (unsorted) order, eigenvectors as columns."""
+    n = a.shape[0]
+    if a.shape[0] != a.shape[1]:
+        raise ValueError("NotSquare")
+    vals = np.zeros(n, dtype=a.dtype)
+    if n < 1:
+        return vals, (np.zeros((0, 0), dtype=a.dtype) if vectors else None)
+    q = np.zeros((n, n), dtype=a.dtype) if vectors else np.zeros((1, 1), dtype=a.dtype)
+    off = np.zeros(n, dtype=a.dtype)
+    work = np.zeros(n, dtype=a.dtype)
+    e = np.finfo(a.dtype).eps if eps is None else eps
+    f = getattr(lib(), "lfo_symmetric_eig" + _sfx(a))
+    f.restype = None
+    f(_p(a), _i(n), _i(_es(a, 0)), _i(_es(a, 1)), C.c_int(1 if vectors else 0), _ct(a)(e),
+      _p(vals), _p(q), _i(_es(q, 0)), _i(_es(q, 1)), _p(off), _p(work))
+    return vals, (q if vectors else None)

@@ -18,7 +18,7 @@ def _declared():
 def test_header_declares_both_scalar_families():
     names = _declared()
     for base in ("lfb_qr", "lfb_assemble_q", "lfb_qt_mul", "lfb_cholesky", "lfb_solve_triangular",
-                 "lfb_sym_tridiagonal", "lfb_bidiagonal"):
+                 "lfb_sym_tridiagonal", "lfb_bidiagonal", "lfb_eigh"):
         assert base + "_f32" in names and base + "_f64" in names
 
 
@@ -65,3 +65,22 @@ def test_shape_errors_raised_before_any_device_work():
         L.bidiagonal(np.zeros((0, 0)), eng=object())
     with pytest.raises(L.WrongRows):
         L.solve_triangular_inplace(np.eye(2), np.zeros((1, 2)), L.UPPER, eng=object())
+    with pytest.raises(L.NotSquare):                                     # eigh.rs:15 check_square
+        L.eigh(np.zeros((2, 3)), eng=object())
+    vals, vecs = L.eigh(np.zeros((0, 0)), eng=object())                  # eigh.rs:16-25 / :411-420 corner
+    assert vals.shape == (0,) and vecs.shape == (0, 0)
+    assert L.eigvalsh(np.zeros((0, 0)), eng=object()).shape == (0,)
+
+
+def test_sort_eig_host_side():
+    """eigh.rs:275-325 EigSort."""
+    import numpy as np
+    import linfa_linalg_b200 as L
+    vals = np.array([3.0, -1.0, 2.0])
+    vecs = np.arange(9.0).reshape(3, 3)
+    v, q = L.sort_eig_asc((vals, vecs))
+    np.testing.assert_array_equal(v, [-1, 2, 3])
+    np.testing.assert_array_equal(q, vecs[:, [1, 2, 0]])
+    np.testing.assert_array_equal(L.sort_eig_desc(vals), [3, 2, -1])
+    with pytest.raises(ValueError):
+        L.sort_eig(np.array([1.0, np.nan]))

@@ -156,3 +156,18 @@ def test_tsqr_local_graph_replay(use_stream):
             assert np.all(np.diag(r) >= 0) and np.all(np.tril(r, -1) == 0)
             assert np.max(np.abs(r - r_ref)) <= 64 * cols * EPS * np.linalg.norm(a0, 2) * 8
     e.close()
+
+
+def test_eigh_1500_properties():
+    """eigh.rs end to end at a size where the rotation wavefront runs many passes: eigenvalues against LAPACK,
+    residual and orthogonality (tests/eigh.rs:10-27)."""
+    import linfa_linalg_b200 as L
+    n = 1500
+    g = np.random.default_rng(11).uniform(-1, 1, (n, n))
+    a0 = (g + g.T) / 2
+    vals, vecs = L.eigh(a0)
+    s = np.linalg.norm(a0, 2)
+    assert np.max(np.abs(np.sort(vals) - np.linalg.eigvalsh(a0))) <= 64 * n * EPS * s
+    assert np.linalg.norm(a0 @ vecs - vecs * vals[None, :]) <= 64 * n * EPS * s
+    assert np.linalg.norm(vecs.T @ vecs - np.eye(n)) <= 64 * n * EPS
+    assert np.max(np.abs(np.sort(L.eigvalsh(a0)) - np.sort(vals))) <= 64 * n * EPS * s

@@ -334,6 +334,52 @@ def test_tridiagonal_parity(L, n, dt):
     L.sym_tridiagonal(rnd((n, n), dt, seed=1)).generate_q()                    # non-symmetric must not crash
 
 
+# ---- eigh (tridiagonalisation + Givens phase, src/eigh.rs) -----------------------------------------
+def test_eigh_kats(L):  # src/eigh.rs:357-409, tests/eigh.rs:59-65
+    vals = L.eigvalsh(np.array([[6.0, 2], [2, 6]]))
+    np.testing.assert_allclose(vals, [8, 4], atol=1e-12)
+    vals = L.eigvalsh(np.array([[1.0, -5, 7], [-5, 2, -9], [7, -9, 3]]))
+    np.testing.assert_allclose(L.sort_eig_asc(vals), [-6.86819, -3.41558, 16.28378], atol=1e-5)
+    for a, exp in (([[3.0, 1, 1], [1, 3, 1], [1, 1, 3]], [5, 2, 2]), ([[6.0, 2], [2, 6]], [8, 4]),
+                   ([[1.0, -5, 7], [-5, 2, -9], [7, -9, 3]], [16.28378, -3.41558, -6.86819])):
+        a = np.array(a)
+        vals, vecs = L.sort_eig_desc(L.eigh(a))
+        np.testing.assert_allclose(vals, exp, atol=1e-5)
+        np.testing.assert_allclose(vecs.T @ vecs, np.eye(len(exp)), atol=1e-5)
+        np.testing.assert_allclose(a @ vecs, vecs * vals[None, :], atol=1e-5)
+    v32 = L.eigvalsh(np.array([[1, -5, 7], [-5, 2, -9], [7, -9, 3]], dtype=np.float32))
+    np.testing.assert_allclose(v32, [16.28378, -3.41558, -6.86819], atol=1e-5)      # unsorted, as the reference's test
+    vals, vecs = L.eigh(np.array([[2.5]]))
+    assert vals[0] == 2.5 and vecs[0, 0] == 1.0
+    vals, vecs = L.eigh(np.zeros((3, 3)))                                             # amax == 0 (eigh.rs:32)
+    assert np.all(vals == 0) and np.allclose(np.abs(vecs), np.eye(3))
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [2, 3, 10, 33, 100, 257, 600])
+def test_eigh_parity(L, n, dt):
+    """Against the oracle's symmetric_eig (same order of eigenvalues: both follow eigh.rs:51-128; a rounding-level
+    difference of the tridiagonal may only reorder deflation, so the elementwise check is on sorted values) and
+    the reference's own properties (tests/eigh.rs:10-27): A v = lambda v, orthogonality, eigvalsh == eigh values."""
+    g = rnd((n, n), np.float64, seed=n, lo=-100, hi=100)
+    a0 = ((g + g.T) / 2).astype(dt)
+    vr, qr_ = O.symmetric_eig(a0.copy(), vectors=True)
+    scale = np.linalg.norm(a0.astype(np.float64), 2)
+    c = 64
+    for name, a in layouts(a0)[:5]:
+        vals, vecs = L.eigh_into(a)
+        assert np.max(np.abs(np.sort(vals) - np.sort(vr))) <= c * n * EPS[dt] * scale, name
+        v64, q64 = vals.astype(np.float64), vecs.astype(np.float64)
+        assert np.linalg.norm(a0.astype(np.float64) @ q64 - q64 * v64[None, :]) <= c * n * EPS[dt] * scale, name
+        assert np.linalg.norm(q64.T @ q64 - np.eye(n)) <= c * n * EPS[dt], name
+    vals_only = L.eigvalsh(a0)
+    assert np.max(np.abs(np.sort(vals_only) - np.sort(vr))) <= c * n * EPS[dt] * scale
+    if n <= 33:   # same deflation order in practice: unsorted elementwise agreement
+        vals, _ = L.eigh(a0)
+        assert np.max(np.abs(vals - vr)) <= c * n * EPS[dt] * scale
+    L.eigh(rnd((n, n), dt, seed=2))                                                  # non-symmetric must not crash (tests/eigh.rs:52-56)
+
+
 # ---- bidiagonal ----------------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 @pytest.mark.parametrize("shape", [(1, 1), (3, 4), (4, 3), (10, 10), (1, 7), (7, 1), (40, 23), (23, 40), (130, 70), (64, 200)])

@@ -177,3 +177,33 @@ def test_bidiagonal_kat(arr):
     np.testing.assert_allclose(u.T @ u if upper else u @ u.T, np.eye(md), atol=1e-5)
     np.testing.assert_allclose(vt @ vt.T, np.eye(md), atol=1e-5)
     np.testing.assert_allclose(u @ b @ vt, arr, atol=1e-5)
+
+
+# ---- eigh.rs KATs (the Givens phase on top of sym_tridiagonal) -------------------------------------
+def test_eigh_kats():
+    # src/eigh.rs:357-372 symm_eigvals
+    vals, vecs = O.symmetric_eig(np.array([[6.0, 2], [2, 6]]), vectors=False)
+    np.testing.assert_allclose(vals, [8, 4], atol=1e-12)
+    assert vecs is None
+    vals, _ = O.symmetric_eig(np.array([[1.0, -5, 7], [-5, 2, -9], [7, -9, 3]]), vectors=False)
+    np.testing.assert_allclose(np.sort(vals), [-6.86819, -3.41558, 16.28378], atol=1e-5)
+    # src/eigh.rs:374-409 sym_eigvecs1..3
+    for a, exp in (([[3.0, 1, 1], [1, 3, 1], [1, 1, 3]], [5, 2, 2]), ([[6.0, 2], [2, 6]], [8, 4]),
+                   ([[1.0, -5, 7], [-5, 2, -9], [7, -9, 3]], [16.28378, -3.41558, -6.86819])):
+        a = np.array(a)
+        vals, vecs = O.symmetric_eig(a.copy(), vectors=True)
+        order = np.argsort(-vals)
+        np.testing.assert_allclose(vals[order], exp, atol=1e-5)
+        np.testing.assert_allclose(vecs.T @ vecs, np.eye(len(exp)), atol=1e-5)
+        np.testing.assert_allclose(a @ vecs, vecs * vals[None, :], atol=1e-5)
+    # tests/eigh.rs:59-65 eigh_f32
+    v32, _ = O.symmetric_eig(np.array([[1, -5, 7], [-5, 2, -9], [7, -9, 3]], dtype=np.float32), vectors=False)
+    np.testing.assert_allclose(v32, [16.28378, -3.41558, -6.86819], atol=1e-5)
+    # 1 x 1 and a random symmetric matrix against LAPACK
+    vals, vecs = O.symmetric_eig(np.array([[2.5]]))
+    assert vals[0] == 2.5 and vecs[0, 0] == 1.0
+    g = np.random.default_rng(0).uniform(-100, 100, (40, 40))
+    s = (g + g.T) / 2
+    vals, vecs = O.symmetric_eig(s.copy())
+    np.testing.assert_allclose(np.sort(vals), np.linalg.eigvalsh(s), atol=1e-10)
+    np.testing.assert_allclose(s @ vecs, vecs * vals[None, :], atol=1e-9)

@@ -49,6 +49,25 @@ elif kind == "tridiag":
     off = torch.zeros(n, dtype=torch.float64, device=dev)
     step = lambda: (W.copy_(S), lib.lfb_sym_tridiagonal_dev_f64(eng.h, p(W), n, n, p(off)))
     flops = 4.0 / 3.0 * n ** 3
+elif kind == "eigvalsh":
+    import numpy as np
+    S = torch.rand((n, n), dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    S = (S + S.t()) / 2
+    W = torch.empty_like(S)
+    vals = np.zeros(n)
+    vp = C.c_void_p(vals.ctypes.data)
+    step = lambda: (W.copy_(S), lib.lfb_eigh_dev_f64(eng.h, p(W), n, n, vp, None, n))
+    flops = 4.0 / 3.0 * n ** 3
+elif kind == "eigh":
+    import numpy as np
+    S = torch.rand((n, n), dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    S = (S + S.t()) / 2
+    W = torch.empty_like(S)
+    Q = torch.empty_like(S)
+    vals = np.zeros(n)
+    vp = C.c_void_p(vals.ctypes.data)
+    step = lambda: (W.copy_(S), lib.lfb_eigh_dev_f64(eng.h, p(W), n, n, vp, p(Q), n))
+    flops = 4.0 / 3.0 * n ** 3
 elif kind == "bidiag":
     A = torch.rand((n, m), dtype=torch.float64, device=dev, generator=g) * 2 - 1   # column-major m x n
     W = torch.empty_like(A)
