@@ -356,7 +356,9 @@ def main():
 
 
 def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
-    """C2' (QR 16384^2 f64, replicas), C3 (batched QR, batch-sharded), C4 (TSQR, row-sharded)."""
+    """C2' (QR 16384^2 f64, replicas), C3 (batched QR, batch-sharded), C4 (TSQR, row-sharded), C5 (eigh / SVD phase 1,
+    eigh end to end)."""
+    import numpy as np
     import torch
     import torch.distributed as dist
     out = {}
