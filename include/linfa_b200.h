@@ -126,6 +126,17 @@ int lfb_eigh_f64(lfb_handle *h, const double *a, int64_t rows, int64_t cols, int
 int lfb_eigh_f32(lfb_handle *h, const float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
                  float *vals, float *vecs, int64_t vrs, int64_t vcs);
 
+/* ---- svd.rs:415-479 SVDInto / SVD (svd, svd.rs:17-221) ------------------------------------------------
+ * a: rows x cols view (only read; the reference consumes `self`).  sigma: min(rows, cols) contiguous entries in the
+ * reference's own (unsorted) order, all >= 0 -- SvdSort stays host-side.  u: rows x min view or NULL (calc_u = false);
+ * vt: min x cols view or NULL (calc_vt = false).  Scale by max|a|, bidiagonalise, generate U and V on the device; the
+ * scalar implicit-shift QR recurrence of svd.rs:55-208 (eps = 5 * machine epsilon, svd.rs:441) runs on the host and
+ * its Givens rotations are applied to U and V on the device.  LFB_EMPTY_MATRIX for an empty input (svd.rs:23-25). */
+int lfb_svd_f64(lfb_handle *h, const double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double *sigma,
+                double *u, int64_t urs, int64_t ucs, double *vt, int64_t vrs, int64_t vcs);
+int lfb_svd_f32(lfb_handle *h, const float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, float *sigma,
+                float *u, int64_t urs, int64_t ucs, float *vt, int64_t vrs, int64_t vcs);
+
 /* ---- tridiagonal.rs:31-66 sym_tridiagonal ---------------------------------------------------- */
 /* In place: diag(a) becomes the tridiagonal's diagonal, a[i+1.., i] the reflectors; off (n-1) gets
  * the SIGNED off-diagonal (TridiagonalDecomp, :71-77).  n == 0 -> LFB_EMPTY_MATRIX. */
@@ -155,6 +166,10 @@ int lfb_assemble_q_dev_f64(lfb_handle *h, const double *d_m, int64_t rows, int64
 int lfb_sym_tridiagonal_dev_f64(lfb_handle *h, double *d_a, int64_t n, int64_t ld, double *d_off);
 /* d_a (n x n column-major, consumed) -> vals_host (n, HOST memory), d_q (n x n device, or NULL). */
 int lfb_eigh_dev_f64(lfb_handle *h, double *d_a, int64_t n, int64_t ld, double *vals_host, double *d_q, int64_t ldq);
+/* d_a (rows x cols column-major, consumed) -> sigma_host (min, HOST memory), d_u (rows x min, or NULL),
+ * d_v (cols x min: V = Vt^T column-major, i.e. the row-major buffer of Vt; or NULL). */
+int lfb_svd_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *sigma_host,
+                    double *d_u, int64_t ldu, double *d_v, int64_t ldv);
 int lfb_bidiagonal_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_d, double *d_e);
 /* batched: d_a is [batch][m][n] row-major packed (the ndarray layout), in place */
 int lfb_qr_batched_dev_f32(lfb_handle *h, float *d_a, int64_t batch, int64_t m, int64_t n, float *d_diag);

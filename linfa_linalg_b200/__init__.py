@@ -25,6 +25,7 @@ __all__ = [
     "solvec", "solvec_into", "solvec_inplace", "invc", "invc_inplace",
     "solve_triangular", "solve_triangular_into", "solve_triangular_inplace", "triangular_inplace", "into_triangular",
     "is_triangular", "sym_tridiagonal", "TridiagonalDecomp", "bidiagonal", "BidiagonalDecomp",
+    "svd", "svd_into", "sort_svd", "sort_svd_asc", "sort_svd_desc",
     "eigh", "eigh_into", "eigvalsh", "eigvalsh_into", "sort_eig", "sort_eig_asc", "sort_eig_desc", "LARGEST", "SMALLEST",
 ]
 
@@ -484,6 +485,47 @@ def sort_eig_asc(res):
 
 def sort_eig_desc(res):
     return sort_eig(res, LARGEST)
+
+
+# ---- svd: src/svd.rs ---------------------------------------------------------------------------------
+def svd_into(a: np.ndarray, calc_u: bool, calc_vt: bool, eng=None):
+    """svd.rs:431-443 SVDInto::svd_into -> (u or None, sigma in the reference's order, vt or None)."""
+    e = eng or engine()
+    rows, cols = a.shape
+    if rows == 0 or cols == 0:
+        raise EmptyMatrix()                     # svd.rs:23-25
+    dim = min(rows, cols)
+    s = np.zeros(dim, dtype=a.dtype)
+    u = np.zeros((rows, dim), dtype=a.dtype) if calc_u else None
+    vt = np.zeros((dim, cols), dtype=a.dtype) if calc_vt else None
+    it = a.itemsize
+    up = (_vecp(u), u.strides[0] // it, u.strides[1] // it) if calc_u else (None, 0, 0)
+    vp = (_vecp(vt), vt.strides[0] // it, vt.strides[1] // it) if calc_vt else (None, 0, 0)
+    st = e.call("lfb_svd" + _sfx(a), *_view(a), _vecp(s), *up, *vp)
+    e._check(st)
+    return u, s, vt
+
+
+def svd(a, calc_u: bool, calc_vt: bool, eng=None):
+    """svd.rs:462-478 SVD::svd (works on a copy, like `to_owned()`)."""
+    return svd_into(_owned(a), calc_u, calc_vt, eng)
+
+
+def sort_svd(res, order=LARGEST):
+    """svd.rs:487-527 SvdSort (host-side, as in the reference): stable sort of sigma, columns of U and rows of Vt alike."""
+    u, s, vt = res
+    if np.isnan(s).any():
+        raise ValueError("NaN values in array")
+    idx = np.argsort(-s if order == LARGEST else s, kind="stable")
+    return (None if u is None else np.ascontiguousarray(u[:, idx])), s[idx], (None if vt is None else np.ascontiguousarray(vt[idx, :]))
+
+
+def sort_svd_asc(res):
+    return sort_svd(res, SMALLEST)
+
+
+def sort_svd_desc(res):
+    return sort_svd(res, LARGEST)
 
 
 # ---- bidiagonal: src/bidiagonal.rs ---------------------------------------------------------------

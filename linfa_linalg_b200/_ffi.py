@@ -46,6 +46,7 @@ _TYPED = {
     "lfb_sym_tridiagonal": [_vp] + _VIEW + [_vp],
     "lfb_bidiagonal": [_vp] + _VIEW + [_vp, _vp],
     "lfb_eigh": [_vp] + _VIEW + [_vp, _vp, _i64, _i64],
+    "lfb_svd": [_vp] + _VIEW + [_vp, _vp, _i64, _i64, _vp, _i64, _i64],
     "lfb_qr_batched": [_vp, _vp, _i64, _i64, _i64, _vp],
     "lfb_qr_dev": [_vp, _vp, _i64, _i64, _i64, _vp],
     "lfb_cholesky_dev": [_vp, _vp, _i64, _i64, _int, _vp],
@@ -58,6 +59,7 @@ SIGNATURES.update({
     "lfb_sym_tridiagonal_dev_f64": [_vp, _vp, _i64, _i64, _vp],
     "lfb_bidiagonal_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _vp],
     "lfb_eigh_dev_f64": [_vp, _vp, _i64, _i64, _vp, _vp, _i64],
+    "lfb_svd_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _i64],
     "lfb_qr_batched_dev_f32": [_vp, _vp, _i64, _i64, _i64, _vp],
     "lfb_tsqr_local_r_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
     "lfb_gemm_dev_f64": [_vp, _int, _int, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _dbl, _vp, _i64],

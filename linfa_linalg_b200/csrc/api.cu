@@ -279,6 +279,22 @@ int eigh_host(lfb_handle *h, const T *a, int64_t rows, int64_t cols, int64_t rs,
 }
 
 template <typename T>
+int svd_host(lfb_handle *h, const T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *sv, T *u, int64_t urs, int64_t ucs,
+             T *vt, int64_t vrs, int64_t vcs) {
+    if (rows <= 0 || cols <= 0) return fail(h, LFB_EMPTY_MATRIX, "Matrix is empty");           // svd.rs:23-25
+    if (!sv) return fail(h, LFB_INVALID_ARGUMENT, "sigma is null");
+    LFB_API_BEGIN(h)
+    const int64_t dim = std::min(rows, cols);
+    const int64_t ld = round_up(rows, 2), ldv = round_up(cols, 2);
+    DevBuf<T> dA(*h, (size_t)ld * cols), dU(*h, u ? (size_t)ld * dim : 1), dV(*h, vt ? (size_t)ldv * dim : 1);
+    upload<T>(*h, a, rows, cols, rs, cs, dA, ld);
+    svd_dev<T>(*h, dA, rows, cols, ld, sv, u ? dU.get() : nullptr, ld, vt ? dV.get() : nullptr, ldv);
+    if (u) download<T>(*h, dU, ld, u, rows, dim, urs, ucs);
+    if (vt) download<T>(*h, dV, ldv, vt, cols, dim, vcs, vrs);      // the device holds V = Vt^T: swap the strides
+    LFB_API_END(h)
+}
+
+template <typename T>
 int bidiagonal_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *d, T *e) {
     const int64_t md = std::min(rows, cols);
     if (md <= 0) return fail(h, LFB_EMPTY_MATRIX, "Matrix is empty");                         // bidiagonal.rs:30-32
@@ -460,6 +476,8 @@ int lfb_sym_tridiagonal_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int6
 int lfb_sym_tridiagonal_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *off) { return sym_tridiagonal_host<float>(h, a, r, c, rs, cs, off); }
 int lfb_eigh_f64(lfb_handle *h, const double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *vals, double *vecs, int64_t vrs, int64_t vcs) { return eigh_host<double>(h, a, r, c, rs, cs, vals, vecs, vrs, vcs); }
 int lfb_eigh_f32(lfb_handle *h, const float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *vals, float *vecs, int64_t vrs, int64_t vcs) { return eigh_host<float>(h, a, r, c, rs, cs, vals, vecs, vrs, vcs); }
+int lfb_svd_f64(lfb_handle *h, const double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *sv, double *u, int64_t urs, int64_t ucs, double *vt, int64_t vrs, int64_t vcs) { return svd_host<double>(h, a, r, c, rs, cs, sv, u, urs, ucs, vt, vrs, vcs); }
+int lfb_svd_f32(lfb_handle *h, const float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *sv, float *u, int64_t urs, int64_t ucs, float *vt, int64_t vrs, int64_t vcs) { return svd_host<float>(h, a, r, c, rs, cs, sv, u, urs, ucs, vt, vrs, vcs); }
 int lfb_bidiagonal_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *d, double *e) { return bidiagonal_host<double>(h, a, r, c, rs, cs, d, e); }
 int lfb_bidiagonal_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *d, float *e) { return bidiagonal_host<float>(h, a, r, c, rs, cs, d, e); }
 int lfb_qr_batched_f32(lfb_handle *h, float *a, int64_t batch, int64_t m, int64_t n, float *diag) { return qr_batched_host<float>(h, a, batch, m, n, diag); }
@@ -505,6 +523,14 @@ int lfb_eigh_dev_f64(lfb_handle *h, double *d_a, int64_t n, int64_t ld, double *
     if (n < 0 || (n > 0 && !vals_host)) return fail(h, LFB_INVALID_ARGUMENT, "bad arguments");
     LFB_API_BEGIN(h)
     symmetric_eig<double>(*h, d_a, n, ld, vals_host, d_q, ldq);
+    LFB_API_END(h)
+}
+int lfb_svd_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *sv_host, double *d_u, int64_t ldu,
+                    double *d_v, int64_t ldv) {
+    if (std::min(rows, cols) < 1) return fail(h, LFB_EMPTY_MATRIX, "Matrix is empty");
+    if (!sv_host) return fail(h, LFB_INVALID_ARGUMENT, "sigma is null");
+    LFB_API_BEGIN(h)
+    svd_dev<double>(*h, d_a, rows, cols, ld, sv_host, d_u, ldu, d_v, ldv);
     LFB_API_END(h)
 }
 int lfb_bidiagonal_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_d, double *d_e) {

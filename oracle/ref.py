@@ -239,3 +239,24 @@ def symmetric_eig(a: np.ndarray, vectors: bool = True, eps=None):
     f(_p(a), _i(n), _i(_es(a, 0)), _i(_es(a, 1)), C.c_int(1 if vectors else 0), _ct(a)(e),
       _p(vals), _p(q), _i(_es(q, 0)), _i(_es(q, 1)), _p(off), _p(work))
     return vals, (q if vectors else None)
+
+
+def svd(a: np.ndarray, calc_u: bool = True, calc_vt: bool = True, eps=None):
+    """svd.rs:17-221 (svd), `a` is consumed; returns (u or None, s, vt or None) in the reference's own order.
+    eps defaults to 5 * machine epsilon like SVDInto::svd_into (svd.rs:441)."""
+    rows, cols = a.shape
+    if rows == 0 or cols == 0:
+        raise ValueError("EmptyMatrix")
+    dim = min(rows, cols)
+    s = np.zeros(dim, dtype=a.dtype)
+    u = np.zeros((rows, dim), dtype=a.dtype) if calc_u else None
+    vt = np.zeros((dim, cols), dtype=a.dtype) if calc_vt else None
+    off = np.zeros(max(dim, 1), dtype=a.dtype)
+    e = 5 * np.finfo(a.dtype).eps if eps is None else eps
+    f = getattr(lib(), "lfo_svd" + _sfx(a))
+    f.restype = C.c_int
+    up = (_p(u), _i(_es(u, 0)), _i(_es(u, 1))) if calc_u else (None, _i(0), _i(0))
+    vp = (_p(vt), _i(_es(vt, 0)), _i(_es(vt, 1))) if calc_vt else (None, _i(0), _i(0))
+    st = f(_p(a), _i(rows), _i(cols), _i(_es(a, 0)), _i(_es(a, 1)), _ct(a)(e), _p(s), *up, *vp, _p(off))
+    assert st == 0
+    return u, s, vt

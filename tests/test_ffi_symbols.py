@@ -18,7 +18,7 @@ def _declared():
 def test_header_declares_both_scalar_families():
     names = _declared()
     for base in ("lfb_qr", "lfb_assemble_q", "lfb_qt_mul", "lfb_cholesky", "lfb_solve_triangular",
-                 "lfb_sym_tridiagonal", "lfb_bidiagonal", "lfb_eigh"):
+                 "lfb_sym_tridiagonal", "lfb_bidiagonal", "lfb_eigh", "lfb_svd"):
         assert base + "_f32" in names and base + "_f64" in names
 
 
@@ -70,6 +70,8 @@ def test_shape_errors_raised_before_any_device_work():
     vals, vecs = L.eigh(np.zeros((0, 0)), eng=object())                  # eigh.rs:16-25 / :411-420 corner
     assert vals.shape == (0,) and vecs.shape == (0, 0)
     assert L.eigvalsh(np.zeros((0, 0)), eng=object()).shape == (0,)
+    with pytest.raises(L.EmptyMatrix):                                   # svd.rs:23-25, :602-607
+        L.svd(np.zeros((0, 1)), False, False, eng=object())
 
 
 def test_sort_eig_host_side():

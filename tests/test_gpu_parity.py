@@ -380,6 +380,92 @@ def test_eigh_parity(L, n, dt):
     L.eigh(rnd((n, n), dt, seed=2))                                                  # non-symmetric must not crash (tests/eigh.rs:52-56)
 
 
+# ---- svd (bidiagonalisation + Givens phase, src/svd.rs) --------------------------------------------
+def test_svd_kats(L):  # src/svd.rs:537-614, tests/svd.rs:66-72
+    u, s, vt = L.sort_svd_desc(L.svd(np.array([[3.0, 0], [0, -2]]), True, True))
+    np.testing.assert_allclose(s, [3, 2], atol=1e-7)
+    np.testing.assert_allclose(u, [[1, 0], [0, -1]], atol=1e-7)
+    np.testing.assert_allclose(vt, [[1, 0], [0, 1]], atol=1e-7)
+    u, s, vt = L.sort_svd_asc(L.svd(np.array([[3.0, 0], [0, -2]]), True, True))
+    np.testing.assert_allclose(s, [2, 3], atol=1e-7)
+    np.testing.assert_allclose(u, [[0, 1], [-1, 0]], atol=1e-7)
+    np.testing.assert_allclose(vt, [[0, 1], [1, 0]], atol=1e-7)
+    u, s, vt = L.svd(np.array([[1.0, 0, -1], [-2, 1, 4]]), False, False)
+    np.testing.assert_allclose(s, [0.51371, 4.76824], atol=1e-5)
+    assert u is None and vt is None
+    big = np.array([[10.74785316637712, -5.994983325167452, -6.064492921857296],
+                    [-4.149751381521569, 20.654504205822462, -4.470436210703133],
+                    [-22.772715014220207, -1.4554372570788008, 18.108113992170573]]).T
+    for a, exp in ((np.array([[-2.0, 1, 4]]), [np.sqrt(21)]), (np.array([[1.0, 1], [1, 1]]), [2, 0]),
+                   (np.array([[-3.0, 4], [4.3, 2.1], [6.6, 8.7]]), [11.80876, 5.2633658]),
+                   (big, [3.16188022e+01, 2.23811978e+01, 0])):
+        u, s, vt = L.sort_svd_desc(L.svd(a, True, True))
+        np.testing.assert_allclose(s, exp, atol=1e-5)
+        assert not np.any(np.signbit(s))
+        np.testing.assert_allclose(u @ np.diag(s) @ vt, a, atol=1e-5)
+        for cu, cv in ((False, True), (True, False), (False, False)):
+            u2, s2, vt2 = L.sort_svd_desc(L.svd(a, cu, cv))
+            assert (u2 is None) == (not cu) and (vt2 is None) == (not cv)
+            np.testing.assert_allclose(s2, s, atol=1e-9)
+            if cu:
+                np.testing.assert_allclose(u2, u, atol=1e-9)
+            if cv:
+                np.testing.assert_allclose(vt2, vt, atol=1e-9)
+    u, s, vt = L.svd(np.array([[0.0]]), True, True)
+    assert s[0] == 0 and u[0, 0] == 1 and vt[0, 0] == 1
+    u, s, vt = L.svd(np.array([[3, 0], [0, -2]], dtype=np.float32), True, True)
+    np.testing.assert_allclose(s, [3, 2], atol=1e-7)
+    np.testing.assert_allclose(u, [[1, 0], [0, -1]], atol=1e-7)
+    np.testing.assert_allclose(vt, [[1, 0], [0, 1]], atol=1e-7)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(1, 1), (3, 4), (4, 3), (10, 10), (1, 7), (7, 1), (40, 23), (23, 40), (130, 70), (64, 200), (300, 300)])
+def test_svd_parity(L, shape, dt):
+    """Singular values against the oracle's svd (svd.rs:17-221, same algorithm and order up to rounding-level
+    reordering of deflations -> compared sorted) and the reference's own properties (tests/svd.rs:10-43)."""
+    a0 = rnd(shape, dt, seed=shape[0] * 1000 + shape[1])
+    _, sr, _ = O.svd(a0.copy(), False, False)
+    md = min(shape)
+    scale = np.linalg.norm(a0.astype(np.float64), 2)
+    c = 64
+    t = c * max(shape) * EPS[dt] * scale
+    for name, a in layouts(a0)[:5]:
+        u, s, vt = L.svd_into(a, True, True)
+        assert u.shape == (shape[0], md) and vt.shape == (md, shape[1]) and s.shape == (md,)
+        assert not np.any(np.signbit(s)), name
+        assert np.max(np.abs(np.sort(s) - np.sort(sr))) <= t, name
+        u64, s64, vt64 = u.astype(np.float64), s.astype(np.float64), vt.astype(np.float64)
+        e = c * max(shape) * EPS[dt]
+        assert np.linalg.norm((u64.T @ u64 if shape[0] >= shape[1] else u64 @ u64.T) - np.eye(md)) <= e, name
+        assert np.linalg.norm(vt64 @ vt64.T - np.eye(md)) <= e, name
+        assert np.linalg.norm(u64 @ np.diag(s64) @ vt64 - a0.astype(np.float64)) <= e * np.linalg.norm(a0.astype(np.float64)), name
+    for cu, cv in ((False, True), (True, False), (False, False)):
+        u2, s2, vt2 = L.svd(a0, cu, cv)
+        assert (u2 is None) == (not cu) and (vt2 is None) == (not cv)
+        assert np.max(np.abs(np.sort(s2) - np.sort(sr))) <= t
+
+
+def test_svd_rank_deficient(L):
+    """Vanishing diagonal entries take the cancel_horizontal / cancel_vertical paths (svd.rs:293-370).  On numerically
+    rank-deficient input the reference's algorithm itself is only as accurate as its absolute `<= eps` tests allow: the
+    oracle (verbatim restatement) deviates from LAPACK by up to ~5e-3 when such an input is perturbed by 1e-15.  The
+    bar for the engine is therefore the reference's own accuracy envelope on the same matrix, measured here."""
+    rng = np.random.default_rng(5)
+    for shape, rank in (((12, 8), 3), ((8, 12), 3), ((20, 20), 7), ((6, 6), 0)):
+        a = rng.uniform(-1, 1, (shape[0], rank)) @ rng.uniform(-1, 1, (rank, shape[1]))
+        envelope = 1e-10
+        for _ in range(16):
+            p = a * (1 + 1e-15 * rng.standard_normal(shape))
+            _, sp, _ = O.svd(p.copy(), False, False)
+            envelope = max(envelope, 10 * np.max(np.abs(np.sort(sp)[::-1] - np.linalg.svd(p, compute_uv=False))))
+        u, s, vt = L.svd(a, True, True)
+        assert u.shape == (shape[0], min(shape)) and vt.shape == (min(shape), shape[1])
+        assert not np.any(np.signbit(s))
+        assert np.max(np.abs(np.sort(s)[::-1] - np.linalg.svd(a, compute_uv=False))) <= envelope
+        assert np.linalg.norm(u @ np.diag(s) @ vt - a) <= 10 * envelope
+
+
 # ---- bidiagonal ----------------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 @pytest.mark.parametrize("shape", [(1, 1), (3, 4), (4, 3), (10, 10), (1, 7), (7, 1), (40, 23), (23, 40), (130, 70), (64, 200)])

@@ -207,3 +207,54 @@ def test_eigh_kats():
     vals, vecs = O.symmetric_eig(s.copy())
     np.testing.assert_allclose(np.sort(vals), np.linalg.eigvalsh(s), atol=1e-10)
     np.testing.assert_allclose(s @ vecs, vecs * vals[None, :], atol=1e-9)
+
+
+# ---- svd.rs KATs (the Givens phase on top of bidiagonal) -------------------------------------------
+def _sort_svd(u, s, vt, desc=True):
+    idx = np.argsort(-s if desc else s, kind="stable")
+    return (None if u is None else u[:, idx]), s[idx], (None if vt is None else vt[idx, :])
+
+
+def test_svd_kats():
+    # src/svd.rs:537-553 svd_test
+    u, s, vt = _sort_svd(*O.svd(np.array([[3.0, 0], [0, -2]]), eps=1e-15))
+    np.testing.assert_allclose(s, [3, 2], atol=1e-7)
+    np.testing.assert_allclose(u, [[1, 0], [0, -1]], atol=1e-7)
+    np.testing.assert_allclose(vt, [[1, 0], [0, 1]], atol=1e-7)
+    u, s, vt = O.svd(np.array([[1.0, 0, -1], [-2, 1, 4]]), False, False, eps=1e-15)
+    np.testing.assert_allclose(s, [0.51371, 4.76824], atol=1e-5)          # unsorted, as the reference's test
+    assert u is None and vt is None
+    # src/svd.rs:555-600 svd_props
+    big = np.array([[10.74785316637712, -5.994983325167452, -6.064492921857296],
+                    [-4.149751381521569, 20.654504205822462, -4.470436210703133],
+                    [-22.772715014220207, -1.4554372570788008, 18.108113992170573]]).T
+    for a, exp in ((np.array([[-2.0, 1, 4]]), [np.sqrt(21)]), (np.array([[1.0, 1], [1, 1]]), [2, 0]),
+                   (np.array([[-3.0, 4], [4.3, 2.1], [6.6, 8.7]]), [11.80876, 5.2633658]),
+                   (big, [3.16188022e+01, 2.23811978e+01, 0])):
+        u, s, vt = _sort_svd(*O.svd(a.copy(), eps=1e-15))
+        np.testing.assert_allclose(s, exp, atol=1e-5)
+        assert not np.any(np.signbit(s))
+        np.testing.assert_allclose(u @ np.diag(s) @ vt, a, atol=1e-5)
+        for cu, cv in ((False, True), (True, False), (False, False)):
+            u2, s2, vt2 = _sort_svd(*O.svd(a.copy(), cu, cv, eps=1e-15))
+            np.testing.assert_allclose(s2, s, atol=1e-9)
+            if cu:
+                np.testing.assert_allclose(u2, u, atol=1e-9)
+            if cv:
+                np.testing.assert_allclose(vt2, vt, atol=1e-9)
+    # src/svd.rs:602-614 svd_corner, tests/svd.rs:66-72 svd_f32
+    u, s, vt = O.svd(np.array([[0.0]]), eps=1e-15)
+    assert s[0] == 0 and u[0, 0] == 1 and vt[0, 0] == 1
+    u, s, vt = O.svd(np.array([[3, 0], [0, -2]], dtype=np.float32))
+    np.testing.assert_allclose(s, [3, 2], atol=1e-7)
+    np.testing.assert_allclose(u, [[1, 0], [0, -1]], atol=1e-7)
+    np.testing.assert_allclose(vt, [[1, 0], [0, 1]], atol=1e-7)
+    # random rectangular matrices against LAPACK + the reference's properties (tests/svd.rs:10-30)
+    for shape in ((30, 30), (50, 20), (20, 50), (1, 9), (9, 1)):
+        a = np.random.default_rng(shape[0] * 64 + shape[1]).uniform(-100, 100, shape)
+        u, s, vt = O.svd(a.copy())
+        np.testing.assert_allclose(np.sort(s)[::-1], np.linalg.svd(a, compute_uv=False), atol=1e-9)
+        np.testing.assert_allclose(u @ np.diag(s) @ vt, a, atol=1e-9)
+        k = min(shape)
+        np.testing.assert_allclose(vt @ vt.T, np.eye(k), atol=1e-10)
+        np.testing.assert_allclose(u.T @ u if shape[0] >= shape[1] else u @ u.T, np.eye(k), atol=1e-10)

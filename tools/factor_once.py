@@ -68,6 +68,15 @@ elif kind == "eigh":
     vp = C.c_void_p(vals.ctypes.data)
     step = lambda: (W.copy_(S), lib.lfb_eigh_dev_f64(eng.h, p(W), n, n, vp, p(Q), n))
     flops = 4.0 / 3.0 * n ** 3
+elif kind == "svd":
+    import numpy as np
+    A = torch.rand((n, m), dtype=torch.float64, device=dev, generator=g) * 2 - 1   # column-major m x n
+    W = torch.empty_like(A)
+    U = torch.empty((n, m), dtype=torch.float64, device=dev)                       # column-major m x n
+    V = torch.empty((n, n), dtype=torch.float64, device=dev)                       # column-major n x n (V = Vt^T)
+    sv = np.zeros(n)
+    step = lambda: (W.copy_(A), lib.lfb_svd_dev_f64(eng.h, p(W), m, n, m, C.c_void_p(sv.ctypes.data), p(U), m, p(V), n))
+    flops = 4.0 * m * n * n - 4.0 / 3.0 * n ** 3
 elif kind == "bidiag":
     A = torch.rand((n, m), dtype=torch.float64, device=dev, generator=g) * 2 - 1   # column-major m x n
     W = torch.empty_like(A)
