@@ -507,7 +507,25 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
                              "hbm_peak_GBps": hbm, "frac_of_hbm_lower_bound": gemv_bytes / (ms_b * 1e-3) / 1e9 / hbm,
                              "gemv_kernels_at_full_size": {"n_us": us_n.value, "n_GBps": full / max(us_n.value, 1e-9) / 1e3,
                                                            "t_us": us_t.value, "t_GBps": full / max(us_t.value, 1e-9) / 1e3}}
-        del B0, Bw
+        # SVD end to end (svd.rs:17-221): scale, bidiagonalise, U and V, Golub-Kahan Givens phase
+        Ud = torch.empty((n2, m2), dtype=torch.float64, device=dev)       # column-major m2 x n2
+        Vd = torch.empty((n2, n2), dtype=torch.float64, device=dev)       # column-major n2 x n2, V = Vt^T
+        sv = np.zeros(n2)
+
+        def svd_step():
+            Bw.copy_(B0)
+            st = lib.lfb_svd_dev_f64(eng.h, C.c_void_p(Bw.data_ptr()), m2, n2, m2, C.c_void_p(sv.ctypes.data),
+                                     C.c_void_p(Ud.data_ptr()), m2, C.c_void_p(Vd.data_ptr()), n2)
+            if st != 0:
+                raise RuntimeError(f"lfb_svd_dev_f64 status {st}")
+        barrier()
+        t0 = time.perf_counter(); svd_step(); torch.cuda.synchronize(); t_svd = time.perf_counter() - t0
+        # torch sees the column-major buffers transposed: Ud = U^T (n2 x m2), Vd = V^T = Vt (n2 x n2); B0 = A^T
+        rec = (Vd.t() * torch.from_numpy(sv).to(dev)[None, :]) @ Ud                  # (U S Vt)^T = V S U^T
+        resid = float((rec - B0).norm() / B0.norm())
+        out["svd_f64"] = {"workload": f"svd {m2}x{n2} f64 with U and Vt (C5b end to end)", "ms": t_svd * 1e3,
+                          "relative_residual": resid, "timing": "wall clock around one call (host recurrence inside)"}
+        del B0, Bw, Ud, Vd, rec
         torch.cuda.empty_cache()
     except Exception as ex:
         out["tridiag_bidiag"] = {"error": str(ex)[:200]}
