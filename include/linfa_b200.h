@@ -114,6 +114,36 @@ int lfb_solve_triangular_f32(lfb_handle *h, const float *a, int64_t a_rows, int6
 int lfb_triangular_inplace_f64(lfb_handle *h, double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int uplo);
 int lfb_triangular_inplace_f32(lfb_handle *h, float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int uplo);
 
+/* ---- fused solve drivers: one upload, every stage on the device, one download -------------------------
+ * qr.rs:207-248 LeastSquaresQrInto / LeastSquaresQr: a (rows x cols), b (rows x bcols) -> x (cols x bcols).
+ * rows >= cols: qr_into + QRDecomp::solve_into (qr.rs:124-152); rows < cols: QR of the transpose +
+ * solve_tr_into (qr.rs:156-181).  LFB_WRONG_ROWS, LFB_NON_INVERTIBLE (a zero on diag(R), qr.rs:194-197). */
+int lfb_least_squares_f64(lfb_handle *h, const double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                          const double *b, int64_t b_rows, int64_t bcols, int64_t b_rs, int64_t b_cs,
+                          double *x, int64_t x_rs, int64_t x_cs);
+int lfb_least_squares_f32(lfb_handle *h, const float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                          const float *b, int64_t b_rows, int64_t bcols, int64_t b_rs, int64_t b_cs,
+                          float *x, int64_t x_rs, int64_t x_cs);
+/* qr.rs:124-152 QRDecomp::solve_into (and :200-203 inverse with b = I) on an existing compact factor + diag. */
+int lfb_qr_solve_f64(lfb_handle *h, const double *qr, int64_t rows, int64_t cols, int64_t rs, int64_t cs, const double *diag,
+                     const double *b, int64_t b_rows, int64_t bcols, int64_t b_rs, int64_t b_cs,
+                     double *x, int64_t x_rs, int64_t x_cs);
+int lfb_qr_solve_f32(lfb_handle *h, const float *qr, int64_t rows, int64_t cols, int64_t rs, int64_t cs, const float *diag,
+                     const float *b, int64_t b_rows, int64_t bcols, int64_t b_rs, int64_t b_cs,
+                     float *x, int64_t x_rs, int64_t x_cs);
+/* cholesky.rs:118-163 SolveCInplace / SolveC: b (n x bcols) is overwritten with the solution of A x = b;
+ * with write_factor != 0, a receives its Cholesky factor in the lower triangle (solvec_inplace, :136-144).
+ * LFB_NOT_POSITIVE_DEFINITE reports the failing pivot in *fail_index. */
+int lfb_solvec_f64(lfb_handle *h, double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int write_factor,
+                   double *b, int64_t b_rows, int64_t bcols, int64_t b_rs, int64_t b_cs, int64_t *fail_index);
+int lfb_solvec_f32(lfb_handle *h, float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int write_factor,
+                   float *b, int64_t b_rows, int64_t bcols, int64_t b_rs, int64_t b_cs, int64_t *fail_index);
+/* cholesky.rs:166-199 InverseCInplace / InverseC: inv (n x n) = A^-1; the identity is generated on the device. */
+int lfb_invc_f64(lfb_handle *h, const double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                 double *inv, int64_t i_rs, int64_t i_cs, int64_t *fail_index);
+int lfb_invc_f32(lfb_handle *h, const float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                 float *inv, int64_t i_rs, int64_t i_cs, int64_t *fail_index);
+
 /* ---- eigh.rs:202-268 EighInto / Eigh / EigValshInto / EigValsh (symmetric_eig, eigh.rs:10-129) ---------
  * a: n x n view (only read; the reference consumes `self`, nothing of it is observable afterwards).
  * vals: n contiguous entries, in the reference's own (unsorted) order -- EigSort stays host-side.

@@ -137,6 +137,10 @@ class Engine:
     def _check(self, st: int):
         if st == _ffi.OK:
             return
+        if st == _ffi.NON_INVERTIBLE:            # qr.rs:134-136
+            raise NonInvertible()
+        if st == _ffi.EMPTY_MATRIX:
+            raise EmptyMatrix()
         msg = (self.lib.lfb_last_error(self.h) or b"").decode()
         raise DeviceError(f"liblinfa_b200 status {st}: {msg}")
 
@@ -198,14 +202,16 @@ class QRDecomp:
         return bool(np.all(self.diag != 0))
 
     def solve_into(self, b: np.ndarray) -> np.ndarray:  # qr.rs:124-152
+        """Q^T b and the triangular solve run back to back on the device (lfb_qr_solve); the solution lands in the
+        first `ncols` rows of `b`, which is what the reference returns (`b.slice_move(s![..ncols, ..])`)."""
         if self.qr.shape[0] != b.shape[0]:
             raise WrongRows(self.qr.shape[0], b.shape[0])
         if not self.is_invertible():
             raise NonInvertible()
-        self.qt_mul(b)
         n = self.qr.shape[1]
         x = b[:n, :]
-        _solve_tri(self._e, self.qr[:n, :n], x, UPPER, np.abs(self.diag))
+        st = self._e.call("lfb_qr_solve" + _sfx(self.qr), *_view(self.qr), _vecp(self.diag), *_view(b), *_view(x)[:1], *_view(x)[3:])
+        self._e._check(st)
         return x
 
     def solve_tr_into(self, b: np.ndarray) -> np.ndarray:  # qr.rs:156-181
@@ -246,10 +252,15 @@ def qr(a, eng: Engine | None = None) -> QRDecomp:
 
 
 def least_squares_into(a: np.ndarray, b: np.ndarray, eng: Engine | None = None) -> np.ndarray:
-    """qr.rs:207-229."""
-    if a.shape[0] >= a.shape[1]:
-        return np.array(qr_into(a, eng).solve_into(b))
-    return qr_into(a.T, eng).solve_tr_into(b)
+    """qr.rs:207-229 -- factorisation, Q^T b (or the wide case's R^T solve and Q m) and the triangular solve as ONE
+    library call (lfb_least_squares): a and b cross PCIe once, x comes back once."""
+    e = eng or engine()
+    if a.shape[0] != b.shape[0]:
+        raise WrongRows(a.shape[0], b.shape[0])
+    x = np.zeros((a.shape[1], b.shape[1]), dtype=a.dtype)
+    st = e.call("lfb_least_squares" + _sfx(a), *_view(a), *_view(b), *_view(x)[:1], *_view(x)[3:])
+    e._check(st)
+    return x
 
 
 def least_squares(a: np.ndarray, b, eng: Engine | None = None) -> np.ndarray:
@@ -317,24 +328,41 @@ def cholesky(a, eng=None):  # cholesky.rs:111-114
     return _chol(_owned(a), True, eng or engine())
 
 
-def solvec_inplace(a: np.ndarray, b: np.ndarray, eng=None) -> np.ndarray:  # cholesky.rs:136-144
-    e = eng or engine()
-    chol = cholesky_inplace_dirty(a, e)
-    _solve_tri(e, chol, b, LOWER, None)
-    _solve_tri(e, chol.T, b, UPPER, None)
+def _solvec(a: np.ndarray, b: np.ndarray, write_factor: bool, e: Engine) -> np.ndarray:
+    _check_square(a)
+    if a.shape[0] != b.shape[0]:
+        raise WrongRows(a.shape[0], b.shape[0])
+    fail = C.c_int64(-1)
+    st = e.call("lfb_solvec" + _sfx(a), *_view(a), 1 if write_factor else 0, *_view(b), C.byref(fail))
+    if st == _ffi.NOT_POSITIVE_DEFINITE:
+        raise NotPositiveDefinite(fail.value)
+    e._check(st)
     return b
 
 
-def solvec_into(a, b, eng=None):  # cholesky.rs:127-130
-    return solvec_inplace(a, b, eng)
+def solvec_inplace(a: np.ndarray, b: np.ndarray, eng=None) -> np.ndarray:  # cholesky.rs:136-144
+    """Cholesky + both triangular solves in one library call (lfb_solvec); `a` receives its factor (dirty)."""
+    return _solvec(a, b, True, eng or engine())
+
+
+def solvec_into(a, b, eng=None):  # cholesky.rs:127-130 (consumes a: the factor is not written back)
+    return _solvec(a, b, False, eng or engine())
 
 
 def solvec(a, b, eng=None):  # cholesky.rs:155-163
     return solvec_inplace(a, _owned(b).astype(a.dtype, copy=False), eng)
 
 
-def invc_inplace(a, eng=None):  # cholesky.rs:178-182
-    return solvec_into(a, np.eye(a.shape[0], dtype=a.dtype), eng)
+def invc_inplace(a, eng=None):  # cholesky.rs:178-182 (the identity right-hand side is generated on the device)
+    e = eng or engine()
+    n = _check_square(a)
+    inv = np.zeros((n, n), dtype=a.dtype)
+    fail = C.c_int64(-1)
+    st = e.call("lfb_invc" + _sfx(a), *_view(a), *_view(inv)[:1], *_view(inv)[3:], C.byref(fail))
+    if st == _ffi.NOT_POSITIVE_DEFINITE:
+        raise NotPositiveDefinite(fail.value)
+    e._check(st)
+    return inv
 
 
 def invc(a, eng=None):  # cholesky.rs:193-199

@@ -46,6 +46,10 @@ _TYPED = {
     "lfb_sym_tridiagonal": [_vp] + _VIEW + [_vp],
     "lfb_bidiagonal": [_vp] + _VIEW + [_vp, _vp],
     "lfb_eigh": [_vp] + _VIEW + [_vp, _vp, _i64, _i64],
+    "lfb_least_squares": [_vp] + _VIEW + _VIEW + [_vp, _i64, _i64],
+    "lfb_qr_solve": [_vp] + _VIEW + [_vp] + _VIEW + [_vp, _i64, _i64],
+    "lfb_solvec": [_vp] + _VIEW + [_int] + _VIEW + [C.POINTER(_i64)],
+    "lfb_invc": [_vp] + _VIEW + [_vp, _i64, _i64, C.POINTER(_i64)],
     "lfb_svd": [_vp] + _VIEW + [_vp, _vp, _i64, _i64, _vp, _i64, _i64],
     "lfb_qr_batched": [_vp, _vp, _i64, _i64, _i64, _vp],
     "lfb_qr_dev": [_vp, _vp, _i64, _i64, _i64, _vp],

@@ -246,6 +246,158 @@ int triangular_inplace_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int
     LFB_API_END(h)
 }
 
+// ---- fused solve drivers: one upload, every stage on the device, one download ----------
+// True if any of the n device values is exactly zero (QRDecomp::is_invertible, qr.rs:194-197).
+template <typename T>
+bool any_zero_dev(lfb_handle &h, const T *d, int64_t n) {
+    std::vector<T> v((size_t)std::max<int64_t>(n, 1));
+    download_vec<T>(h, d, n, v.data());
+    for (int64_t i = 0; i < n; ++i)
+        if (v[i] == T(0)) return true;
+    return false;
+}
+
+// |d| on the host round trip is avoided: a tiny kernel-free path -- upload of |diag| is replaced by reusing diag
+// with a device abs (util.cu has no abs kernel; n values through the host cost nothing next to the factorisation).
+template <typename T>
+void abs_dev(lfb_handle &h, T *d, int64_t n) {
+    std::vector<T> v((size_t)std::max<int64_t>(n, 1));
+    download_vec<T>(h, d, n, v.data());
+    for (int64_t i = 0; i < n; ++i) v[i] = std::fabs(v[i]);
+    upload_vec<T>(h, v.data(), n, d);
+    LFB_CUDA(cudaStreamSynchronize(h.stream));
+}
+
+// qr.rs:207-229 LeastSquaresQrInto::least_squares_into: thin (rows >= cols): qr_into + solve_into (:124-152);
+// wide: qr_into of the transpose + solve_tr_into (:156-181).  x: cols x bcols.
+template <typename T>
+int least_squares_host(lfb_handle *h, const T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, const T *b, int64_t b_rows,
+                       int64_t bcols, int64_t b_rs, int64_t b_cs, T *x, int64_t x_rs, int64_t x_cs) {
+    if (b_rows != rows) return fail(h, LFB_WRONG_ROWS, "Matrix has the wrong number of rows");      // qr.rs:128-133 / :160-165
+    if (rows == 0 || cols == 0) return LFB_OK;
+    LFB_API_BEGIN(h)
+    if (rows >= cols) {
+        const int64_t ld = round_up(rows, 2);
+        DevBuf<T> dA(*h, (size_t)ld * cols), dB(*h, (size_t)ld * std::max<int64_t>(bcols, 1)), dD(*h, cols);
+        upload<T>(*h, a, rows, cols, rs, cs, dA, ld);
+        upload<T>(*h, b, rows, bcols, b_rs, b_cs, dB, ld);
+        qr_factor<T>(*h, dA, rows, cols, ld, dD);                                                    // :32-44
+        if (any_zero_dev<T>(*h, dD, cols)) return fail(h, LFB_NON_INVERTIBLE, "Matrix is not invertible");   // :134-136
+        if (bcols > 0) {
+            qt_mul<T>(*h, dA, rows, cols, ld, dD, dB, bcols, ld);                                    // :139
+            abs_dev<T>(*h, dD, cols);
+            trsm_left<T>(*h, 0, 0, cols, bcols, dA, ld, dD, dB, ld);                                 // :145-150: R x = Q^T b, |diag| as the diagonal
+            download<T>(*h, dB, ld, x, cols, bcols, x_rs, x_cs);
+        }
+    } else {
+        // A^T = Q R (cols x rows, thin); solve R^T m = b, x = Q m
+        const int64_t ldt = round_up(cols, 2), ldb = round_up(rows, 2);
+        DevBuf<T> dA(*h, (size_t)ldb * cols), dT(*h, (size_t)ldt * rows), dB(*h, (size_t)ldb * std::max<int64_t>(bcols, 1)), dD(*h, rows);
+        upload<T>(*h, a, rows, cols, rs, cs, dA, ldb);
+        transpose<T>(*h, dA, rows, cols, ldb, dT, ldt);
+        upload<T>(*h, b, rows, bcols, b_rs, b_cs, dB, ldb);
+        qr_factor<T>(*h, dT, cols, rows, ldt, dD);
+        if (any_zero_dev<T>(*h, dD, rows)) return fail(h, LFB_NON_INVERTIBLE, "Matrix is not invertible");   // :166-168
+        if (bcols > 0) {
+            DevBuf<T> dQ(*h, (size_t)ldt * rows), dX(*h, (size_t)ldt * bcols), dAbs(*h, rows);
+            assemble_q<T>(*h, dT, cols, rows, ldt, 0, dD, dQ, ldt);                                  // :180 generate_q (needs the signed diag)
+            LFB_CUDA(cudaMemcpyAsync(dAbs.get(), dD.get(), sizeof(T) * rows, cudaMemcpyDeviceToDevice, h->stream));
+            abs_dev<T>(*h, dAbs, rows);
+            trsm_left<T>(*h, 0, 1, rows, bcols, dT, ldt, dAbs, dB, ldb);                             // :172-177: R^T m = b
+            gemm<T>(*h, 0, 0, cols, bcols, rows, T(1), dQ, ldt, dB, ldb, T(0), dX, ldt);             // :180: Q m
+            download<T>(*h, dX, ldt, x, cols, bcols, x_rs, x_cs);
+        }
+    }
+    LFB_API_END(h)
+}
+
+// QRDecomp::solve_into (qr.rs:124-152) on an existing decomposition: x (cols x bcols) = R^-1 (Q^T b)[..cols].
+template <typename T>
+int qr_solve_host(lfb_handle *h, const T *qr, int64_t rows, int64_t cols, int64_t rs, int64_t cs, const T *diag, const T *b,
+                  int64_t b_rows, int64_t bcols, int64_t b_rs, int64_t b_cs, T *x, int64_t x_rs, int64_t x_cs) {
+    if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
+    if (b_rows != rows) return fail(h, LFB_WRONG_ROWS, "Matrix has the wrong number of rows");      // :128-133
+    for (int64_t i = 0; i < cols; ++i)
+        if (diag[i] == T(0)) return fail(h, LFB_NON_INVERTIBLE, "Matrix is not invertible");         // :134-136
+    if (rows == 0 || cols == 0 || bcols == 0) return LFB_OK;
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(rows, 2);
+    DevBuf<T> dM(*h, (size_t)ld * cols), dB(*h, (size_t)ld * bcols), dD(*h, cols), dAbs(*h, cols);
+    std::vector<T> ad((size_t)cols);
+    for (int64_t i = 0; i < cols; ++i) ad[i] = std::fabs(diag[i]);
+    upload<T>(*h, qr, rows, cols, rs, cs, dM, ld);
+    upload<T>(*h, b, rows, bcols, b_rs, b_cs, dB, ld);
+    upload_vec<T>(*h, diag, cols, dD);
+    upload_vec<T>(*h, ad.data(), cols, dAbs);
+    qt_mul<T>(*h, dM, rows, cols, ld, dD, dB, bcols, ld);
+    trsm_left<T>(*h, 0, 0, cols, bcols, dM, ld, dAbs, dB, ld);
+    download<T>(*h, dB, ld, x, cols, bcols, x_rs, x_cs);
+    LFB_API_END(h)
+}
+
+// cholesky.rs:136-144 SolveCInplace::solvec_inplace (b in place; a receives its Cholesky factor in the lower
+// triangle when write_factor != 0, as `cholesky_inplace_dirty` leaves it) and, with b == nullptr, cholesky.rs:178-182
+// InverseCInplace::invc_inplace (the identity right-hand side is generated on the device; result in x).
+template <typename T>
+int solvec_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int write_factor, T *b, int64_t b_rows,
+                int64_t bcols, int64_t b_rs, int64_t b_cs, int64_t *fail_index) {
+    if (rows != cols) return fail(h, LFB_NOT_SQUARE, "Matrix is not square");
+    if (b_rows != rows) return fail(h, LFB_WRONG_ROWS, "Matrix has the wrong number of rows");      // triangular.rs:103-108
+    if (fail_index) *fail_index = -1;
+    const int64_t n = rows;
+    if (n == 0) return LFB_OK;
+    int64_t info = 0;
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(n, 2);
+    DevBuf<T> dA(*h, (size_t)ld * n), dB(*h, (size_t)ld * std::max<int64_t>(bcols, 1));
+    DevBuf<int64_t> dInfo(*h, 1);
+    upload<T>(*h, a, n, n, rs, cs, dA, ld);
+    if (b) upload<T>(*h, b, n, bcols, b_rs, b_cs, dB, ld);
+    cholesky_lower<T>(*h, dA, n, ld, 0, dInfo);                                                      // :139 (dirty)
+    LFB_CUDA(cudaMemcpyAsync(&info, dInfo.get(), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    LFB_CUDA(cudaStreamSynchronize(h->stream));
+    if (info != 0) {
+        if (fail_index) *fail_index = info - 1;
+        h->err = "Matrix is not positive definite";
+        return LFB_NOT_POSITIVE_DEFINITE;
+    }
+    if (bcols > 0 && b) {
+        trsm_left<T>(*h, 1, 0, n, bcols, dA, ld, (const T *)nullptr, dB, ld);                        // :140  L y = b
+        trsm_left<T>(*h, 1, 1, n, bcols, dA, ld, (const T *)nullptr, dB, ld);                        // :141  L^T x = y
+        download<T>(*h, dB, ld, b, n, bcols, b_rs, b_cs);
+    }
+    if (write_factor) download<T>(*h, dA, ld, a, n, n, rs, cs);
+    LFB_API_END(h)
+}
+
+template <typename T>
+int invc_host(lfb_handle *h, const T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *inv, int64_t i_rs, int64_t i_cs,
+              int64_t *fail_index) {
+    if (rows != cols) return fail(h, LFB_NOT_SQUARE, "Matrix is not square");
+    if (fail_index) *fail_index = -1;
+    const int64_t n = rows;
+    if (n == 0) return LFB_OK;
+    int64_t info = 0;
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(n, 2);
+    DevBuf<T> dA(*h, (size_t)ld * n), dB(*h, (size_t)ld * n);
+    DevBuf<int64_t> dInfo(*h, 1);
+    upload<T>(*h, a, n, n, rs, cs, dA, ld);
+    fill<T>(*h, dB, n, n, ld, T(0), T(1));                                                           // :180 Array2::eye
+    cholesky_lower<T>(*h, dA, n, ld, 0, dInfo);
+    LFB_CUDA(cudaMemcpyAsync(&info, dInfo.get(), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    LFB_CUDA(cudaStreamSynchronize(h->stream));
+    if (info != 0) {
+        if (fail_index) *fail_index = info - 1;
+        h->err = "Matrix is not positive definite";
+        return LFB_NOT_POSITIVE_DEFINITE;
+    }
+    trsm_left<T>(*h, 1, 0, n, n, dA, ld, (const T *)nullptr, dB, ld);
+    trsm_left<T>(*h, 1, 1, n, n, dA, ld, (const T *)nullptr, dB, ld);
+    download<T>(*h, dB, ld, inv, n, n, i_rs, i_cs);
+    LFB_API_END(h)
+}
+
 template <typename T>
 int sym_tridiagonal_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *off) {
     if (rows != cols) return fail(h, LFB_NOT_SQUARE, "Matrix is not square");                 // tridiagonal.rs:32
@@ -476,6 +628,26 @@ int lfb_sym_tridiagonal_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int6
 int lfb_sym_tridiagonal_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *off) { return sym_tridiagonal_host<float>(h, a, r, c, rs, cs, off); }
 int lfb_eigh_f64(lfb_handle *h, const double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *vals, double *vecs, int64_t vrs, int64_t vcs) { return eigh_host<double>(h, a, r, c, rs, cs, vals, vecs, vrs, vcs); }
 int lfb_eigh_f32(lfb_handle *h, const float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *vals, float *vecs, int64_t vrs, int64_t vcs) { return eigh_host<float>(h, a, r, c, rs, cs, vals, vecs, vrs, vcs); }
+#define LFB_SOLVE_ENTRIES(SFX, T)                                                                                          \
+    int lfb_least_squares_##SFX(lfb_handle *h, const T *a, int64_t r, int64_t c, int64_t rs, int64_t cs, const T *b, int64_t br, \
+                                int64_t bc, int64_t brs, int64_t bcs, T *x, int64_t xrs, int64_t xcs) {                    \
+        return least_squares_host<T>(h, a, r, c, rs, cs, b, br, bc, brs, bcs, x, xrs, xcs);                                \
+    }                                                                                                                      \
+    int lfb_qr_solve_##SFX(lfb_handle *h, const T *qr, int64_t r, int64_t c, int64_t rs, int64_t cs, const T *diag, const T *b, \
+                           int64_t br, int64_t bc, int64_t brs, int64_t bcs, T *x, int64_t xrs, int64_t xcs) {             \
+        return qr_solve_host<T>(h, qr, r, c, rs, cs, diag, b, br, bc, brs, bcs, x, xrs, xcs);                              \
+    }                                                                                                                      \
+    int lfb_solvec_##SFX(lfb_handle *h, T *a, int64_t r, int64_t c, int64_t rs, int64_t cs, int write_factor, T *b, int64_t br, \
+                         int64_t bc, int64_t brs, int64_t bcs, int64_t *fail_index) {                                      \
+        return solvec_host<T>(h, a, r, c, rs, cs, write_factor, b, br, bc, brs, bcs, fail_index);                          \
+    }                                                                                                                      \
+    int lfb_invc_##SFX(lfb_handle *h, const T *a, int64_t r, int64_t c, int64_t rs, int64_t cs, T *inv, int64_t irs,       \
+                       int64_t ics, int64_t *fail_index) {                                                                 \
+        return invc_host<T>(h, a, r, c, rs, cs, inv, irs, ics, fail_index);                                                \
+    }
+LFB_SOLVE_ENTRIES(f64, double)
+LFB_SOLVE_ENTRIES(f32, float)
+#undef LFB_SOLVE_ENTRIES
 int lfb_svd_f64(lfb_handle *h, const double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *sv, double *u, int64_t urs, int64_t ucs, double *vt, int64_t vrs, int64_t vcs) { return svd_host<double>(h, a, r, c, rs, cs, sv, u, urs, ucs, vt, vrs, vcs); }
 int lfb_svd_f32(lfb_handle *h, const float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *sv, float *u, int64_t urs, int64_t ucs, float *vt, int64_t vrs, int64_t vcs) { return svd_host<float>(h, a, r, c, rs, cs, sv, u, urs, ucs, vt, vrs, vcs); }
 int lfb_bidiagonal_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *d, double *e) { return bidiagonal_host<double>(h, a, r, c, rs, cs, d, e); }

@@ -180,6 +180,30 @@ def test_qr_solve_qtmul_inverse(L, shape, k):
         assert np.max(np.abs(aw @ sw - bw)) <= 1e-7 * np.max(np.abs(bw)) * max(shape)
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("shape,k", [((5, 3), 2), ((90, 40), 5), ((40, 90), 3), ((257, 257), 4)])
+def test_least_squares_fused_vs_oracle_composition(L, shape, k, dt):
+    """lfb_least_squares (one call) against the reference's own composition restated with the oracle:
+    qr.rs:207-229 = qr_into + solve_into (qt_mul, then the upper solve with |diag|) / solve_tr_into for wide input."""
+    a0 = rnd(shape, dt, seed=shape[0] + 7 * shape[1], lo=-1, hi=1)
+    b0 = rnd((shape[0], k), dt, seed=k + shape[0], lo=-1, hi=1)
+    m, n = shape
+    if m >= n:
+        ref = a0.copy(); dref = O.qr(ref); bo = b0.copy(); O.qt_mul(ref, dref, bo)
+        xo = bo[:n, :].copy(); O.solve_triangular(ref[:n, :n], xo, O.UPPER, ext_diag=np.abs(dref))
+    else:
+        xo = None      # wide: checked through the minimum-norm property below (x = Q R^-T b solves A x = b exactly)
+    for name, a in layouts(a0, square_t=False)[:3]:
+        x = L.least_squares_into(a, b0.copy())
+        assert x.shape == (n, k)
+        if xo is not None:
+            assert np.max(np.abs(x - xo)) <= 64 * max(shape) * EPS[dt] * max(1.0, np.max(np.abs(xo))) * np.linalg.cond(a0.astype(np.float64)), name
+        a64, x64, b64 = a0.astype(np.float64), x.astype(np.float64), b0.astype(np.float64)
+        # normal equations hold for the least-squares / minimum-norm solution
+        lhs = a64.T @ (a64 @ x64 - b64) if m >= n else a64 @ x64 - b64
+        assert np.linalg.norm(lhs) <= 256 * max(shape) * EPS[dt] * np.linalg.norm(a64) * max(np.linalg.norm(b64), np.linalg.norm(a64) * np.linalg.norm(x64)), name
+
+
 def test_qr_errors(L):  # src/qr.rs:338-361
     with pytest.raises(L.NonInvertible):
         L.qr(np.zeros((2, 2))).inverse()
