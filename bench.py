@@ -276,9 +276,18 @@ def main():
     lib.lfb_profile_end(eng.h, C.byref(g_ms), C.byref(g_fl), C.byref(g_calls))
     peak_tf = max(peak_dmma.value, peak_dfma.value) / 1e3
     achieved_tf = g_fl.value / (g_ms.value * 1e-3) / 1e12 if g_ms.value > 0 else 0.0
+    # DRAM traffic of the same launches from the committed ncu capture (bytes per launch, like `achieved`)
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_chol16384_gemm_traffic.json")
+    if n == 16384 and os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic = tj["traffic_bytes_per_launch"]
+        traffic_note = (f"ncu dram__bytes_read+write over the {tj['launches']} dgemm launches of one step: "
+                        f"{(tj['dram_read_bytes'] + tj['dram_write_bytes']) / 1e9:.1f} GB = "
+                        f"{(tj['dram_read_bytes'] + tj['dram_write_bytes']) / tj['algorithmic_flops'] * 1e3:.1f} B per kflop (compute bound)")
     roofline = {
         "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": None,
+        "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": traffic, "traffic_note": traffic_note,
         "kernel": "dgemm (FP64 DMMA.8x8x4) launches of one Cholesky step",
         "launches": int(g_calls.value), "kernel_ms_per_step": g_ms.value, "kernel_share_of_step": g_ms.value / (ms / args.steps),
         "peak_source": ("measured in this run by lfb_microbench_fp64 (register-resident DMMA / DFMA chains); "
