@@ -225,6 +225,229 @@ __device__ __forceinline__ void column_steps4(float (&a)[4][32], float *colbuf, 
     }
 }
 
+// ---- f32, 32 x 32 exactly: every column step specialised at compile time ---------------------------
+// ncu on qr_batched4_kernel (profiles/r1_batched.md): 2966 warp instructions per matrix, only 32 % of them FFMA;
+// 37 % are ISETP / IMAD / LOP3 / FSEL / BRA / LEA -- the row and column predicates of a run-time pivot index j
+// (`r >= j`, `c == j`, `c > j`).  With J a template parameter the row ranges are exact (rows >= J, not rows
+// >= 8 * (J / 8)), the column blocks right of the pivot block run unpredicated, and only the pivot block keeps
+// two lane predicates.
+template <int J>
+__device__ __forceinline__ void column_step_fixed(float (&a)[4][32], float *colbuf, float *vbuf, int g, float (&dg)[4],
+                                                  unsigned gmask) {
+    constexpr int Q = J / 8, JJ = J % 8, R4 = J & ~3;
+    if (g == JJ) {
+#pragma unroll
+        for (int r = R4; r < 32; r += 4)
+            *reinterpret_cast<float4 *>(colbuf + r) = make_float4(a[Q][r], a[Q][r + 1], a[Q][r + 2], a[Q][r + 3]);
+    }
+    __syncwarp();
+    float nsq = 0.f, xs[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int r = g + 8 * t;
+        xs[t] = (8 * t + 7 >= J) ? ((r >= J) ? colbuf[r] : 0.f) : 0.f;     // rows of this lane: g, g+8, g+16, g+24
+        nsq = fmaf(xs[t], xs[t], nsq);
+    }
+    // the four matrices of the warp run in lockstep: full-mask shuffles (xor 1, 2, 4 stay inside the 8-lane group)
+    // avoid the WARPSYNC / collective bracket a partial mask costs
+    nsq += __shfl_xor_sync(0xffffffffu, nsq, 1);
+    nsq += __shfl_xor_sync(0xffffffffu, nsq, 2);
+    nsq += __shfl_xor_sync(0xffffffffu, nsq, 4);
+    const float f = colbuf[J];
+    const float rn = nsq > 0.f ? rsqrtf(nsq) : 0.f;
+    float nrm = nsq * rn;                                        // householder.rs:13
+    nrm = fmaf(0.5f * rn, fmaf(-nrm, nrm, nsq), nrm);
+    const float s = (signbit(f) ? -1.f : 1.f) * nrm;             // :16
+    const float newsq = (nsq + fabsf(f) * nrm) * 2.f;            // :19-20
+    const bool some = newsq != 0.f;                              // :22
+    const float rd = some ? rsqrtf(newsq) : 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (8 * t + 7 >= R4) {
+            const int r = g + 8 * t;
+            if (r >= R4) vbuf[r] = (some && r >= J) ? ((r == J ? xs[t] + s : xs[t]) * rd) : 0.f;   // :17,23
+        }
+    }
+    if (g == JJ) dg[Q] = some ? -s : 0.f;                        // :24/26
+    __syncwarp();
+    if (some) {
+        float vr[32 - R4];
+#pragma unroll
+        for (int r = R4; r < 32; r += 4) {
+            const float4 q4 = *reinterpret_cast<const float4 *>(vbuf + r);
+            vr[r - R4] = q4.x; vr[r + 1 - R4] = q4.y; vr[r + 2 - R4] = q4.z; vr[r + 3 - R4] = q4.w;
+        }
+        {   // the pivot's own block of columns: lane JJ keeps v, lanes > JJ are reflected, lanes < JJ are done
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int r = J; r < 32; r += 2) {
+                d0 = fmaf(vr[r - R4], a[Q][r], d0);
+                if (r + 1 < 32) d1 = fmaf(vr[r + 1 - R4], a[Q][r + 1], d1);
+            }
+            const float fac = (g > JJ) ? -2.f * (d0 + d1) : 0.f;
+            const bool piv = g == JJ;
+#pragma unroll
+            for (int r = J; r < 32; ++r) a[Q][r] = piv ? vr[r - R4] : fmaf(fac, vr[r - R4], a[Q][r]);   // reflection.rs:29-30
+        }
+#pragma unroll
+        for (int qq = Q + 1; qq < 4; ++qq) {   // columns right of the pivot block: no predicates at all
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+            for (int r = J; r < 32; r += 4) {
+                d0 = fmaf(vr[r - R4], a[qq][r], d0);
+                if (r + 1 < 32) d1 = fmaf(vr[r + 1 - R4], a[qq][r + 1], d1);
+                if (r + 2 < 32) d2 = fmaf(vr[r + 2 - R4], a[qq][r + 2], d2);
+                if (r + 3 < 32) d3 = fmaf(vr[r + 3 - R4], a[qq][r + 3], d3);
+            }
+            const float fac = -2.f * ((d0 + d1) + (d2 + d3));
+#pragma unroll
+            for (int r = J; r < 32; ++r) a[qq][r] = fmaf(fac, vr[r - R4], a[qq][r]);
+        }
+    }
+    __syncwarp();
+}
+
+// Third generation of the column step: the pivot lane holds its whole column in registers, so it makes the
+// reflector alone (the other lanes run the same instructions on their own column of the block -- free under SIMT --
+// and discard the result) and v crosses shared memory ONCE.  Compared with column_step_fixed this removes one of the
+// two shared-memory round trips and the three shuffles from the dependent chain of a step (ncu: short_scoreboard
+// 1.37 and wait 1.05 stalls per issue with only two warps per scheduler to hide them).  MEASURED: 1.21 ms against
+// 1.06 ms for column_step_fixed -- the redundant norm / scaling arithmetic on eight lanes (+14 % instructions) costs
+// more than the shorter chain saves -- so it is kept only behind batched_quad = 3.
+template <int J>
+__device__ __forceinline__ void column_step_fixed2(float (&a)[4][32], float *vbuf, int g, int lane, float (&dg)[4]) {
+    constexpr int Q = J / 8, JJ = J % 8, R4 = J & ~3;
+    const bool piv = g == JJ;
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+#pragma unroll
+    for (int r = J; r < 32; r += 4) {
+        n0 = fmaf(a[Q][r], a[Q][r], n0);
+        if (r + 1 < 32) n1 = fmaf(a[Q][r + 1], a[Q][r + 1], n1);
+        if (r + 2 < 32) n2 = fmaf(a[Q][r + 2], a[Q][r + 2], n2);
+        if (r + 3 < 32) n3 = fmaf(a[Q][r + 3], a[Q][r + 3], n3);
+    }
+    const float nsq = (n0 + n1) + (n2 + n3);                     // householder.rs:12
+    const float f = a[Q][J];
+    const float rn = nsq > 0.f ? rsqrtf(nsq) : 0.f;
+    float nrm = nsq * rn;                                        // :13
+    nrm = fmaf(0.5f * rn, fmaf(-nrm, nrm, nsq), nrm);
+    const float s = (signbit(f) ? -1.f : 1.f) * nrm;             // :16
+    const float newsq = (nsq + fabsf(f) * nrm) * 2.f;            // :19-20
+    const bool some = newsq != 0.f;                              // :22
+    const float rd = some ? rsqrtf(newsq) : 0.f;
+    float v[32 - R4];
+#pragma unroll
+    for (int r = R4; r < 32; ++r) v[r - R4] = (r < J) ? 0.f : (some ? ((r == J ? a[Q][r] + s : a[Q][r]) * rd) : 0.f);   // :17,23
+    if (piv) {
+#pragma unroll
+        for (int r = R4; r < 32; r += 4)
+            *reinterpret_cast<float4 *>(vbuf + r) = make_float4(v[r - R4], v[r + 1 - R4], v[r + 2 - R4], v[r + 3 - R4]);
+        dg[Q] = some ? -s : 0.f;                                 // :24/26
+        if (some) {
+#pragma unroll
+            for (int r = J; r < 32; ++r) a[Q][r] = v[r - R4];    // the pivot column keeps v
+        }
+    }
+    const bool some_m = __shfl_sync(0xffffffffu, some ? 1 : 0, (lane & 24) + JJ) != 0;    // the pivot lane's verdict
+    __syncwarp();
+    if (some_m) {
+        float vr[32 - R4];
+#pragma unroll
+        for (int r = R4; r < 32; r += 4) {
+            const float4 q4 = *reinterpret_cast<const float4 *>(vbuf + r);
+            vr[r - R4] = q4.x; vr[r + 1 - R4] = q4.y; vr[r + 2 - R4] = q4.z; vr[r + 3 - R4] = q4.w;
+        }
+        {   // the pivot's own block: lanes > JJ are reflected; fac = 0 leaves the others (the pivot lane holds v) alone
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+            for (int r = J; r < 32; r += 4) {
+                d0 = fmaf(vr[r - R4], a[Q][r], d0);
+                if (r + 1 < 32) d1 = fmaf(vr[r + 1 - R4], a[Q][r + 1], d1);
+                if (r + 2 < 32) d2 = fmaf(vr[r + 2 - R4], a[Q][r + 2], d2);
+                if (r + 3 < 32) d3 = fmaf(vr[r + 3 - R4], a[Q][r + 3], d3);
+            }
+            const float fac = (g > JJ) ? -2.f * ((d0 + d1) + (d2 + d3)) : 0.f;
+#pragma unroll
+            for (int r = J; r < 32; ++r) a[Q][r] = fmaf(fac, vr[r - R4], a[Q][r]);   // reflection.rs:29-30
+        }
+#pragma unroll
+        for (int qq = Q + 1; qq < 4; ++qq) {
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+            for (int r = J; r < 32; r += 4) {
+                d0 = fmaf(vr[r - R4], a[qq][r], d0);
+                if (r + 1 < 32) d1 = fmaf(vr[r + 1 - R4], a[qq][r + 1], d1);
+                if (r + 2 < 32) d2 = fmaf(vr[r + 2 - R4], a[qq][r + 2], d2);
+                if (r + 3 < 32) d3 = fmaf(vr[r + 3 - R4], a[qq][r + 3], d3);
+            }
+            const float fac = -2.f * ((d0 + d1) + (d2 + d3));
+#pragma unroll
+            for (int r = J; r < 32; ++r) a[qq][r] = fmaf(fac, vr[r - R4], a[qq][r]);
+        }
+    }
+    __syncwarp();
+}
+
+template <int J0, int GEN>
+__device__ __forceinline__ void column_steps_fixed8(float (&a)[4][32], float *colbuf, float *vbuf, int g, int lane, float (&dg)[4],
+                                                    unsigned gmask) {
+#define LFB_STEP(J)                                                            \
+    if constexpr (GEN == 2) column_step_fixed<J>(a, colbuf, vbuf, g, dg, gmask); \
+    else column_step_fixed2<J>(a, vbuf, g, lane, dg);
+    LFB_STEP(J0 + 0) LFB_STEP(J0 + 1) LFB_STEP(J0 + 2) LFB_STEP(J0 + 3)
+    LFB_STEP(J0 + 4) LFB_STEP(J0 + 5) LFB_STEP(J0 + 6) LFB_STEP(J0 + 7)
+#undef LFB_STEP
+}
+
+template <int GEN>
+__global__ void __launch_bounds__(128, 2) qr_batched4_32_kernel(float *__restrict__ A, int64_t batch, float *__restrict__ diag) {
+    __shared__ __align__(16) float s_col[4][4][32];
+    __shared__ __align__(16) float s_v[4][4][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane & 7, grp = lane >> 3;
+    float *colbuf = s_col[warp][grp], *vbuf = s_v[warp][grp];
+    const unsigned gmask = 0xffu << (lane & 24);
+    const int64_t nquads = (batch + 3) / 4;
+    for (int64_t qd = (int64_t)blockIdx.x * 4 + warp; qd < nquads; qd += (int64_t)gridDim.x * 4) {
+        const int64_t b = qd * 4 + grp;
+        const bool live = b < batch;
+        float *mat = A + (live ? b : 0) * 1024;
+        float a[4][32];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[q][i] = live ? mat[i * 32 + 8 * q + g] : 0.f;
+        float dg[4] = {0.f, 0.f, 0.f, 0.f};
+        column_steps_fixed8<0, GEN>(a, colbuf, vbuf, g, lane, dg, gmask);
+        column_steps_fixed8<8, GEN>(a, colbuf, vbuf, g, lane, dg, gmask);
+        column_steps_fixed8<16, GEN>(a, colbuf, vbuf, g, lane, dg, gmask);
+        column_steps_fixed8<24, GEN>(a, colbuf, vbuf, g, lane, dg, gmask);
+        // reference sign convention, applied once: running sign P_r over the pivots of this matrix
+        float p = 1.f, prev[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (8 * q + g == r) prev[q] = p;                                 // P_{c-1}
+            const float br = __shfl_sync(0xffffffffu, dg[r >> 3], (lane & 24) + (r & 7));
+            if (br != 0.f) p = signbit(br) ? -1.f : 1.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (8 * q + 7 > r && r < 8 * q + g) a[q][r] *= p;                // R[r, c] *= P_r
+        }
+        if (live) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = 8 * q + g;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mat[i * 32 + c] = (i < c) ? a[q][i] : prev[q] * a[q][i];
+                diag[b * 32 + c] = prev[q] * dg[q];
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void __launch_bounds__(128, 2) qr_batched4_kernel(float *__restrict__ A, int64_t batch, int m, int n, float *__restrict__ diag) {
     __shared__ __align__(16) float s_col[4][4][32];
     __shared__ __align__(16) float s_v[4][4][32];
@@ -284,7 +507,12 @@ void qr_batched(lfb_handle &h, T *A, int64_t batch, int64_t m, int64_t n, T *dia
     if constexpr (sizeof(T) == 4) {
         if (h.opt.batched_quad) {
             int64_t blocks4 = std::min<int64_t>(cdiv(cdiv(batch, 4), 4), (int64_t)h.sm_count * 16);
-            qr_batched4_kernel<<<(unsigned)blocks4, 128, 0, h.stream>>>(A, batch, (int)m, (int)n, diag);
+            if (m == 32 && n == 32 && h.opt.batched_quad >= 3)
+                qr_batched4_32_kernel<3><<<(unsigned)blocks4, 128, 0, h.stream>>>(A, batch, diag);
+            else if (m == 32 && n == 32 && h.opt.batched_quad == 2)
+                qr_batched4_32_kernel<2><<<(unsigned)blocks4, 128, 0, h.stream>>>(A, batch, diag);
+            else
+                qr_batched4_kernel<<<(unsigned)blocks4, 128, 0, h.stream>>>(A, batch, (int)m, (int)n, diag);
             LFB_LAUNCH_CHECK(h);
             return;
         }

@@ -49,7 +49,8 @@ struct Options {
     int64_t panel_cluster = 2; // cluster/DSMEM panel kernel: 2 = second generation, 1 = first, 0 = per-column launches
     int64_t lookahead = 1;     // factor the next panel on a side stream while the trailing update runs
     int64_t panel_cluster_max = 16; // largest cluster size tried (16 is non-portable but supported on B200)
-    int64_t batched_quad = 1;       // f32 batched QR: four matrices per warp
+    int64_t batched_quad = 2;       // f32 batched QR: 1 = four matrices per warp; 32 x 32: 2 = compile-time column steps (1.06 ms),
+                                    // 3 = reflector made by the pivot lane alone, one shared-memory trip per step (measured slower: 1.21 ms)
     int64_t tsqr_chunk = 12288;     // rows per concurrently factored chunk (12288 x 32 f64 is the widest sub-panel a 16-CTA cluster holds)
     int64_t trd_fused = 1;          // tridiagonalisation: cluster head kernel + lower-triangle SYMV (0 = first generation)
     int64_t trd_symv_async = 1;     // SYMV tiles staged through shared memory with cp.async (0 = direct register loads)
