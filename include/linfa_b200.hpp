@@ -84,6 +84,12 @@ inline int tridiag(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, i
 inline int tridiag(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *off) { return lfb_sym_tridiagonal_f32(h, a, r, c, rs, cs, off); }
 inline int bidiag(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *d, double *e) { return lfb_bidiagonal_f64(h, a, r, c, rs, cs, d, e); }
 inline int bidiag(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *d, float *e) { return lfb_bidiagonal_f32(h, a, r, c, rs, cs, d, e); }
+inline int eigh(lfb_handle *h, const double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *v, double *q, int64_t qrs, int64_t qcs) { return lfb_eigh_f64(h, a, r, c, rs, cs, v, q, qrs, qcs); }
+inline int eigh(lfb_handle *h, const float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *v, float *q, int64_t qrs, int64_t qcs) { return lfb_eigh_f32(h, a, r, c, rs, cs, v, q, qrs, qcs); }
+inline int svd(lfb_handle *h, const double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *s, double *u, int64_t urs, int64_t ucs, double *vt, int64_t vrs, int64_t vcs) { return lfb_svd_f64(h, a, r, c, rs, cs, s, u, urs, ucs, vt, vrs, vcs); }
+inline int svd(lfb_handle *h, const float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *s, float *u, int64_t urs, int64_t ucs, float *vt, int64_t vrs, int64_t vcs) { return lfb_svd_f32(h, a, r, c, rs, cs, s, u, urs, ucs, vt, vrs, vcs); }
+inline int least_squares(lfb_handle *h, const double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, const double *b, int64_t br, int64_t bc, int64_t brs, int64_t bcs, double *x, int64_t xrs, int64_t xcs) { return lfb_least_squares_f64(h, a, r, c, rs, cs, b, br, bc, brs, bcs, x, xrs, xcs); }
+inline int least_squares(lfb_handle *h, const float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, const float *b, int64_t br, int64_t bc, int64_t brs, int64_t bcs, float *x, int64_t xrs, int64_t xcs) { return lfb_least_squares_f32(h, a, r, c, rs, cs, b, br, bc, brs, bcs, x, xrs, xcs); }
 template <typename T> T signum(T x) { return std::signbit(x) ? T(-1) : T(1); }
 }  // namespace detail
 
@@ -212,6 +218,50 @@ BidiagonalDecomp<T> bidiagonal(Engine &e, View<T> a) {
     e.check(detail::bidiag(e.handle(), a.ptr, a.rows, a.cols, a.rs, a.cs, d.data(), off.data()));
     off.resize((size_t)(md - 1));
     return {e, a, std::move(d), std::move(off), a.rows >= a.cols};
+}
+
+// eigh.rs:202-268 EighInto / EigValshInto: eigenvalues in the reference's (unsorted) order, eigenvectors as columns.
+template <typename T>
+std::pair<std::vector<T>, Matrix<T>> eigh_into(Engine &e, View<T> a) {
+    if (a.rows != a.cols) throw NotSquare(a.rows, a.cols);
+    std::vector<T> vals((size_t)a.rows, T(0));
+    Matrix<T> vecs(a.rows, a.rows);
+    if (a.rows) e.check(detail::eigh(e.handle(), a.ptr, a.rows, a.cols, a.rs, a.cs, vals.data(), vecs.data.data(), a.rows, 1));
+    return {std::move(vals), std::move(vecs)};
+}
+template <typename T>
+std::vector<T> eigvalsh_into(Engine &e, View<T> a) {
+    if (a.rows != a.cols) throw NotSquare(a.rows, a.cols);
+    std::vector<T> vals((size_t)a.rows, T(0));
+    if (a.rows) e.check(detail::eigh(e.handle(), a.ptr, a.rows, a.cols, a.rs, a.cs, vals.data(), (T *)nullptr, 0, 0));
+    return vals;
+}
+
+// svd.rs:415-479 SVDInto: (u, sigma, vt); u / vt are empty matrices when not requested.
+template <typename T>
+struct SvdResult { Matrix<T> u; std::vector<T> sigma; Matrix<T> vt; };
+template <typename T>
+SvdResult<T> svd_into(Engine &e, View<T> a, bool calc_u, bool calc_vt) {
+    if (a.rows == 0 || a.cols == 0) throw EmptyMatrix();
+    const int64_t dim = std::min(a.rows, a.cols);
+    SvdResult<T> r;
+    r.sigma.assign((size_t)dim, T(0));
+    if (calc_u) r.u = Matrix<T>(a.rows, dim);
+    if (calc_vt) r.vt = Matrix<T>(dim, a.cols);
+    e.check(detail::svd(e.handle(), a.ptr, a.rows, a.cols, a.rs, a.cs, r.sigma.data(), calc_u ? r.u.data.data() : (T *)nullptr, dim, 1,
+                        calc_vt ? r.vt.data.data() : (T *)nullptr, a.cols, 1));
+    return r;
+}
+
+// qr.rs:207-229 LeastSquaresQrInto (thin and wide), one library call.
+template <typename T>
+Matrix<T> least_squares_into(Engine &e, View<T> a, View<T> b) {
+    if (a.rows != b.rows) throw WrongRows(a.rows, b.rows);
+    Matrix<T> x(a.cols, b.cols);
+    const int st = detail::least_squares(e.handle(), a.ptr, a.rows, a.cols, a.rs, a.cs, b.ptr, b.rows, b.cols, b.rs, b.cs, x.data.data(), b.cols, 1);
+    if (st == LFB_NON_INVERTIBLE) throw NonInvertible();
+    e.check(st);
+    return x;
 }
 
 }  // namespace linfa_b200
