@@ -1,6 +1,8 @@
 // extern "C" entry points of liblinfa_b200.so (include/linfa_b200.h): argument checks that mirror
 // the reference's LinalgError behaviour, packing of arbitrary-stride host views into the engine's
 // column-major HBM layout, and the device-resident variants.
+#include <memory>
+
 #include "common.cuh"
 
 using namespace lfb;
@@ -185,9 +187,66 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
         }
         transpose<T>(*h, tmp.get(), n, n, hld, dA, ld);   // the unread upper triangle carries whatever tmp held
     }
-    cholesky_lower<T>(*h, dA, n, ld, clean, dInfo);
+    // Dirty factorisation of a large matrix: every finished block column of L starts its way back to the host as
+    // soon as its panel is factored (a copy stream waits on an event recorded behind the panel), so the D2H traffic
+    // hides behind the trailing updates instead of following the factorisation.
+    // Only for page-locked host memory: a D2H copy into pageable memory is staged synchronously and would stall
+    // the thread that is still enqueueing the factorisation.
+    bool pinned_host = false;
+    {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, a) == cudaSuccess) pinned_host = pa.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
+    const bool overlap = tri && !clean && h->opt.chol_overlap_d2h && pinned_host;
+    std::vector<cudaEvent_t> pev;
+    std::unique_ptr<DevBuf<T>> stage;
+    if (overlap) {
+        if (!h->copy_stream) LFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        if (lay != L_COL) stage.reset(new DevBuf<T>(*h, (size_t)n * n));
+        lfb_handle *hh = h;
+        T *dAp = dA.get();
+        T *stg = stage ? stage->get() : nullptr;
+        h->chol_panel_hook = [hh, dAp, stg, a, n, ld, hld, lay, &pev](int64_t k0, int64_t nb) {
+            cudaEvent_t e;
+            LFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            pev.push_back(e);
+            LFB_CUDA(cudaEventRecord(e, hh->stream));
+            LFB_CUDA(cudaStreamWaitEvent(hh->copy_stream, e, 0));
+            const int64_t below = n - k0;
+            if (lay == L_COL) {      // host column-major: the block column is a 2-D copy as it is
+                LFB_CUDA(cudaMemcpy2DAsync(a + k0 + k0 * hld, hld * sizeof(T), dAp + k0 + k0 * ld, ld * sizeof(T), below * sizeof(T), nb,
+                                           cudaMemcpyDeviceToHost, hh->copy_stream));
+            } else {                 // host row-major: transpose the block column into nb-wide rows first
+                T *t = stg + (size_t)k0 * n;
+                cudaStream_t keep = hh->stream;
+                hh->stream = hh->copy_stream;
+                try {
+                    transpose<T>(*hh, dAp + k0 + k0 * ld, below, nb, ld, t, nb);
+                } catch (...) {
+                    hh->stream = keep;
+                    throw;
+                }
+                hh->stream = keep;
+                LFB_CUDA(cudaMemcpy2DAsync(a + k0 * hld + k0, hld * sizeof(T), t, nb * sizeof(T), nb * sizeof(T), below, cudaMemcpyDeviceToHost,
+                                           hh->copy_stream));
+            }
+        };
+    }
+    try {
+        cholesky_lower<T>(*h, dA, n, ld, clean, dInfo);
+    } catch (...) {
+        h->chol_panel_hook = nullptr;
+        for (auto e : pev) cudaEventDestroy(e);
+        throw;
+    }
+    h->chol_panel_hook = nullptr;
     LFB_CUDA(cudaMemcpyAsync(&info, dInfo.get(), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-    if (!tri || clean) {
+    if (overlap) {
+        LFB_CUDA(cudaStreamSynchronize(h->copy_stream));
+        LFB_CUDA(cudaStreamSynchronize(h->stream));
+        for (auto e : pev) cudaEventDestroy(e);
+    } else if (!tri || clean) {
         download<T>(*h, dA, ld, a, n, n, rs, cs);
     } else if (lay == L_COL) {
         for (int64_t c0 = 0; c0 < n; c0 += BAND) {
@@ -522,6 +581,7 @@ int lfb_destroy(lfb_handle *h) {
     h->subs.clear();
     for (auto &b : h->blocks) cudaFree(b.p);
     if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
@@ -585,6 +645,7 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     else if (k == "tsqr_streams") h->opt.tsqr_streams = value;
     else if (k == "tsqr_graph") h->opt.tsqr_graph = value;
     else if (k == "trd_fused") h->opt.trd_fused = value;
+    else if (k == "chol_overlap_d2h") h->opt.chol_overlap_d2h = value;
     else if (k == "rot_staged") h->opt.rot_staged = value;
     else if (k == "eigh_stable_2x2") h->opt.eigh_stable_2x2 = value;
     else if (k == "rot_serial") h->opt.rot_serial = value;

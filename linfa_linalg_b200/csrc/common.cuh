@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -60,6 +61,7 @@ struct Options {
     int64_t rot_serial = 0;         // debug: one chain per pass
     int64_t eigh_stable_2x2 = 1;    // eigh.rs:111 basis without cancellation (0 = the reference's formula verbatim)
     int64_t fast_hypot = 1;         // host recurrence: sqrt(x^2 + y^2) instead of hypot when far from underflow
+    int64_t chol_overlap_d2h = 1;   // host Cholesky (dirty, n >= 2048): finished block columns go back to the host during the factorisation
     int64_t tsqr_streams = 8;       // chunks in flight (each panel kernel occupies one 16-SM cluster)
     int64_t tsqr_graph = 0;         // 1: replay the local TSQR stage of a (buffer, shape) seen before as one CUDA graph
                                     // (measured: 145 vs 147 ms -- the stage is GPU bound, not launch bound -- so off by default)
@@ -96,6 +98,11 @@ struct lfb_handle {
     std::vector<GraphEntry> graphs;
     bool in_capture = false;
     cudaEvent_t ev_graph[2] = {nullptr, nullptr};
+
+    // ---- Cholesky host path: called (at enqueue time) right after panel [k0, k0 + nb) has been factored on `stream`,
+    //      so that the finished block column can start its way back to the host while the trailing update runs ----
+    std::function<void(int64_t k0, int64_t nb)> chol_panel_hook;
+    cudaStream_t copy_stream = nullptr;
     void drop_graphs() {
         for (auto &g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
         graphs.clear();

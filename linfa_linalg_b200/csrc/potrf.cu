@@ -215,6 +215,7 @@ void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64
     cudaStream_t sm = h.stream, sp = h.aux_stream;
     const bool la = h.opt.lookahead && sp != nullptr && !h.prof_on && n >= 4 * NB;
     factor_panel(0, std::min<int64_t>(NB, n));
+    if (h.chol_panel_hook) h.chol_panel_hook(0, std::min<int64_t>(NB, n));
     for (int64_t k0 = 0; k0 < n; k0 += NB) {
         const int64_t nb = std::min<int64_t>(NB, n - k0);
         const int64_t pend = k0 + nb;
@@ -229,6 +230,7 @@ void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64
             h.stream = sp;
             try {
                 factor_panel(pend, nbn);
+                if (h.chol_panel_hook) h.chol_panel_hook(pend, nbn);     // h.stream is the side stream here
             } catch (...) {
                 h.stream = sm;
                 throw;
@@ -244,6 +246,7 @@ void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64
         } else {
             gemm<T>(h, 0, 1, rows, rows, nb, T(-1), P, ld, P, ld, T(1), A + pend + pend * ld, ld, /*lower_only=*/1);
             factor_panel(pend, nbn);
+            if (h.chol_panel_hook) h.chol_panel_hook(pend, nbn);
         }
     }
     if (clean) triangular_zero<T>(h, A, n, ld, /*keep_lower=*/1);

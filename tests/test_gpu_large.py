@@ -171,3 +171,30 @@ def test_eigh_1500_properties():
     assert np.linalg.norm(a0 @ vecs - vecs * vals[None, :]) <= 64 * n * EPS * s
     assert np.linalg.norm(vecs.T @ vecs - np.eye(n)) <= 64 * n * EPS
     assert np.max(np.abs(np.sort(L.eigvalsh(a0)) - np.sort(vals))) <= 64 * n * EPS * s
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_cholesky_dirty_pinned_overlapped_download(order):
+    """Page-locked host matrices take the overlapped path: every finished block column of L is copied back while the
+    trailing updates still run.  Same contract as the plain path: strict upper triangle untouched, L L^T = A."""
+    import torch
+    import linfa_linalg_b200 as L
+    n = 3000
+    rng = np.random.default_rng(8)
+    g = rng.uniform(-1, 1, (n, n))
+    a0 = (g + g.T) / 2 + n * np.eye(n)
+    a0[np.triu_indices(n, 1)] = rng.uniform(5, 6, n * (n - 1) // 2)
+    pinned = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
+    a = pinned.numpy() if order == "C" else pinned.numpy().T            # row-major / column-major views of pinned memory
+    a[...] = a0
+    L.cholesky_inplace_dirty(a)
+    np.testing.assert_array_equal(np.triu(a, 1), np.triu(a0, 1))
+    l = np.tril(a)
+    sym = np.tril(a0) + np.tril(a0, -1).T
+    assert np.linalg.norm(l @ l.T - sym) <= 8 * n * EPS * np.linalg.norm(sym)
+    e2 = L.Engine(0)
+    e2.set_option("chol_overlap_d2h", 0)
+    b = a0.copy()
+    L.cholesky_inplace_dirty(b, e2)
+    e2.close()
+    assert np.max(np.abs(np.tril(a) - np.tril(b))) <= 8 * n * EPS * np.linalg.norm(sym, 2)
