@@ -399,13 +399,15 @@ __global__ void __launch_bounds__(HNT) trd_head_kernel(T *A, int64_t ld, int64_t
     __shared__ T sred[HNT / 32][2];
     __shared__ T stt[2 * TB];
     __shared__ T cw[TB], cv[TB], t1[TB], t2[TB];
-    __shared__ T wpart[HNT / 32][16];
+    __shared__ T sv[HNT];
     __shared__ T inbox[16][2 * TB];
     const int par = j & 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t stride = (int64_t)nc * HNT;
     const int64_t first = i + (int64_t)b * HNT + threadIdx.x;
     const int jp = j - 1;
+    const bool single = first + stride >= n;          // this thread owns at most one row: it stays in registers across the phases
+    T keep_p = T(0), keep_v = T(0), keep_c = T(0), keep_x = T(0);
     T *col = A + i * ld;
     const T *vp = V + (int64_t)(jp > 0 ? jp : 0) * ldv;
     T *wp = Wm + (int64_t)(jp > 0 ? jp : 0) * ldv;
@@ -432,6 +434,7 @@ __global__ void __launch_bounds__(HNT) trd_head_kernel(T *A, int64_t ld, int64_t
         T part = T(0);
         for (int64_t r = first; r < n; r += stride) {
             T pr = P[r], S = T(0);
+            const T vjp_ = vp[r];                         // issued with the panel rows, used after them
             for (int kb = 0; kb < jp; kb += 16) {
                 T vv[16], ww[16];
 #pragma unroll
@@ -446,9 +449,11 @@ __global__ void __launch_bounds__(HNT) trd_head_kernel(T *A, int64_t ld, int64_t
                     S += vv[q] * cw[kb + q] + ww[q] * cv[kb + q];
                 }
             }
-            P2[r] = pr;
-            if (!final_only) col[r] -= S;
-            part += vp[r] * pr;
+            T cx = T(0);
+            if (!final_only) { cx = col[r] - S; if (!single) col[r] = cx; }
+            if (!single) P2[r] = pr;
+            keep_p = pr; keep_v = vjp_; keep_c = cx;      // a thread that owns one row keeps it in registers
+            part += vjp_ * pr;
         }
         T dummy;
         cluster_sum2<T, HNT>(cl, part, T(0), slotA, sred, resA, dprev, dummy);
@@ -461,16 +466,17 @@ __global__ void __launch_bounds__(HNT) trd_head_kernel(T *A, int64_t ld, int64_t
     for (int64_t r = first; r < n; r += stride) {
         T xx = T(0);
         if (j > 0) {
-            const T vjp = vp[r];
-            const T w = P2[r] - dprev * vjp;
+            const T vjp = single ? keep_v : vp[r];
+            const T w = (single ? keep_p : P2[r]) - dprev * vjp;
             wp[r] = w;
             if (!final_only) {
-                xx = col[r] - (vjp * cw[jp] + w * cv[jp]);
-                col[r] = xx;
+                xx = (single ? keep_c : col[r]) - (vjp * cw[jp] + w * cv[jp]);
+                if (!single || r == i) col[r] = xx;       // row i is the diagonal entry d_i; the rest is rewritten below
             }
         } else {
             xx = col[r];
         }
+        keep_x = xx;
         if (r > i) {
             part += xx * xx;
             if (r == i + 1) headv = xx;
@@ -493,50 +499,46 @@ __global__ void __launch_bounds__(HNT) trd_head_kernel(T *A, int64_t ld, int64_t
         acc->some = some ? 1 : 0;
     }
     T *vout = V + (int64_t)j * ldv;
-    for (int64_t r = first; r < n; r += stride) {
-        if (r <= i) continue;
+    // ---- the reflector, and W^T v / V^T v: the CTA's rows of one pass are a contiguous block of HNT rows; v is staged
+    //      in shared memory and warp k % 16 takes panel column k with 2 x 16 independent coalesced loads per lane ----
+    for (int64_t base = i + (int64_t)b * HNT; base < n; base += stride) {
+        const int64_t r = base + threadIdx.x;
         T v = T(0);
+        if (r < n && r > i) {
+            const T xx = single ? keep_x : col[r];
+            if (some) v = ((r == i + 1) ? xx + s : xx) / d;
+            col[r] = some ? v : xx;
+            vout[r] = v;
+            P[r] = T(0);                                 // target of the SYMV that follows
+        }
+        sv[threadIdx.x] = v;
+        __syncthreads();
         if (some) {
-            const T xx = col[r];
-            v = ((r == i + 1) ? xx + s : xx) / d;
-            col[r] = v;
-        }
-        vout[r] = v;
-        P[r] = T(0);                                 // target of the SYMV that follows
-    }
-    // ---- W^T v and V^T v, eight panel columns at a time: per-thread products, transpose-reduce in the warp ----
-    if (some) {
-        for (int kb = 0; kb < j; kb += 8) {
-            T c[16];
+            for (int k = warp; k < j; k += HNT / 32) {
+                const T *wk = Wm + (int64_t)k * ldv + base, *vk = V + (int64_t)k * ldv + base;
+                T lw[HNT / 32], lv[HNT / 32];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) c[q] = T(0);
-            for (int64_t r = first; r < n; r += stride) {
-                if (r <= i) continue;
-                const T v = vout[r];
-                T vv[8], ww[8];
+                for (int q = 0; q < HNT / 32; ++q) {
+                    const int t = lane + 32 * q;
+                    const bool ok = base + t < n;
+                    lw[q] = ok ? wk[t] : T(0);
+                    lv[q] = ok ? vk[t] : T(0);
+                }
+                T s1 = T(0), s2 = T(0);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const bool ok = kb + q < j;
-                    vv[q] = ok ? V[r + (int64_t)(kb + q) * ldv] : T(0);
-                    ww[q] = ok ? Wm[r + (int64_t)(kb + q) * ldv] : T(0);
+                for (int q = 0; q < HNT / 32; ++q) {
+                    s1 += lw[q] * sv[lane + 32 * q];
+                    s2 += lv[q] * sv[lane + 32 * q];
                 }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    c[q] += ww[q] * v;
-                    c[8 + q] += vv[q] * v;
+                for (int o = 16; o > 0; o >>= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                 }
+                if (lane == 0) { stt[k] += s1; stt[TB + k] += s2; }   // warp k % 16 owns entry k
             }
-            warp_transpose_reduce16<T>(c, lane);
-            if (lane < 16) wpart[warp][lane] = c[0];
-            __syncthreads();
-            if (threadIdx.x < 16) {
-                T sum = T(0);
-#pragma unroll
-                for (int w = 0; w < HNT / 32; ++w) sum += wpart[w][threadIdx.x];
-                stt[(threadIdx.x < 8 ? 0 : TB - 8) + kb + threadIdx.x] = sum;
-            }
-            __syncthreads();
         }
+        __syncthreads();
     }
     // push the per-CTA partials into rank 0's inbox (parallel DSMEM stores), one barrier, local sum
     if (threadIdx.x < 2 * TB) cl.map_shared_rank(&inbox[0][0], 0)[b * 2 * TB + threadIdx.x] = stt[threadIdx.x];
