@@ -258,11 +258,13 @@ __global__ void __launch_bounds__(HNT) bd_head_kernel(const HeadArgs<T> a) {
     __shared__ T sred[HNT / 32][2];
     __shared__ T stt[2 * TB + 2];
     __shared__ T ta[TB + 1], tb[TB + 1], ca[TB + 1], cb[TB + 1];
-    __shared__ T wpart[HNT / 32][16];
+    __shared__ T sw[HNT];
     __shared__ T inbox[16][2 * TB + 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t stride = (int64_t)nc * HNT;
     const int64_t first = a.t0 + (int64_t)b * HNT + threadIdx.x;
+    const bool single = first + stride >= a.tn;        // at most one entry per thread: it stays in a register
+    T keep_x = T(0);
     const T sigma = a.st->sigma;
     if (threadIdx.x <= TB) {
         const int k = threadIdx.x;
@@ -303,7 +305,8 @@ __global__ void __launch_bounds__(HNT) bd_head_kernel(const HeadArgs<T> a) {
         }
         if (!a.final_only) {
             const T xx = a.src[t * a.sinc] - S;
-            a.src[t * a.sinc] = xx;
+            if (!single) a.src[t * a.sinc] = xx;
+            keep_x = xx;                                   // a thread that owns one entry keeps it in a register
             part += xx * xx;
             if (t == a.t0) headv = xx;
         }
@@ -317,45 +320,47 @@ __global__ void __launch_bounds__(HNT) bd_head_kernel(const HeadArgs<T> a) {
     const T newsq = (nsq + t_abs(fh) * nrm) * T(2);
     const bool some = newsq != T(0);
     const T dd = t_sqrt(newsq);
-    for (int64_t t = first; t < a.tn; t += stride) {
-        const T xx = a.src[t * a.sinc];
+    // ---- the reflector, then P1^T w and P2^T w: the CTA's entries of one pass are a contiguous block of HNT; w is
+    //      staged in shared memory and warp k % 16 takes panel column k of both matrices (coalesced, independent loads) ----
+    const int nt = a.n1t > a.n2t ? a.n1t : a.n2t;
+    for (int64_t base = a.t0 + (int64_t)b * HNT; base < a.tn; base += stride) {
+        const int64_t t = base + threadIdx.x;
         T w = T(0);
-        if (some) w = ((t == a.t0) ? xx + s : xx) / dd;
-        a.src[t * a.sinc] = sigma * (some ? w : xx);     // what the reference stores (householder.rs:23 on sigma x)
-        a.pout[t] = w;
-    }
-    // ---- P1^T w and P2^T w, eight panel columns at a time ----
-    if (some) {
-        const int nt = a.n1t > a.n2t ? a.n1t : a.n2t;
-        for (int kb = 0; kb < nt; kb += 8) {
-            T c[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) c[q] = T(0);
-            for (int64_t t = first; t < a.tn; t += stride) {
-                const T w = a.pout[t];
-                T p1[8], p2[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    p1[q] = (kb + q < a.n1t) ? a.P1[t + (int64_t)(kb + q) * a.ldp] : T(0);
-                    p2[q] = (kb + q < a.n2t) ? a.P2[t + (int64_t)(kb + q) * a.ldp] : T(0);
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    c[q] += p1[q] * w;
-                    c[8 + q] += p2[q] * w;
-                }
-            }
-            warp_transpose_reduce16<T>(c, lane);
-            if (lane < 16) wpart[warp][lane] = c[0];
-            __syncthreads();
-            if (threadIdx.x < 16) {
-                T sum = T(0);
-#pragma unroll
-                for (int w = 0; w < HNT / 32; ++w) sum += wpart[w][threadIdx.x];
-                stt[(threadIdx.x < 8 ? 0 : TB + 1 - 8) + kb + threadIdx.x] = sum;
-            }
-            __syncthreads();
+        if (t < a.tn) {
+            const T xx = single ? keep_x : a.src[t * a.sinc];
+            if (some) w = ((t == a.t0) ? xx + s : xx) / dd;
+            a.src[t * a.sinc] = sigma * (some ? w : xx);     // what the reference stores (householder.rs:23 on sigma x)
+            a.pout[t] = w;
         }
+        sw[threadIdx.x] = w;
+        __syncthreads();
+        if (some) {
+            for (int k = warp; k < nt; k += HNT / 32) {
+                const T *p1 = a.P1 + (int64_t)k * a.ldp + base, *p2 = a.P2 + (int64_t)k * a.ldp + base;
+                const bool k1 = k < a.n1t, k2 = k < a.n2t;
+                T l1[HNT / 32], l2[HNT / 32];
+#pragma unroll
+                for (int q = 0; q < HNT / 32; ++q) {
+                    const int tt = lane + 32 * q;
+                    const bool ok = base + tt < a.tn;
+                    l1[q] = (ok && k1) ? p1[tt] : T(0);
+                    l2[q] = (ok && k2) ? p2[tt] : T(0);
+                }
+                T s1 = T(0), s2 = T(0);
+#pragma unroll
+                for (int q = 0; q < HNT / 32; ++q) {
+                    s1 += l1[q] * sw[lane + 32 * q];
+                    s2 += l2[q] * sw[lane + 32 * q];
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                if (lane == 0) { stt[k] += s1; stt[TB + 1 + k] += s2; }   // warp k % 16 owns entry k
+            }
+        }
+        __syncthreads();
     }
     if (threadIdx.x < 2 * TB + 2) cl.map_shared_rank(&inbox[0][0], 0)[b * (2 * TB + 2) + threadIdx.x] = stt[threadIdx.x];
     cl.sync();
