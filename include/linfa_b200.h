@@ -183,6 +183,11 @@ int lfb_bidiagonal_f32(lfb_handle *h, float *a, int64_t rows, int64_t cols, int6
 /* a: [batch][m][n] contiguous, diag: [batch][n].  Batch-sharded across GPUs by the caller. */
 int lfb_qr_batched_f32(lfb_handle *h, float *a, int64_t batch, int64_t m, int64_t n, float *diag);
 int lfb_qr_batched_f64(lfb_handle *h, double *a, int64_t batch, int64_t m, int64_t n, double *diag);
+/* cholesky.rs:51-83 over `batch` packed row-major n x n matrices (n <= 32), in place (clean != 0 zeroes the strict upper
+ * triangles, cholesky.rs:78-82).  LFB_NOT_POSITIVE_DEFINITE if any matrix fails: *fail_matrix / *fail_index name the
+ * first one in batch order and its failing row.  Batch-sharded across GPUs like lfb_qr_batched_*. */
+int lfb_cholesky_batched_f32(lfb_handle *h, float *a, int64_t batch, int64_t n, int clean, int64_t *fail_matrix, int64_t *fail_index);
+int lfb_cholesky_batched_f64(lfb_handle *h, double *a, int64_t batch, int64_t n, int clean, int64_t *fail_matrix, int64_t *fail_index);
 
 /* ---- device-resident entry points (column-major, leading dimension, async on the stream) ----- */
 int lfb_qr_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_diag);
@@ -203,6 +208,8 @@ int lfb_svd_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int6
 int lfb_bidiagonal_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_d, double *d_e);
 /* batched: d_a is [batch][m][n] row-major packed (the ndarray layout), in place */
 int lfb_qr_batched_dev_f32(lfb_handle *h, float *d_a, int64_t batch, int64_t m, int64_t n, float *d_diag);
+/* d_fail: device int[batch], first failing row per matrix or -1. */
+int lfb_cholesky_batched_dev_f32(lfb_handle *h, float *d_a, int64_t batch, int64_t n, int clean, int *d_fail);
 /* Tall-skinny local stage of TSQR: R (cols x cols, column-major ldr, diag >= 0, strict lower zeroed)
  * of a rows x cols column-major block.  d_a is overwritten (compact local factor). */
 int lfb_tsqr_local_r_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_r, int64_t ldr);

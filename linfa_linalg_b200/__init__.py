@@ -20,7 +20,7 @@ from ._ffi import LOWER, UPPER  # noqa: F401  (triangular.rs:10-13 UPLO)
 __all__ = [
     "LinalgError", "NotSquare", "NotThin", "NotPositiveDefinite", "NonInvertible", "EmptyMatrix", "WrongRows",
     "Engine", "engine", "UPPER", "LOWER",
-    "qr", "qr_into", "QRDecomp", "least_squares", "least_squares_into", "qr_batched",
+    "qr", "qr_into", "QRDecomp", "least_squares", "least_squares_into", "qr_batched", "cholesky_batched",
     "cholesky", "cholesky_dirty", "cholesky_into", "cholesky_into_dirty", "cholesky_inplace", "cholesky_inplace_dirty",
     "solvec", "solvec_into", "solvec_inplace", "invc", "invc_inplace",
     "solve_triangular", "solve_triangular_into", "solve_triangular_inplace", "triangular_inplace", "into_triangular",
@@ -293,6 +293,24 @@ def qr_batched(a: np.ndarray, eng: Engine | None = None) -> np.ndarray:
     st = e.call("lfb_qr_batched" + _sfx(a), C.c_void_p(a.ctypes.data), batch, m, n, _vecp(diag))
     e._check(st)
     return diag
+
+
+def cholesky_batched(a: np.ndarray, clean: bool = True, eng: Engine | None = None) -> np.ndarray:
+    """cholesky.rs:51-83 over a C-contiguous [batch][n][n] array (n <= 32), in place.  NotPositiveDefinite carries the
+    failing row of the FIRST failing matrix (`.index`) and that matrix's position in the batch (`.matrix`)."""
+    e = eng or engine()
+    assert a.ndim == 3 and a.flags.c_contiguous
+    batch, n, n2 = a.shape
+    if n != n2:
+        raise NotSquare(n, n2)
+    fm, fi = C.c_int64(-1), C.c_int64(-1)
+    st = e.call("lfb_cholesky_batched" + _sfx(a), C.c_void_p(a.ctypes.data), batch, n, int(clean), C.byref(fm), C.byref(fi))
+    if st == _ffi.NOT_POSITIVE_DEFINITE:
+        err = NotPositiveDefinite(fi.value)
+        err.matrix = fm.value
+        raise err
+    e._check(st)
+    return a
 
 
 # ---- Cholesky: src/cholesky.rs -----------------------------------------------------------------

@@ -52,6 +52,7 @@ _TYPED = {
     "lfb_invc": [_vp] + _VIEW + [_vp, _i64, _i64, C.POINTER(_i64)],
     "lfb_svd": [_vp] + _VIEW + [_vp, _vp, _i64, _i64, _vp, _i64, _i64],
     "lfb_qr_batched": [_vp, _vp, _i64, _i64, _i64, _vp],
+    "lfb_cholesky_batched": [_vp, _vp, _i64, _i64, _int, C.POINTER(_i64), C.POINTER(_i64)],
     "lfb_qr_dev": [_vp, _vp, _i64, _i64, _i64, _vp],
     "lfb_cholesky_dev": [_vp, _vp, _i64, _i64, _int, _vp],
 }
@@ -65,6 +66,7 @@ SIGNATURES.update({
     "lfb_eigh_dev_f64": [_vp, _vp, _i64, _i64, _vp, _vp, _i64],
     "lfb_svd_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _i64],
     "lfb_qr_batched_dev_f32": [_vp, _vp, _i64, _i64, _i64, _vp],
+    "lfb_cholesky_batched_dev_f32": [_vp, _vp, _i64, _i64, _int, _vp],
     "lfb_tsqr_local_r_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
     "lfb_gemm_dev_f64": [_vp, _int, _int, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _dbl, _vp, _i64],
     "lfb_gemm_dev_f32": [_vp, _int, _int, _i64, _i64, _i64, _flt, _vp, _i64, _vp, _i64, _flt, _vp, _i64],

@@ -535,6 +535,33 @@ int qr_batched_host(lfb_handle *h, T *a, int64_t batch, int64_t m, int64_t n, T 
     LFB_API_END(h)
 }
 
+// cholesky.rs:51-83 over a packed batch.  Returns LFB_NOT_POSITIVE_DEFINITE if any matrix fails; *fail_matrix /
+// *fail_index then name the first failing matrix (batch order) and its failing row.
+template <typename T>
+int cholesky_batched_host(lfb_handle *h, T *a, int64_t batch, int64_t n, int clean, int64_t *fail_matrix, int64_t *fail_index) {
+    if (fail_matrix) *fail_matrix = -1;
+    if (fail_index) *fail_index = -1;
+    if (n > 32) return fail(h, LFB_UNSUPPORTED, "batched Cholesky supports n <= 32");
+    if (batch <= 0 || n <= 0) return LFB_OK;
+    LFB_API_BEGIN(h)
+    DevBuf<T> dA(*h, (size_t)batch * n * n);
+    DevBuf<int> dF(*h, (size_t)batch);
+    std::vector<int> hf((size_t)batch);
+    LFB_CUDA(cudaMemcpyAsync(dA.get(), a, sizeof(T) * batch * n * n, cudaMemcpyHostToDevice, h->stream));
+    cholesky_batched<T>(*h, dA, batch, n, clean, dF);
+    LFB_CUDA(cudaMemcpyAsync(a, dA.get(), sizeof(T) * batch * n * n, cudaMemcpyDeviceToHost, h->stream));
+    LFB_CUDA(cudaMemcpyAsync(hf.data(), dF.get(), sizeof(int) * batch, cudaMemcpyDeviceToHost, h->stream));
+    LFB_CUDA(cudaStreamSynchronize(h->stream));
+    for (int64_t b = 0; b < batch; ++b)
+        if (hf[b] >= 0) {
+            if (fail_matrix) *fail_matrix = b;
+            if (fail_index) *fail_index = hf[b];
+            h->err = "Matrix is not positive definite";
+            return LFB_NOT_POSITIVE_DEFINITE;
+        }
+    LFB_API_END(h)
+}
+
 }  // namespace
 
 extern "C" {
@@ -715,6 +742,14 @@ int lfb_bidiagonal_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t r
 int lfb_bidiagonal_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *d, float *e) { return bidiagonal_host<float>(h, a, r, c, rs, cs, d, e); }
 int lfb_qr_batched_f32(lfb_handle *h, float *a, int64_t batch, int64_t m, int64_t n, float *diag) { return qr_batched_host<float>(h, a, batch, m, n, diag); }
 int lfb_qr_batched_f64(lfb_handle *h, double *a, int64_t batch, int64_t m, int64_t n, double *diag) { return qr_batched_host<double>(h, a, batch, m, n, diag); }
+int lfb_cholesky_batched_f32(lfb_handle *h, float *a, int64_t batch, int64_t n, int clean, int64_t *fm, int64_t *fi) { return cholesky_batched_host<float>(h, a, batch, n, clean, fm, fi); }
+int lfb_cholesky_batched_f64(lfb_handle *h, double *a, int64_t batch, int64_t n, int clean, int64_t *fm, int64_t *fi) { return cholesky_batched_host<double>(h, a, batch, n, clean, fm, fi); }
+int lfb_cholesky_batched_dev_f32(lfb_handle *h, float *d_a, int64_t batch, int64_t n, int clean, int *d_fail) {
+    if (n > 32) return fail(h, LFB_UNSUPPORTED, "batched Cholesky supports n <= 32");
+    LFB_API_BEGIN(h)
+    cholesky_batched<float>(*h, d_a, batch, n, clean, d_fail);
+    LFB_API_END(h)
+}
 
 // ---- device-resident variants (async on the handle's stream) ----
 int lfb_qr_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_diag) {

@@ -501,6 +501,68 @@ __global__ void __launch_bounds__(128, 2) qr_batched4_kernel(float *__restrict__
 
 }  // namespace
 
+// ---- batched Cholesky of n x n (n <= 32) matrices, packed row-major [batch][n][n] -------------------------
+// cholesky.rs:51-83 per matrix (the reference has no batched entry point: this is the loop a caller writes).  Warp per
+// matrix, lane = row: lane i keeps row i of the LOWER triangle in registers (the strict upper triangle is never read
+// and, for the dirty variant, never written -- cholesky.rs:17-19).  Right-looking: column j is scaled by 1/sqrt(pivot),
+// then every lane subtracts l_ij * l_kj from its row, l_kj arriving by shuffle from lane k.  fail[b] = the first row
+// whose pivot is not positive (cholesky.rs:69-71), -1 otherwise; a failed matrix is left partly factored, as in the
+// reference.
+template <typename T>
+__global__ void __launch_bounds__(128) chol_batched_kernel(T *__restrict__ A, int64_t batch, int n, int clean, int *__restrict__ fail) {
+    __shared__ T tile[4][32][33];                           // per-warp staging: coalesced global access, conflict-free row reads
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (b >= batch) return;
+    T *mat = A + b * (int64_t)n * n;
+    const int nn = n * n;
+    for (int e = lane; e < nn; e += 32) tile[warp][e / n][e % n] = mat[e];       // the whole matrix, 128-byte transactions
+    __syncwarp();
+    T row[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) row[c] = (lane < n && c <= lane) ? tile[warp][lane][c] : T(0);   // only the lower triangle is used
+    int bad = -1;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (j < n && bad < 0) {                            // warp-uniform
+            const T p = __shfl_sync(0xffffffffu, row[j], j);
+            if (p <= T(0)) bad = j;                        // cholesky.rs:69 (false for NaN: the reference goes on with a NaN factor)
+            if (bad < 0) {
+                const T d = t_sqrt(p);
+                const T lij = (lane == j) ? d : row[j] / d;
+                if (lane >= j) row[j] = lij;
+#pragma unroll
+                for (int k = j + 1; k < 32; ++k) {
+                    if (k < n) {
+                        const T lkj = __shfl_sync(0xffffffffu, lij, k);
+                        if (lane >= k) row[k] -= lij * lkj;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < n) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            if (c <= lane) tile[warp][lane][c] = row[c];
+            else if (clean && c < n) tile[warp][lane][c] = T(0);                 // cholesky.rs:78-82; dirty: the staged originals go back
+        }
+    }
+    __syncwarp();
+    for (int e = lane; e < nn; e += 32) mat[e] = tile[warp][e / n][e % n];
+    if (lane == 0) fail[b] = bad;
+}
+
+template <typename T>
+void cholesky_batched(lfb_handle &h, T *A, int64_t batch, int64_t n, int clean, int *fail) {
+    if (batch <= 0 || n <= 0) return;
+    chol_batched_kernel<T><<<(unsigned)cdiv(batch, 4), 128, 0, h.stream>>>(A, batch, (int)n, clean, fail);
+    LFB_LAUNCH_CHECK(h);
+}
+template void cholesky_batched<float>(lfb_handle &, float *, int64_t, int64_t, int, int *);
+template void cholesky_batched<double>(lfb_handle &, double *, int64_t, int64_t, int, int *);
+
 template <typename T>
 void qr_batched(lfb_handle &h, T *A, int64_t batch, int64_t m, int64_t n, T *diag) {
     if (batch <= 0 || n <= 0) return;

@@ -212,6 +212,8 @@ template <typename T> void symmetric_eig(lfb_handle &h, T *dA, int64_t n, int64_
 // svd.rs:17-221: dA consumed; sv is a HOST array (reference order); dU rows x dim or nullptr; dV = Vt^T, cols x dim, or nullptr.
 template <typename T> void svd_dev(lfb_handle &h, T *dA, int64_t rows, int64_t cols, int64_t ld, T *sv, T *dU, int64_t ldu, T *dV, int64_t ldv);
 template <typename T> void qr_batched(lfb_handle &h, T *A, int64_t batch, int64_t m, int64_t n, T *diag);
+// n <= 32, packed row-major [batch][n][n]; fail[b] = first row with a non-positive pivot or -1.
+template <typename T> void cholesky_batched(lfb_handle &h, T *A, int64_t batch, int64_t n, int clean, int *fail);
 template <typename T> void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *R, int64_t ldr);
 template <typename T> void triangular_zero(lfb_handle &h, T *A, int64_t n, int64_t ld, int keep_lower);
 double microbench_fp64(lfb_handle &h, int kind);

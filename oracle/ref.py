@@ -260,3 +260,14 @@ def svd(a: np.ndarray, calc_u: bool = True, calc_vt: bool = True, eps=None):
     st = f(_p(a), _i(rows), _i(cols), _i(_es(a, 0)), _i(_es(a, 1)), _ct(a)(e), _p(s), *up, *vp, _p(off))
     assert st == 0
     return u, s, vt
+
+
+def cholesky_batched(a: np.ndarray, clean: bool = True):
+    """cholesky.rs:51-83 in a loop over a packed [batch][n][n] array, in place; returns (first failing matrix or -1,
+    its failing row or -1), stopping at the first failure like a caller of the reference would."""
+    assert a.ndim == 3 and a.shape[1] == a.shape[2]
+    for b in range(a.shape[0]):
+        st, fail = cholesky(a[b], clean=clean)
+        if st != 0:
+            return b, fail
+    return -1, -1

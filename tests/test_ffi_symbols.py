@@ -19,7 +19,7 @@ def test_header_declares_both_scalar_families():
     names = _declared()
     for base in ("lfb_qr", "lfb_assemble_q", "lfb_qt_mul", "lfb_cholesky", "lfb_solve_triangular",
                  "lfb_sym_tridiagonal", "lfb_bidiagonal", "lfb_eigh", "lfb_svd",
-                 "lfb_least_squares", "lfb_qr_solve", "lfb_solvec", "lfb_invc"):
+                 "lfb_least_squares", "lfb_qr_solve", "lfb_solvec", "lfb_invc", "lfb_cholesky_batched"):
         assert base + "_f32" in names and base + "_f64" in names
 
 

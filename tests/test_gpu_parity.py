@@ -530,6 +530,32 @@ def test_qr_batched_parity(L, batch, m, n, dt):
     assert np.array_equal(d == 0, dref == 0)
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("batch,n", [(1, 32), (1000, 32), (77, 5), (300, 8), (5, 1), (64, 20)])
+def test_cholesky_batched_parity(L, batch, n, dt):
+    """Batched small Cholesky against the oracle's loop over cholesky.rs:51-83: L elementwise, the strict upper triangle
+    untouched (dirty) or zero (clean), and the first failing matrix / row reported like a sequential caller would see it."""
+    g = rnd((batch, n, n), np.float64, seed=batch * 3 + n, lo=-1, hi=1)
+    a0 = (g @ g.transpose(0, 2, 1) + n * np.eye(n)[None]).astype(dt)
+    a0[:, np.triu_indices(n, 1)[0], np.triu_indices(n, 1)[1]] = 7.5          # garbage in the (never read) upper triangles
+    for clean in (False, True):
+        ref = a0.copy(); fm, fi = O.cholesky_batched(ref, clean)
+        assert fm == -1
+        a = a0.copy(); L.cholesky_batched(a, clean)
+        t = 16 * n * EPS[dt] * np.sqrt(n) * np.max(np.abs(a0))
+        assert np.max(np.abs(np.tril(a) - np.tril(ref))) <= t
+        iu = np.triu_indices(n, 1)
+        assert np.all(a[:, iu[0], iu[1]] == (0 if clean else 7.5))
+    if batch > 3 and n > 2:
+        bad = a0.copy()
+        bad[2, n - 1, n - 1] = -1.0                     # matrix 2 fails at its last row
+        bad[1, 1, 1] = -5.0                             # matrix 1 fails first, at row 1
+        refb = bad.copy(); fm, fi = O.cholesky_batched(refb, False)
+        with pytest.raises(L.NotPositiveDefinite) as ei:
+            L.cholesky_batched(bad.copy(), False)
+        assert (ei.value.matrix, ei.value.index) == (fm, fi) == (1, 1)
+
+
 # ---- mid-size properties (no oracle: size-independent checks) -------------------------------------
 def test_qr_2048_properties(L):
     m, n = 2304, 2048

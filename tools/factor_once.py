@@ -84,6 +84,13 @@ elif kind == "bidiag":
     e = torch.zeros(n, dtype=torch.float64, device=dev)
     step = lambda: (W.copy_(A), lib.lfb_bidiagonal_dev_f64(eng.h, p(W), m, n, m, p(d), p(e)))
     flops = 4.0 * m * n * n - 4.0 / 3.0 * n ** 3
+elif kind == "cholbatched":
+    G = torch.rand((n, 32, 32), dtype=torch.float32, device=dev, generator=g) * 2 - 1
+    A = G @ G.transpose(1, 2) + 32 * torch.eye(32, device=dev)[None]
+    W = torch.empty_like(A)
+    f = torch.zeros(n, dtype=torch.int32, device=dev)
+    step = lambda: (W.copy_(A), lib.lfb_cholesky_batched_dev_f32(eng.h, p(W), n, 32, 1, p(f)))
+    flops = n * 32 ** 3 / 3.0
 elif kind == "batched":
     A = torch.rand((n, 32, 32), dtype=torch.float32, device=dev, generator=g) * 2 - 1
     W = torch.empty_like(A)
