@@ -316,15 +316,17 @@ bool any_zero_dev(lfb_handle &h, const T *d, int64_t n) {
     return false;
 }
 
-// |d| on the host round trip is avoided: a tiny kernel-free path -- upload of |diag| is replaced by reusing diag
-// with a device abs (util.cu has no abs kernel; n values through the host cost nothing next to the factorisation).
+// d <- |d| (qr.rs:149,176 pass `|diag|` as the diagonal of R)
+template <typename T>
+__global__ void abs_kernel(T *d, int64_t n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) d[i] = d[i] < T(0) ? -d[i] : d[i];
+}
 template <typename T>
 void abs_dev(lfb_handle &h, T *d, int64_t n) {
-    std::vector<T> v((size_t)std::max<int64_t>(n, 1));
-    download_vec<T>(h, d, n, v.data());
-    for (int64_t i = 0; i < n; ++i) v[i] = std::fabs(v[i]);
-    upload_vec<T>(h, v.data(), n, d);
-    LFB_CUDA(cudaStreamSynchronize(h.stream));
+    if (n <= 0) return;
+    abs_kernel<T><<<(unsigned)cdiv(n, 256), 256, 0, h.stream>>>(d, n);
+    LFB_LAUNCH_CHECK(h);
 }
 
 // qr.rs:207-229 LeastSquaresQrInto::least_squares_into: thin (rows >= cols): qr_into + solve_into (:124-152);

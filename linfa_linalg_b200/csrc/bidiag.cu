@@ -201,10 +201,9 @@ void launch_gemv(lfb_handle &h, const T *A, int64_t ld, int64_t m, int64_t n, in
         LFB_LAUNCH_CHECK(h);
         return;
     }
-    static bool cfg = false;
-    if (!cfg) {
+    static DeviceOnce cfg;   // function attributes are per device
+    if (cfg.first(h.device)) {
         LFB_CUDA(cudaFuncSetAttribute(bd_gemv_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SW * 32 * sizeof(V2))));
-        cfg = true;
     }
     const int64_t target = 4 * 3 * (int64_t)h.sm_count;     // >= 4 waves of 3 CTAs per SM
     int rch, cstrips;
@@ -382,11 +381,10 @@ __global__ void __launch_bounds__(HNT) bd_head_kernel(const HeadArgs<T> a) {
 
 template <typename T>
 bool launch_head(lfb_handle &h, const HeadArgs<T> &args) {
-    static bool cfg = false;
-    if (!cfg) {
+    static DeviceOnce cfg;   // function attributes are per device
+    if (cfg.first(h.device)) {
         cudaFuncSetAttribute(bd_head_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaGetLastError();
-        cfg = true;
     }
     const int64_t L = args.tn - args.t0;
     int nc = 1;

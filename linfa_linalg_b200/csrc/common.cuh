@@ -168,6 +168,18 @@ struct lfb_handle {
 
 namespace lfb {
 
+// "Done once per device" latch for cudaFuncSetAttribute calls (function attributes belong to a device's context, so a
+// process that drives several GPUs has to set them on each).
+struct DeviceOnce {
+    bool done[64] = {};
+    bool first(int dev) {
+        if (dev < 0 || dev >= 64) return true;
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 // RAII device buffer from the handle's pool.
 template <typename T>
 struct DevBuf {

@@ -316,10 +316,9 @@ __global__ void scale_kernel_d(K *C, int64_t M, int64_t N, int64_t ldc, K beta, 
 template <int AK, int BKm>
 void launch(lfb_handle &h, const CUtensorMap &ma, const CUtensorMap &mb, const TmaP &p, dim3 grid) {
     constexpr size_t smem = STAGES * STAGE_BYTES + 2 * STAGES * sizeof(uint64_t) + 1024;
-    static bool cfg = false;
-    if (!cfg) {
+    static DeviceOnce cfg;   // function attributes are per device
+    if (cfg.first(h.device)) {
         LFB_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BKm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cfg = true;
     }
     dgemm_tma_kernel<AK, BKm><<<grid, NTHREADS, smem, h.stream>>>(ma, mb, p);
     LFB_LAUNCH_CHECK(h);

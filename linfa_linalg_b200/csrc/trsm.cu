@@ -121,11 +121,10 @@ void trsv_block(lfb_handle &h, bool forward, const T *tri, int64_t sj, int64_t s
                 int64_t sv, int64_t sb, int64_t nvec, const int64_t *info) {
     if (nvec <= 0 || nb <= 0) return;
     size_t smem = sizeof(T) * (CB * CB + CB * 129 + CB);
-    static bool cfg = false;
-    if (!cfg) {
+    static DeviceOnce cfg;   // function attributes are per device
+    if (cfg.first(h.device)) {
         LFB_CUDA(cudaFuncSetAttribute(trsv_block_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LFB_CUDA(cudaFuncSetAttribute(trsv_block_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cfg = true;
     }
     unsigned grid = (unsigned)cdiv(nvec, 128);
     if (forward) trsv_block_kernel<T, true><<<grid, 128, smem, h.stream>>>(tri, sj, si, nb, ext_diag, B, sv, sb, nvec, info);
