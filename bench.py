@@ -538,6 +538,43 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         torch.cuda.empty_cache()
     except Exception as ex:
         out["tridiag_bidiag"] = {"error": str(ex)[:200]}
+    # ---- C4 as a drop-in for qr_into: TSQR + Householder reconstruction -> the reference's compact
+    #      factor, rows sharded across ranks; all_gather of R, broadcast of U' and diag.  Last: it is the newest path. ----
+    try:
+        rows_total, cols = 4194304, 256
+        rows = rows_total // world
+        from linfa_linalg_b200 import dist as D
+        gen = torch.Generator(device=dev).manual_seed(0x1F2E3D4C + 4 + rank)
+        T0 = torch.rand((cols, rows), dtype=torch.float64, device=dev, generator=gen).mul_(2).sub_(1)
+        Tw = torch.empty_like(T0)
+        ops = D.GpuTsqrOps(eng)
+        res = {}
+
+        def tsqr_qr_step():
+            Tw.copy_(T0)
+            res["diag"], res["r"] = D.tsqr_qr(Tw, ops, cols)
+        ms = timed(tsqr_qr_step, 2, 1)
+        fl = 2.0 * rows_total * cols * cols - 2.0 / 3.0 * cols ** 3
+        # self-check on the device: every reflector has unit norm (householder.rs:23), |diag| = diag(R), ||R||_F = ||A||_F
+        low = Tw.clone()
+        if rank == 0:
+            low[:, :cols] = torch.triu(low[:, :cols])          # torch sees the block transposed: keep v (on and below the diagonal)
+        ss = (low * low).sum(dim=1)
+        a2 = (T0 * T0).sum().reshape(1)
+        if world > 1:
+            dist.all_reduce(ss)
+            dist.all_reduce(a2)
+        r = res["r"]
+        out["tsqr_qr_f64"] = {"workload": f"qr_into via TSQR + Householder reconstruction {rows_total}x{cols} f64, {rows} rows per GPU",
+                              "gflops_qr_equiv": fl * 2 / (ms * 1e-3) / 1e9, "ms_per_step": ms / 2, "scaling": "strong",
+                              "reflector_norm_err": float((ss.sqrt() - 1).abs().max()),
+                              "diag_vs_r_err": float((res["diag"].abs() - torch.diagonal(r)).abs().max()),
+                              "normR_over_normA_minus_1": float(r.norm() / a2.sqrt()[0] - 1),
+                              "exchange": "all_gather of R + broadcast of U' and diag" if world > 1 else "none"}
+        del T0, Tw, low
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["tsqr_qr_f64"] = {"error": str(ex)[:200]}
     return out
 
 

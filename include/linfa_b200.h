@@ -76,6 +76,14 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value);
 int lfb_qr_f64(lfb_handle *h, double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double *diag);
 int lfb_qr_f32(lfb_handle *h, float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, float *diag);
 
+/* qr.rs:29-45 again, for TALL-SKINNY matrices: identical contract and results (same compact factor, same diag, to
+ * rounding), computed as TSQR over row chunks + Householder reconstruction (LU of Q - S) instead of one panel sweep
+ * over all the rows.  lfb_qr_* takes this route by itself when option "qr_tsqr_auto" is 1 and the matrix has at least
+ * two chunks of rows ("tsqr_chunk") and at most 512 columns.  On rank-deficient input both routes return a valid
+ * factorisation (Q R = A, Q orthonormal) but not the same one -- R is not unique there. */
+int lfb_qr_tsqr_f64(lfb_handle *h, double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double *diag);
+int lfb_qr_tsqr_f32(lfb_handle *h, float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, float *diag);
+
 /* householder.rs:68-93 assemble_q (used by qr.rs:86-88 generate_q, tridiagonal.rs:90-92,
  * bidiagonal.rs:90-109).  m is the compact factor (rows x cols, read only), signs[i] = diag_fn(i)
  * (min(rows,cols) - shift entries are read), q is rows x min(rows,cols) written with (q_rs,q_cs). */
@@ -213,6 +221,21 @@ int lfb_cholesky_batched_dev_f32(lfb_handle *h, float *d_a, int64_t batch, int64
 /* Tall-skinny local stage of TSQR: R (cols x cols, column-major ldr, diag >= 0, strict lower zeroed)
  * of a rows x cols column-major block.  d_a is overwritten (compact local factor). */
 int lfb_tsqr_local_r_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_r, int64_t ldr);
+/* Tall-skinny qr_into on the device: d_a (rows x cols) becomes the reference's compact factor, d_diag the signed
+ * pivots -- TSQR + Householder reconstruction, same contract as lfb_qr_dev_*. */
+int lfb_qr_tsqr_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_diag);
+int lfb_qr_tsqr_dev_f32(lfb_handle *h, float *d_a, int64_t rows, int64_t cols, int64_t ld, float *d_diag);
+/* Its building blocks, for a row-sharded matrix (linfa_linalg_b200/dist.py: tsqr_qr):
+ *   explicit_q:       d_a <- explicit thin Q of the block, d_r <- its R (cols x cols, diag >= 0)
+ *   apply_q:          d_q <- d_q * d_qs   (d_qs: this rank's cols x cols block of the Q of the stacked R factors)
+ *   reconstruct_top:  first n rows of the global Q (on the rank that owns them) -> top block of the compact factor,
+ *                     d_u <- U' (n x n) for everybody else's rows, d_diag <- signed pivots
+ *   reconstruct_rows: d_q (rows x n, any rows below the top block) <- d_q * U'^-1  == the reflector rows */
+int lfb_tsqr_explicit_q_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_r, int64_t ldr);
+int lfb_tsqr_apply_q_dev_f64(lfb_handle *h, double *d_q, int64_t rows, int64_t cols, int64_t ld, const double *d_qs, int64_t ldqs);
+int lfb_hh_reconstruct_top_dev_f64(lfb_handle *h, double *d_qtop, int64_t n, int64_t ld, const double *d_r, int64_t ldr,
+                                   double *d_u, int64_t ldu, double *d_diag);
+int lfb_hh_reconstruct_rows_dev_f64(lfb_handle *h, double *d_q, int64_t rows, int64_t n, int64_t ld, const double *d_u, int64_t ldu);
 /* General column-major GEMM on the engine's own kernels (used by tests / yard-stick benches):
  * C = alpha op(A) op(B) + beta C,  ta/tb: 0 = N, 1 = T. */
 int lfb_gemm_dev_f64(lfb_handle *h, int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha,

@@ -72,6 +72,8 @@ template <typename T> constexpr bool is64 = std::is_same<T, double>::value;
 #define LFB_DISPATCH(name, T, ...) (detail::is64<T> ? name##_f64(__VA_ARGS__) : name##_f32(__VA_ARGS__))
 inline int qr(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *d) { return lfb_qr_f64(h, a, r, c, rs, cs, d); }
 inline int qr(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *d) { return lfb_qr_f32(h, a, r, c, rs, cs, d); }
+inline int qr_tsqr(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *d) { return lfb_qr_tsqr_f64(h, a, r, c, rs, cs, d); }
+inline int qr_tsqr(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *d) { return lfb_qr_tsqr_f32(h, a, r, c, rs, cs, d); }
 inline int assemble_q(lfb_handle *h, const double *m, int64_t r, int64_t c, int64_t rs, int64_t cs, int64_t sh, const double *s, double *q, int64_t qrs, int64_t qcs) { return lfb_assemble_q_f64(h, m, r, c, rs, cs, sh, s, q, qrs, qcs); }
 inline int assemble_q(lfb_handle *h, const float *m, int64_t r, int64_t c, int64_t rs, int64_t cs, int64_t sh, const float *s, float *q, int64_t qrs, int64_t qcs) { return lfb_assemble_q_f32(h, m, r, c, rs, cs, sh, s, q, qrs, qcs); }
 inline int qt_mul(lfb_handle *h, const double *m, int64_t r, int64_t c, int64_t rs, int64_t cs, const double *d, double *b, int64_t bc, int64_t brs, int64_t bcs) { return lfb_qt_mul_f64(h, m, r, c, rs, cs, d, b, bc, brs, bcs); }
@@ -153,6 +155,15 @@ QRDecomp<T> qr_into(Engine &e, View<T> a) {
     if (a.rows < a.cols) throw NotThin(a.rows, a.cols);
     std::vector<T> diag((size_t)a.cols, T(0));
     e.check(detail::qr(e.handle(), a.ptr, a.rows, a.cols, a.rs, a.cs, diag.data()));
+    return QRDecomp<T>(e, a, std::move(diag));
+}
+
+// qr.rs:29-45 for a tall-skinny view: the same QRDecomp through TSQR + Householder reconstruction (csrc/tsqr_hr.cu)
+template <typename T>
+QRDecomp<T> qr_tsqr_into(Engine &e, View<T> a) {
+    if (a.rows < a.cols) throw NotThin(a.rows, a.cols);
+    std::vector<T> diag((size_t)a.cols, T(0));
+    e.check(detail::qr_tsqr(e.handle(), a.ptr, a.rows, a.cols, a.rs, a.cs, diag.data()));
     return QRDecomp<T>(e, a, std::move(diag));
 }
 

@@ -20,7 +20,7 @@ from ._ffi import LOWER, UPPER  # noqa: F401  (triangular.rs:10-13 UPLO)
 __all__ = [
     "LinalgError", "NotSquare", "NotThin", "NotPositiveDefinite", "NonInvertible", "EmptyMatrix", "WrongRows",
     "Engine", "engine", "UPPER", "LOWER",
-    "qr", "qr_into", "QRDecomp", "least_squares", "least_squares_into", "qr_batched", "cholesky_batched",
+    "qr", "qr_into", "qr_tsqr", "qr_tsqr_into", "QRDecomp", "least_squares", "least_squares_into", "qr_batched", "cholesky_batched",
     "cholesky", "cholesky_dirty", "cholesky_into", "cholesky_into_dirty", "cholesky_inplace", "cholesky_inplace_dirty",
     "solvec", "solvec_into", "solvec_inplace", "invc", "invc_inplace",
     "solve_triangular", "solve_triangular_into", "solve_triangular_inplace", "triangular_inplace", "into_triangular",
@@ -249,6 +249,24 @@ def qr_into(a: np.ndarray, eng: Engine | None = None) -> QRDecomp:
 def qr(a, eng: Engine | None = None) -> QRDecomp:
     """qr.rs:57-63 QR::qr (by reference: copies first)."""
     return qr_into(_owned(a), eng)
+
+
+def qr_tsqr_into(a: np.ndarray, eng: Engine | None = None) -> QRDecomp:
+    """qr.rs:29-45 for a tall-skinny `a`: the same QRDecomp (same compact factor and diag, to rounding), computed
+    as TSQR over row chunks + Householder reconstruction (csrc/tsqr_hr.cu).  `qr_into` takes this route by itself
+    once `engine().set_option("qr_tsqr_auto", 1)` is set and the matrix is tall and skinny enough."""
+    e = eng or engine()
+    rows, cols = a.shape
+    if rows < cols:
+        raise NotThin(rows, cols)
+    diag = np.zeros(cols, dtype=a.dtype)
+    st = e.call("lfb_qr_tsqr" + _sfx(a), *_view(a), _vecp(diag))
+    e._check(st)
+    return QRDecomp(a, diag, e)
+
+
+def qr_tsqr(a, eng: Engine | None = None) -> QRDecomp:
+    return qr_tsqr_into(_owned(a), eng)
 
 
 def least_squares_into(a: np.ndarray, b: np.ndarray, eng: Engine | None = None) -> np.ndarray:

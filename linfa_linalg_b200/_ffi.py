@@ -38,6 +38,7 @@ SIGNATURES = {
 }
 _TYPED = {
     "lfb_qr": [_vp] + _VIEW + [_vp],
+    "lfb_qr_tsqr": [_vp] + _VIEW + [_vp],
     "lfb_assemble_q": [_vp] + _VIEW + [_i64, _vp, _vp, _i64, _i64],
     "lfb_qt_mul": [_vp] + _VIEW + [_vp, _vp, _i64, _i64, _i64],
     "lfb_cholesky": [_vp] + _VIEW + [_int, C.POINTER(_i64)],
@@ -54,6 +55,7 @@ _TYPED = {
     "lfb_qr_batched": [_vp, _vp, _i64, _i64, _i64, _vp],
     "lfb_cholesky_batched": [_vp, _vp, _i64, _i64, _int, C.POINTER(_i64), C.POINTER(_i64)],
     "lfb_qr_dev": [_vp, _vp, _i64, _i64, _i64, _vp],
+    "lfb_qr_tsqr_dev": [_vp, _vp, _i64, _i64, _i64, _vp],
     "lfb_cholesky_dev": [_vp, _vp, _i64, _i64, _int, _vp],
 }
 for _n, _a in _TYPED.items():
@@ -68,6 +70,10 @@ SIGNATURES.update({
     "lfb_qr_batched_dev_f32": [_vp, _vp, _i64, _i64, _i64, _vp],
     "lfb_cholesky_batched_dev_f32": [_vp, _vp, _i64, _i64, _int, _vp],
     "lfb_tsqr_local_r_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
+    "lfb_tsqr_explicit_q_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
+    "lfb_tsqr_apply_q_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
+    "lfb_hh_reconstruct_top_dev_f64": [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp],
+    "lfb_hh_reconstruct_rows_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
     "lfb_gemm_dev_f64": [_vp, _int, _int, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _dbl, _vp, _i64],
     "lfb_gemm_dev_f32": [_vp, _int, _int, _i64, _i64, _i64, _flt, _vp, _i64, _vp, _i64, _flt, _vp, _i64],
 })

@@ -104,8 +104,18 @@ int fail(lfb_handle *h, int code, const char *msg) {
     return LFB_OK;
 
 // ---------------------------------------------------------------------------------------------
+// Tall-skinny route of qr_into: TSQR + Householder reconstruction (tsqr_hr.cu) delivers the same compact factor.
+// Taken when the caller asks for it (lfb_qr_tsqr_*), or, with option qr_tsqr_auto, whenever the matrix is tall enough
+// to be cut into at least two chunks and skinny enough for the single-CTA LU of the reconstruction.
+inline bool tsqr_route(const lfb_handle &h, int64_t rows, int64_t cols, bool force) {
+    if (cols < 1) return false;
+    if (force) return true;
+    const int64_t CH = std::max<int64_t>(h.opt.tsqr_chunk, 2 * cols);
+    return h.opt.qr_tsqr_auto != 0 && cols <= 512 && rows >= 2 * CH;
+}
+
 template <typename T>
-int qr_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *diag) {
+int qr_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *diag, bool force_tsqr = false) {
     if (rows < 0 || cols < 0) return fail(h, LFB_INVALID_ARGUMENT, "negative dimension");
     if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");           // qr.rs:34-36
     if (cols == 0) return LFB_OK;                                                            // 0x0 legal, qr.rs:383-388
@@ -113,7 +123,8 @@ int qr_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t
     const int64_t ld = round_up(rows, 2);
     DevBuf<T> dA(*h, (size_t)ld * cols), dD(*h, cols);
     upload<T>(*h, a, rows, cols, rs, cs, dA, ld);
-    qr_factor<T>(*h, dA, rows, cols, ld, dD);
+    if (tsqr_route(*h, rows, cols, force_tsqr)) qr_tsqr<T>(*h, dA, rows, cols, ld, dD);
+    else qr_factor<T>(*h, dA, rows, cols, ld, dD);
     download<T>(*h, dA, ld, a, rows, cols, rs, cs);
     download_vec<T>(*h, dD, cols, diag);
     LFB_API_END(h)
@@ -673,6 +684,7 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     else if (k == "batched_quad") h->opt.batched_quad = value;
     else if (k == "tsqr_streams") h->opt.tsqr_streams = value;
     else if (k == "tsqr_graph") h->opt.tsqr_graph = value;
+    else if (k == "qr_tsqr_auto") h->opt.qr_tsqr_auto = value;
     else if (k == "trd_fused") h->opt.trd_fused = value;
     else if (k == "chol_overlap_d2h") h->opt.chol_overlap_d2h = value;
     else if (k == "rot_staged") h->opt.rot_staged = value;
@@ -692,6 +704,8 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
 int lfb_qr_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *diag) { return qr_host<double>(h, a, r, c, rs, cs, diag); }
 int lfb_qr_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *diag) { return qr_host<float>(h, a, r, c, rs, cs, diag); }
 
+int lfb_qr_tsqr_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *diag) { return qr_host<double>(h, a, r, c, rs, cs, diag, true); }
+int lfb_qr_tsqr_f32(lfb_handle *h, float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *diag) { return qr_host<float>(h, a, r, c, rs, cs, diag, true); }
 int lfb_assemble_q_f64(lfb_handle *h, const double *m, int64_t r, int64_t c, int64_t rs, int64_t cs, int64_t shift, const double *signs, double *q, int64_t qrs, int64_t qcs) {
     return assemble_q_host<double>(h, m, r, c, rs, cs, shift, signs, q, qrs, qcs);
 }
@@ -820,6 +834,46 @@ int lfb_tsqr_local_r_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t c
     if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
     LFB_API_BEGIN(h)
     tsqr_local_r<double>(*h, d_a, rows, cols, ld, d_r, ldr);
+    LFB_API_END(h)
+}
+int lfb_qr_tsqr_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_diag) {
+    if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
+    LFB_API_BEGIN(h)
+    qr_tsqr<double>(*h, d_a, rows, cols, ld, d_diag);
+    LFB_API_END(h)
+}
+int lfb_qr_tsqr_dev_f32(lfb_handle *h, float *d_a, int64_t rows, int64_t cols, int64_t ld, float *d_diag) {
+    if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
+    LFB_API_BEGIN(h)
+    qr_tsqr<float>(*h, d_a, rows, cols, ld, d_diag);
+    LFB_API_END(h)
+}
+int lfb_tsqr_explicit_q_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_r, int64_t ldr) {
+    if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
+    if (cols < 1) return LFB_OK;
+    LFB_API_BEGIN(h)
+    const int64_t ldw = round_up(rows, 2);
+    DevBuf<double> Wk(*h, (size_t)ldw * cols);
+    tsqr_explicit_q<double>(*h, d_a, rows, cols, ld, Wk, ldw, d_r, ldr);
+    LFB_API_END(h)
+}
+int lfb_tsqr_apply_q_dev_f64(lfb_handle *h, double *d_q, int64_t rows, int64_t cols, int64_t ld, const double *d_qs, int64_t ldqs) {
+    if (rows < 0 || cols < 0) return fail(h, LFB_INVALID_ARGUMENT, "negative dimension");
+    LFB_API_BEGIN(h)
+    tsqr_apply_q<double>(*h, d_q, rows, cols, ld, d_qs, ldqs);
+    LFB_API_END(h)
+}
+int lfb_hh_reconstruct_top_dev_f64(lfb_handle *h, double *d_qtop, int64_t n, int64_t ld, const double *d_r, int64_t ldr,
+                                   double *d_u, int64_t ldu, double *d_diag) {
+    if (n < 0) return fail(h, LFB_INVALID_ARGUMENT, "negative dimension");
+    LFB_API_BEGIN(h)
+    hh_reconstruct_top<double>(*h, d_qtop, n, ld, d_r, ldr, d_u, ldu, d_diag);
+    LFB_API_END(h)
+}
+int lfb_hh_reconstruct_rows_dev_f64(lfb_handle *h, double *d_q, int64_t rows, int64_t n, int64_t ld, const double *d_u, int64_t ldu) {
+    if (rows < 0 || n < 0) return fail(h, LFB_INVALID_ARGUMENT, "negative dimension");
+    LFB_API_BEGIN(h)
+    trsm_right_upper<double>(*h, rows, n, d_u, ldu, d_q, ld);
     LFB_API_END(h)
 }
 int lfb_gemm_dev_f64(lfb_handle *h, int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha, const double *d_a,

@@ -63,6 +63,7 @@ struct Options {
     int64_t fast_hypot = 1;         // host recurrence: sqrt(x^2 + y^2) instead of hypot when far from underflow
     int64_t chol_overlap_d2h = 1;   // host Cholesky (dirty, n >= 2048): finished block columns go back to the host during the factorisation
     int64_t tsqr_streams = 8;       // chunks in flight (each panel kernel occupies one 16-SM cluster)
+    int64_t qr_tsqr_auto = 0;       // 1: lfb_qr_* takes the TSQR + Householder-reconstruction route for tall-skinny inputs (rows >= 2 chunks, cols <= 512)
     int64_t tsqr_graph = 0;         // 1: replay the local TSQR stage of a (buffer, shape) seen before as one CUDA graph
                                     // (measured: 145 vs 147 ms -- the stage is GPU bound, not launch bound -- so off by default)
 };
@@ -227,6 +228,15 @@ template <typename T> void qr_batched(lfb_handle &h, T *A, int64_t batch, int64_
 // n <= 32, packed row-major [batch][n][n]; fail[b] = first row with a non-positive pivot or -1.
 template <typename T> void cholesky_batched(lfb_handle &h, T *A, int64_t batch, int64_t n, int clean, int *fail);
 template <typename T> void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *R, int64_t ldr);
+// TSQR keeping the orthogonal factor: A <- explicit thin Q, R <- triangular factor (diag >= 0); Wk: rows x cols scratch.
+template <typename T> void tsqr_explicit_q(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *Wk, int64_t ldw, T *R, int64_t ldr);
+template <typename T> void tsqr_apply_q(lfb_handle &h, T *Q, int64_t rows, int64_t cols, int64_t ld, const T *Qs, int64_t ldqs);
+// X U = B in place on B (rows x n), U upper triangular n x n.
+template <typename T> void trsm_right_upper(lfb_handle &h, int64_t rows, int64_t n, const T *U, int64_t ldu, T *B, int64_t ldb);
+// Householder reconstruction (tsqr_hr.cu): top n x n block of an explicit Q -> reference compact form; U' for the rows below.
+template <typename T> void hh_reconstruct_top(lfb_handle &h, T *Qtop, int64_t n, int64_t ld, const T *R, int64_t ldr, T *U, int64_t ldu, T *diag);
+// Tall-skinny thin QR in the reference's compact form (identical contract to qr_factor) via TSQR + reconstruction.
+template <typename T> void qr_tsqr(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *diag);
 template <typename T> void triangular_zero(lfb_handle &h, T *A, int64_t n, int64_t ld, int keep_lower);
 double microbench_fp64(lfb_handle &h, int kind);
 double microbench_trd(lfb_handle &h, int kind, int64_t n, int reps);

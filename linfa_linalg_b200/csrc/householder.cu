@@ -859,6 +859,71 @@ void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T
 }
 
 
+// TSQR with the orthogonal factor kept (the first half of making tall-skinny results fit
+// QRDecomp, qr.rs:68-73).  On return A holds the EXPLICIT thin Q (rows x cols) of the block and R (cols x cols,
+// upper, diag >= 0, qr.rs:96) its triangular factor, A_in = Q R.  Same chunking as tsqr_local_r: every chunk is
+// factored to the reference's compact form, its thin Q_i is assembled (householder.rs:68-93) into the scratch
+// Wk (rows x cols, leading dimension ldw), the stacked R_i are reduced recursively to (Qs, R), and
+// Q[chunk i] = Q_i Qs[i*cols .. (i+1)*cols, :] is written back over the chunk by one tensor-core GEMM per chunk.
+template <typename T>
+void tsqr_explicit_q(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *Wk, int64_t ldw, T *R, int64_t ldr) {
+    if (cols <= 0 || rows <= 0) return;
+    const int64_t CH = std::max<int64_t>(h.opt.tsqr_chunk, 2 * cols);
+    if (rows < 2 * CH || h.is_sub) {
+        DevBuf<T> diag(h, cols);
+        qr_factor<T>(h, A, rows, cols, ld, diag);
+        dim3 grid((unsigned)cdiv(cols, 256), ycap(cols));
+        extract_r_kernel<T><<<grid, 256, 0, h.stream>>>(A, ld, cols, diag, R, ldr);
+        LFB_LAUNCH_CHECK(h);
+        assemble_q<T>(h, A, rows, cols, ld, 0, diag, Wk, ldw);
+        copy2d<T>(h, Wk, ldw, A, ld, rows, cols);
+        return;
+    }
+    const int64_t nch = rows / CH;   // the last chunk absorbs the remainder (< 2 CH rows)
+    const int64_t srows = nch * cols, lds = round_up(srows, 2);   // even leading dimension: 16-byte aligned columns
+    DevBuf<T> Rstack(h, (size_t)lds * cols), Ws(h, (size_t)lds * cols);
+    const int NS = (int)std::min<int64_t>(std::max<int64_t>(h.opt.tsqr_streams, 1), nch);
+    lfb_ensure_subs(h, NS);
+    LFB_CUDA(cudaEventRecord(h.ev[4], h.stream));
+    for (int s = 0; s < NS; ++s) LFB_CUDA(cudaStreamWaitEvent(h.subs[s]->stream, h.ev[4], 0));
+    for (int64_t i = 0; i < nch; ++i) {
+        lfb_handle &sub = *h.subs[i % NS];
+        const int64_t r0 = i * CH, nr = (i == nch - 1) ? rows - r0 : CH;
+        DevBuf<T> diag(sub, cols);
+        qr_factor<T>(sub, A + r0, nr, cols, ld, diag);
+        dim3 grid((unsigned)cdiv(cols, 256), ycap(cols));
+        extract_r_kernel<T><<<grid, 256, 0, sub.stream>>>(A + r0, ld, cols, diag, Rstack.get() + i * cols, lds);
+        LFB_LAUNCH_CHECK(sub);
+        assemble_q<T>(sub, A + r0, nr, cols, ld, 0, diag, Wk + r0, ldw);
+    }
+    for (int s = 0; s < NS; ++s) {
+        LFB_CUDA(cudaEventRecord(h.subs[s]->ev[5], h.subs[s]->stream));
+        LFB_CUDA(cudaStreamWaitEvent(h.stream, h.subs[s]->ev[5], 0));
+        h.launches += h.subs[s]->launches;
+        h.subs[s]->launches = 0;
+    }
+    tsqr_explicit_q<T>(h, Rstack, srows, cols, lds, Ws, lds, R, ldr);   // Rstack <- Qs
+    for (int64_t i = 0; i < nch; ++i) {
+        const int64_t r0 = i * CH, nr = (i == nch - 1) ? rows - r0 : CH;
+        gemm<T>(h, 0, 0, nr, cols, cols, T(1), Wk + r0, ldw, Rstack.get() + i * cols, lds, T(0), A + r0, ld);
+    }
+}
+
+// Q <- Q Qs in place (Q rows x cols, Qs cols x cols): the second level of a multi-GPU TSQR, where Qs is this rank's
+// block of the explicit Q of the stacked R factors.  Row chunks go through a scratch so the GEMM never aliases.
+template <typename T>
+void tsqr_apply_q(lfb_handle &h, T *Q, int64_t rows, int64_t cols, int64_t ld, const T *Qs, int64_t ldqs) {
+    if (rows <= 0 || cols <= 0) return;
+    const int64_t CH = std::min<int64_t>(rows, 65536);
+    const int64_t ldt = round_up(CH, 2);
+    DevBuf<T> tmp(h, (size_t)ldt * cols);
+    for (int64_t r0 = 0; r0 < rows; r0 += CH) {
+        const int64_t nr = std::min(CH, rows - r0);
+        copy2d<T>(h, Q + r0, ld, tmp, ldt, nr, cols);
+        gemm<T>(h, 0, 0, nr, cols, cols, T(1), tmp, ldt, Qs, ldqs, T(0), Q + r0, ld);
+    }
+}
+
 template <typename T>
 void assemble_q(lfb_handle &h, const T *M, int64_t rows, int64_t cols, int64_t ld, int64_t shift, const T *signs, T *Q,
                 int64_t ldq) {
@@ -914,6 +979,8 @@ void qt_mul(lfb_handle &h, const T *QR, int64_t rows, int64_t cols, int64_t ld, 
 #define INST(T)                                                                                                   \
     template void qr_factor<T>(lfb_handle &, T *, int64_t, int64_t, int64_t, T *);                                \
     template void tsqr_local_r<T>(lfb_handle &, T *, int64_t, int64_t, int64_t, T *, int64_t);                    \
+    template void tsqr_explicit_q<T>(lfb_handle &, T *, int64_t, int64_t, int64_t, T *, int64_t, T *, int64_t);   \
+    template void tsqr_apply_q<T>(lfb_handle &, T *, int64_t, int64_t, int64_t, const T *, int64_t);              \
     template void assemble_q<T>(lfb_handle &, const T *, int64_t, int64_t, int64_t, int64_t, const T *, T *, int64_t); \
     template void qt_mul<T>(lfb_handle &, const T *, int64_t, int64_t, int64_t, const T *, T *, int64_t, int64_t);
 INST(float)

@@ -170,8 +170,24 @@ void trsm_left(lfb_handle &h, int lower, int trans, int64_t n, int64_t nrhs, con
     }
 }
 
+// X U = B in place on B (rows x n, column-major), U n x n upper triangular (only that triangle is read): the
+// right-hand solve Y2 = Q2 U^-1 of the Householder reconstruction (tsqr_hr.cu).  Left-looking over 64-column
+// blocks: the finished block columns enter by one GEMM, the diagonal block by the base kernel with every ROW of B as
+// one right-hand side (element j of vector v at B[v + j*ldb]).
+template <typename T>
+void trsm_right_upper(lfb_handle &h, int64_t rows, int64_t n, const T *U, int64_t ldu, T *B, int64_t ldb) {
+    if (rows <= 0 || n <= 0) return;
+    for (int64_t j0 = 0; j0 < n; j0 += CB) {
+        const int nb = (int)std::min<int64_t>(CB, n - j0);
+        if (j0 > 0) gemm<T>(h, 0, 0, rows, nb, j0, T(-1), B, ldb, U + j0 * ldu, ldu, T(1), B + j0 * ldb, ldb);
+        // equation j: sum_{i <= j} x_i U[i, j] = b_j  ->  M(j, i) = U[i + j*ldu]: sj = ldu, si = 1, forward
+        trsv_block<T>(h, true, U + j0 + j0 * ldu, ldu, 1, nb, (const T *)nullptr, B + j0 * ldb, /*sv=*/1, /*sb=*/ldb, rows, nullptr);
+    }
+}
+
 #define INST(T)                                                                                       \
-    template void trsm_left<T>(lfb_handle &, int, int, int64_t, int64_t, const T *, int64_t, const T *, T *, int64_t);
+    template void trsm_left<T>(lfb_handle &, int, int, int64_t, int64_t, const T *, int64_t, const T *, T *, int64_t); \
+    template void trsm_right_upper<T>(lfb_handle &, int64_t, int64_t, const T *, int64_t, T *, int64_t);
 INST(float)
 INST(double)
 #undef INST

@@ -7,6 +7,12 @@ One process per GPU (torch.distributed, NCCL over NVLink on the GPU box, gloo in
   (diag >= 0, qr.rs:96), ONE all_gather of the R factors (n*n*8 bytes per rank, latency bound on
   NVSwitch), then every rank factors the stacked (world*n) x n matrix -> the global R, replicated.
 
+* tall-skinny QR delivered as the reference's QRDecomp (`tsqr_qr`): the same row blocks; every rank
+  keeps its explicit Q_r, the all-gathered R factors are reduced (replicated) to (Qs, R), Q_r <- Q_r Qs[r], the rank
+  that owns the first n rows runs the Householder reconstruction of the top block (LU of Q - S) and broadcasts U' and
+  diag (n*n + n values), and every rank turns its rows into reflector rows with one right-hand TRSM.  Two collectives
+  in all, both O(n^2) bytes.
+
 Everything here is host-side plumbing; the arithmetic is behind the callables (`local_r`, `final_r`)
 so that the same code path is exercised by the gloo tests with CPU stand-ins.
 """
@@ -70,3 +76,77 @@ def gpu_final_r(eng, n: int):
             raise RuntimeError(f"lfb_tsqr_local_r_dev_f64 (stacked R) status {st}")
         return r
     return run
+
+
+# ---- TSQR + Householder reconstruction over row blocks ---------------------------------------------------
+def tsqr_qr(block, ops, n: int, group=None):
+    """qr.rs:29-45 of a row-sharded tall-skinny matrix.  `block`: this rank's rows as an (n, rows_local) row-major
+    tensor (== the column-major rows_local x n block); overwritten with ITS ROWS of the reference's compact factor
+    (unit-norm reflectors below the diagonal, R above, householder.rs:34-51).  Returns (diag, r): the signed pivots
+    (n) and the column-major R (diag >= 0) as an (n, n) tensor, both replicated.  `ops` supplies the arithmetic
+    (GpuTsqrOps over the C ABI; CPU stand-ins in the gloo tests):
+        explicit_q(x) -> r            x (n, rows) <- explicit thin Q of x, r = its column-major R
+        apply_q(x, qs)                x <- x * qs          (qs: contiguous (n, n) tensor, column-major n x n)
+        reconstruct_top(x, r, u, diag)   first n rows of x -> top block of the compact factor; u <- U', diag
+        reconstruct_rows(x, row0, u)  rows row0.. of x <- (those rows) U'^-1
+    Rank 0 must own at least n rows."""
+    import torch
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if on else 1
+    rank = dist.get_rank(group) if on else 0
+    rows_local = block.shape[1]
+    if rank == 0 and rows_local < n:
+        raise ValueError(f"rank 0 owns {rows_local} rows, fewer than the {n} columns")
+    r = ops.explicit_q(block)
+    if world > 1:
+        r_all = torch.empty((world * n, n), dtype=r.dtype, device=r.device)
+        dist.all_gather_into_tensor(r_all, r.contiguous(), group=group)
+        stack = stack_r_factors(r_all, world, n)
+        r = ops.explicit_q(stack)                                   # stack <- Qs, replicated
+        ops.apply_q(block, stack[:, rank * n:(rank + 1) * n].contiguous())
+    u = torch.empty((n, n), dtype=block.dtype, device=block.device)
+    diag = torch.empty((n,), dtype=block.dtype, device=block.device)
+    if rank == 0:
+        ops.reconstruct_top(block, r, u, diag)
+    if world > 1:
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(u, src=src, group=group)
+        dist.broadcast(diag, src=src, group=group)
+    ops.reconstruct_rows(block, n if rank == 0 else 0, u)
+    return diag, r
+
+
+class GpuTsqrOps:
+    """The four steps of `tsqr_qr` on liblinfa_b200 (f64, device tensors, the engine's stream)."""
+
+    def __init__(self, eng):
+        self.eng = eng
+
+    def _call(self, name, *args):
+        st = getattr(self.eng.lib, name)(self.eng.h, *args)
+        if st != 0:
+            raise RuntimeError(f"{name} status {st}: {self.eng.lib.lfb_last_error(self.eng.h)}")
+
+    def explicit_q(self, x):
+        import torch
+        n, rows = x.shape
+        r = torch.empty((n, n), dtype=torch.float64, device=x.device)
+        self._call("lfb_tsqr_explicit_q_dev_f64", C.c_void_p(x.data_ptr()), rows, n, rows, C.c_void_p(r.data_ptr()), n)
+        return r
+
+    def apply_q(self, x, qs):
+        n, rows = x.shape
+        self._call("lfb_tsqr_apply_q_dev_f64", C.c_void_p(x.data_ptr()), rows, n, rows, C.c_void_p(qs.data_ptr()), n)
+
+    def reconstruct_top(self, x, r, u, diag):
+        n, rows = x.shape
+        self._call("lfb_hh_reconstruct_top_dev_f64", C.c_void_p(x.data_ptr()), n, rows, C.c_void_p(r.data_ptr()), n,
+                   C.c_void_p(u.data_ptr()), n, C.c_void_p(diag.data_ptr()))
+
+    def reconstruct_rows(self, x, row0, u):
+        n, rows = x.shape
+        if rows - row0 <= 0:
+            return
+        self._call("lfb_hh_reconstruct_rows_dev_f64", C.c_void_p(x.data_ptr() + row0 * x.element_size()), rows - row0, n, rows,
+                   C.c_void_p(u.data_ptr()), n)

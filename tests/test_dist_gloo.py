@@ -84,3 +84,98 @@ def test_stack_layout():
     X = stack.t()
     for g in range(world):
         assert torch.equal(X[g * n:(g + 1) * n, :], rs[g].t())
+
+
+# ---- tsqr_qr: TSQR + Householder reconstruction over row blocks (dist.py), CPU stand-ins for the four device steps ----
+class _CpuTsqrOps:
+    """NumPy/oracle restatement of csrc/tsqr_hr.cu's steps on the same tensor layout ((n, rows) row-major tensors ==
+    column-major rows x n blocks), so the gloo test exercises exactly the plumbing the GPU path uses."""
+
+    @staticmethod
+    def _cm(x):  # numpy view of the column-major matrix (rows x n), writable, shares memory with the tensor
+        return x.numpy().T
+
+    def explicit_q(self, x):
+        import oracle as O
+        a = self._cm(x)
+        f = np.array(a, dtype=np.float64, order="C")
+        d = O.qr(f)
+        a[:] = O.generate_q(f, d)
+        return torch.from_numpy(np.ascontiguousarray(O.qr_into_r(f, d).T))
+
+    def apply_q(self, x, qs):
+        a = self._cm(x)
+        a[:] = a @ qs.numpy().T
+
+    def reconstruct_top(self, x, r, u, diag):
+        n = x.shape[0]
+        q = self._cm(x)[:n]          # top n x n block (view)
+        R = r.numpy().T
+        s = np.zeros(n)
+        for k in range(n):
+            s[k] = -1.0 if q[k, k] >= 0 else 1.0
+            q[k, k] -= s[k]
+            q[k + 1:, k] /= q[k, k]
+            q[k + 1:, k + 1:] -= np.outer(q[k + 1:, k], q[k, k + 1:])
+        U = np.triu(q).copy()
+        sp = 1.0
+        c = np.zeros(n)
+        for k in range(n):
+            c[k] = -sp * s[k] * np.sqrt(abs(U[k, k]) / 2)
+            diag[k] = sp * s[k] * R[k, k]
+            sp = s[k]
+        for k in range(n):
+            q[k + 1:, k] *= c[k]
+            q[k, k] = c[k]
+            q[k, k + 1:] = R[k, k + 1:]
+        u.copy_(torch.from_numpy(np.ascontiguousarray((U / c[:, None]).T)))
+
+    def reconstruct_rows(self, x, row0, u):
+        a = self._cm(x)
+        if a.shape[0] - row0 <= 0:
+            return
+        U = u.numpy().T
+        a[row0:] = np.linalg.solve(U.T, a[row0:].T).T
+
+
+def _tsqr_qr_worker(rank, world, port, rows, n, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = np.random.default_rng(11).uniform(-100, 100, (rows, n))
+    b, e = D.shard_range(rows, world, rank)
+    block = torch.from_numpy(np.ascontiguousarray(full[b:e].T))     # (n, rows_local) row-major == column-major block
+    diag, r = D.tsqr_qr(block, _CpuTsqrOps(), n)
+    out[rank] = (block.numpy().T.copy(), diag.numpy().copy(), r.numpy().T.copy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_tsqr_qr_ranks_match_reference_compact_factor(world):
+    """The row blocks returned by tsqr_qr, stacked, are the reference's compact QR factor of the whole matrix
+    (qr.rs:29-45 via the oracle): reflectors, R rows and signed pivots, elementwise."""
+    import oracle as O
+    rows, n = 301, 9
+    full = np.random.default_rng(11).uniform(-100, 100, (rows, n))
+    if world == 1:
+        block = torch.from_numpy(np.ascontiguousarray(full.T))
+        diag, r = D.tsqr_qr(block, _CpuTsqrOps(), n)
+        got = {0: (block.numpy().T.copy(), diag.numpy().copy(), r.numpy().T.copy())}
+    else:
+        mgr = mp.Manager()
+        got = mgr.dict()
+        mp.spawn(_tsqr_qr_worker, args=(world, _free_port(), rows, n, got), nprocs=world, join=True)
+    ref = full.copy()
+    dref = O.qr(ref)
+    tol = 64 * rows * 2.2e-16 * np.linalg.norm(full, 2)
+    factor = np.vstack([got[rk][0] for rk in range(world)])
+    assert factor.shape == ref.shape
+    assert np.max(np.abs(factor - ref)) <= tol
+    for rk in range(world):
+        assert np.max(np.abs(got[rk][1] - dref)) <= tol
+        assert np.max(np.abs(got[rk][2] - O.qr_into_r(ref.copy(), dref))) <= tol
+    # and the reference's consumers accept it: Q from the stacked factor reproduces A (tests/qr.rs:20-27)
+    q = O.generate_q(factor.copy(), got[0][1])
+    rr = O.qr_into_r(factor.copy(), got[0][1])
+    assert np.linalg.norm(q @ rr - full) <= tol * n
+    assert np.linalg.norm(q.T @ q - np.eye(n)) <= 64 * rows * 2.2e-16
