@@ -202,9 +202,9 @@ void launch_gemv(lfb_handle &h, const T *A, int64_t ld, int64_t m, int64_t n, in
         return;
     }
     static DeviceOnce cfg;   // function attributes are per device
-    if (cfg.first(h.device)) {
+    cfg.run(h.device, [&] {
         LFB_CUDA(cudaFuncSetAttribute(bd_gemv_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SW * 32 * sizeof(V2))));
-    }
+    });
     const int64_t target = 4 * 3 * (int64_t)h.sm_count;     // >= 4 waves of 3 CTAs per SM
     int rch, cstrips;
     if (MODE == 0) {     // few atomics: 256 rows x up to 256 columns per CTA
@@ -382,10 +382,10 @@ __global__ void __launch_bounds__(HNT) bd_head_kernel(const HeadArgs<T> a) {
 template <typename T>
 bool launch_head(lfb_handle &h, const HeadArgs<T> &args) {
     static DeviceOnce cfg;   // function attributes are per device
-    if (cfg.first(h.device)) {
+    cfg.run(h.device, [&] {
         cudaFuncSetAttribute(bd_head_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaGetLastError();
-    }
+    });
     const int64_t L = args.tn - args.t0;
     int nc = 1;
     while (nc < 16 && (int64_t)nc * HNT < L) nc <<= 1;

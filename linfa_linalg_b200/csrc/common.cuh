@@ -8,6 +8,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -170,14 +171,18 @@ struct lfb_handle {
 namespace lfb {
 
 // "Done once per device" latch for cudaFuncSetAttribute calls (function attributes belong to a device's context, so a
-// process that drives several GPUs has to set them on each).
+// process that drives several GPUs has to set them on each).  The latch is taken under a mutex and only set after
+// the body has run, so two handles used from two threads cannot launch before the attribute is in place.
 struct DeviceOnce {
+    std::mutex mu;
     bool done[64] = {};
-    bool first(int dev) {
-        if (dev < 0 || dev >= 64) return true;
-        if (done[dev]) return false;
-        done[dev] = true;
-        return true;
+    template <typename F>
+    void run(int dev, F &&body) {
+        std::lock_guard<std::mutex> g(mu);
+        const bool tracked = dev >= 0 && dev < 64;
+        if (tracked && done[dev]) return;
+        body();                        // may throw (LFB_CUDA): the latch then stays open
+        if (tracked) done[dev] = true;
     }
 };
 

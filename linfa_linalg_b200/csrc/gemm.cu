@@ -436,10 +436,10 @@ void launch_dgemm(lfb_handle &h, const GemmP &p, dim3 grid) {
     constexpr size_t smem = sizeof(double) * 2 * (A_SZ + B_SZ);
     constexpr size_t smem2 = sizeof(double) * V2_STAGES * (A_SZ + B_SZ);
     static DeviceOnce configured;   // function attributes are per device
-    if (configured.first(h.device)) {
+    configured.run(h.device, [&] {
         LFB_CUDA(cudaFuncSetAttribute(dgemm_kernel<AM, BMo>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LFB_CUDA(cudaFuncSetAttribute(dgemm_v2_kernel<AM, BMo>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    }
+    });
     if (p.vecA && p.vecB && h.opt.gemm_v2) {
         dgemm_v2_kernel<AM, BMo><<<grid, 512, smem2, h.stream>>>(p);
     } else {

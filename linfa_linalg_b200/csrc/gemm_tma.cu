@@ -317,9 +317,9 @@ template <int AK, int BKm>
 void launch(lfb_handle &h, const CUtensorMap &ma, const CUtensorMap &mb, const TmaP &p, dim3 grid) {
     constexpr size_t smem = STAGES * STAGE_BYTES + 2 * STAGES * sizeof(uint64_t) + 1024;
     static DeviceOnce cfg;   // function attributes are per device
-    if (cfg.first(h.device)) {
+    cfg.run(h.device, [&] {
         LFB_CUDA(cudaFuncSetAttribute(dgemm_tma_kernel<AK, BKm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    });
     dgemm_tma_kernel<AK, BKm><<<grid, NTHREADS, smem, h.stream>>>(ma, mb, p);
     LFB_LAUNCH_CHECK(h);
 }

@@ -508,10 +508,10 @@ void build_t(lfb_handle &h, const T *V, int64_t ldv, int64_t rows, int nb, T *G,
     while (P < nb) P <<= 1;
     size_t smem = sizeof(T) * (size_t)(P * (P + 1) + (P / 2 + 1) * (P + 1));
     static DeviceOnce cfg;   // function attributes are per device
-    if (cfg.first(h.device)) {
+    cfg.run(h.device, [&] {
         LFB_CUDA(cudaFuncSetAttribute(tinv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(sizeof(T) * (128 * 129 + 65 * 129))));
-    }
+    });
     if (nb <= 128) {
         tinv_kernel<T><<<1, 512, smem, h.stream>>>(G, nb, nb, Tm, ldt);
         LFB_LAUNCH_CHECK(h);
@@ -589,10 +589,10 @@ template <typename T>
 bool factor_subpanel_cluster(lfb_handle &h, T *A, int64_t ld, int64_t m, int64_t c0, int nc, int w, int rpc, size_t smem,
                              T *beta, T *V, int64_t ldv, int64_t vrow0, int vcol0, T *Tout, int ldt) {
     static DeviceOnce cfg;   // function attributes are per device
-    if (cfg.first(h.device)) {
+    cfg.run(h.device, [&] {
         LFB_CUDA(cudaFuncSetAttribute(hh_panel_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem_optin));
         LFB_CUDA(cudaFuncSetAttribute(hh_panel_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    }
+    });
     PanelArgs<T> p;
     p.A = A; p.ld = ld; p.m = m; p.c0 = c0; p.w = w; p.rpc = rpc; p.beta = beta;
     p.V = V; p.ldv = ldv; p.vrow0 = vrow0; p.vcol0 = vcol0; p.Tout = Tout; p.ldt = ldt;

@@ -294,10 +294,10 @@ constexpr size_t panel_extra_elems() { return 2 * MAXC * WMAX + 2 * WMAX + 2 * N
 template <typename T, int WD>
 bool launch_panel(lfb_handle &h, const PanelArgs2<T> &p, int nc, size_t smem) {
     static DeviceOnce cfg;   // function attributes are per device
-    if (cfg.first(h.device)) {
+    cfg.run(h.device, [&] {
         LFB_CUDA(cudaFuncSetAttribute(hh_panel_cluster3<T, WD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem_optin));
         LFB_CUDA(cudaFuncSetAttribute(hh_panel_cluster3<T, WD>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    }
+    });
     cudaLaunchConfig_t cfgl = {};
     cfgl.gridDim = dim3((unsigned)nc);
     cfgl.blockDim = dim3(NT);

@@ -184,10 +184,10 @@ void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64
     const size_t smem_p = sizeof(T) * (2 * CB * SP + 32 * SP);
     const size_t smem_t = sizeof(T) * (CB * 132 + CB * 68);
     static DeviceOnce cfg;   // function attributes are per device
-    if (cfg.first(h.device)) {
+    cfg.run(h.device, [&] {
         LFB_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
         LFB_CUDA(cudaFuncSetAttribute(trsm_mult_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-    }
+    });
     DevBuf<T> Linv(h, CB * CB);
     const int64_t NB = std::max<int64_t>(CB, round_up(h.opt.chol_nb, CB));
     // panel [k0, k0+nb): 64-column blocks, everything on the handle's current stream

@@ -554,10 +554,10 @@ template <typename T>
 bool launch_head(lfb_handle &h, int nc, T *A, int64_t ld, int64_t n, int64_t i, int j, T *V, T *Wm, int64_t ldv, T *P, T *P2,
                  T *off, TrdAcc<T> *acc, int final_only) {
     static DeviceOnce cfg;   // function attributes are per device
-    if (cfg.first(h.device)) {
+    cfg.run(h.device, [&] {
         cudaFuncSetAttribute(trd_head_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaGetLastError();
-    }
+    });
     cudaLaunchConfig_t c = {};
     c.gridDim = dim3((unsigned)nc);
     c.blockDim = dim3(HNT);
@@ -589,10 +589,10 @@ void launch_symv(lfb_handle &h, const T *A, int64_t ld, int64_t n, int64_t i1, c
     if (aligned && h.opt.trd_symv_async) {
         using V2 = typename Vec2<T>::type;
         static DeviceOnce cfg;   // function attributes are per device
-        if (cfg.first(h.device)) {
+        cfg.run(h.device, [&] {
             LFB_CUDA(cudaFuncSetAttribute(trd_symv_async_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(4 * SW * 32 * sizeof(V2))));
-        }
+        });
         int chunk = 256;                                  // one 64-row tile per warp unless the matrix is small
         while (chunk > 64 && strips * cdiv(L, chunk) / 2 < 4 * 3 * (int64_t)h.sm_count) chunk >>= 1;
         const int nw = std::min(4, chunk / 64);

@@ -122,10 +122,10 @@ void trsv_block(lfb_handle &h, bool forward, const T *tri, int64_t sj, int64_t s
     if (nvec <= 0 || nb <= 0) return;
     size_t smem = sizeof(T) * (CB * CB + CB * 129 + CB);
     static DeviceOnce cfg;   // function attributes are per device
-    if (cfg.first(h.device)) {
+    cfg.run(h.device, [&] {
         LFB_CUDA(cudaFuncSetAttribute(trsv_block_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LFB_CUDA(cudaFuncSetAttribute(trsv_block_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    });
     unsigned grid = (unsigned)cdiv(nvec, 128);
     if (forward) trsv_block_kernel<T, true><<<grid, 128, smem, h.stream>>>(tri, sj, si, nb, ext_diag, B, sv, sb, nvec, info);
     else trsv_block_kernel<T, false><<<grid, 128, smem, h.stream>>>(tri, sj, si, nb, ext_diag, B, sv, sb, nvec, info);
