@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(wpb<T>() * 32, 2) qr_batched_kernel(T *__restr
                 mat[i * n + lane] = val;
             }
         }
-        if (lane < n) diag[b * n + lane] = prevp * dg;
+        if (lane < n) diag[b * n + lane] = (dg != T(0)) ? prevp * dg : T(0);   // a `None` pivot is +0.0, never -0.0 (householder.rs:50)
         __syncwarp();
     }
 }
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(128, 2) qr_batched4_32_kernel(float *__restric
                 const int c = 8 * q + g;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) mat[i * 32 + c] = (i < c) ? a[q][i] : prev[q] * a[q][i];
-                diag[b * 32 + c] = prev[q] * dg[q];
+                diag[b * 32 + c] = (dg[q] != 0.0f) ? prev[q] * dg[q] : 0.0f;   // `None` pivot: +0.0 (householder.rs:50)
             }
         }
         __syncwarp();
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(128, 2) qr_batched4_kernel(float *__restrict__
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (i < m) mat[i * n + c] = (i < c) ? a[q][i] : prev[q] * a[q][i];
-                    diag[b * n + c] = prev[q] * dg[q];
+                    diag[b * n + c] = (dg[q] != 0.0f) ? prev[q] * dg[q] : 0.0f;   // `None` pivot: +0.0 (householder.rs:50)
                 }
             }
         }

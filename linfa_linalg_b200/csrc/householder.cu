@@ -436,7 +436,9 @@ __global__ void sign_scan_kernel(const T *__restrict__ beta, int64_t n, T *__res
     T p = T(1);
     for (int64_t j = 0; j < n; ++j) {
         T b = beta[j];
-        diag[j] = p * b;
+        // a `None` column (householder.rs:26, :50: `rn.unwrap_or(A::zero())`) stores +0.0, never -0.0: the reference's
+        // consumers take signum(diag[j]) (householder.rs:45, :89; qr.rs:116) and Rust's signum(-0.0) is -1
+        diag[j] = (b != T(0)) ? p * b : T(0);
         if (b != T(0)) p = t_signum(b);
         psign[j] = p;
     }

@@ -146,6 +146,17 @@ def test_qr_edge_cases(L):
     assert dec.diag[0] == 0.0 and dref[0] == 0.0
     assert np.max(np.abs(a - ref)) <= tol(a0, 16) and np.max(np.abs(dec.diag - dref)) <= tol(a0, 16)
     assert not dec.is_invertible()
+    # a None column stores +0.0 (householder.rs:50 `rn.unwrap_or(A::zero())`): the consumers take signum(diag[i])
+    # (householder.rs:89, qr.rs:116) and Rust's signum(-0.0) = -1 would flip every later column of Q
+    assert np.array_equal(np.signbit(dec.diag), np.signbit(dref))
+    for seed in range(4):
+        z0 = rnd((60, 12), seed=100 + seed)
+        z0[:, 3 + seed] = 0.0
+        q, r = L.qr(z0).into_decomp()
+        assert np.linalg.norm(q @ r - z0) <= tol(z0, 16)
+        assert np.linalg.norm(q.T @ q - np.eye(12)) <= 64 * 60 * EPS[np.float64]
+        qo = O.generate_q(*(lambda w: (w, O.qr(w)))(z0.copy()))
+        assert np.max(np.abs(q - qo)) <= 64 * 60 * EPS[np.float64]
     # negative zero / negative pivots and a square matrix (length-1 last reflector)
     a0 = -np.abs(rnd((50, 50), seed=6))
     ref = a0.copy(); dref = O.qr(ref)
@@ -522,12 +533,15 @@ def test_qr_batched_parity(L, batch, m, n, dt):
     if batch > 3:
         a0[1, :, 0] = 0          # a None column
         a0[2] = 0                # an all-zero matrix
+        if n > 2:
+            a0[3:, :, 2] = 0     # None columns AFTER live ones: the stored pivot is +0.0 whatever the running sign is
     ref = a0.copy(); dref = O.qr_batched(ref)
     a = a0.copy(); d = L.qr_batched(a)
     t = 16 * m * EPS[dt] * np.sqrt(m)
     assert np.max(np.abs(a - ref)) <= t
     assert np.max(np.abs(d - dref)) <= t
     assert np.array_equal(d == 0, dref == 0)
+    assert np.array_equal(np.signbit(d), np.signbit(dref))       # householder.rs:50: None -> +0.0 (signum(-0.0) = -1 in Rust)
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
