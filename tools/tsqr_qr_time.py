@@ -43,6 +43,41 @@ F2 = A.clone(); d2 = d.clone()
 out["qr_blocked_ms"] = run("lfb_qr_dev_f64", C.c_void_p(d.data_ptr()))
 out["factor_max_diff_vs_blocked"] = float((A - F2).abs().max())
 out["diag_max_diff_vs_blocked"] = float((d - d2).abs().max())
+# stage breakdown of the TSQR + reconstruction route through its building-block entry points
+U = torch.empty((cols, cols), dtype=torch.float64, device=dev)
+
+
+def stage(fn, reps=3):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot = 0.0
+    for _ in range(reps):
+        e0.record(s)
+        fn()
+        e1.record(s)
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+def st_q():
+    e._check(e.call("lfb_tsqr_explicit_q_dev_f64", C.c_void_p(A.data_ptr()), rows, cols, rows, C.c_void_p(R.data_ptr()), cols))
+
+
+def st_top():
+    e._check(e.call("lfb_hh_reconstruct_top_dev_f64", C.c_void_p(A.data_ptr()), cols, rows, C.c_void_p(R.data_ptr()), cols,
+                    C.c_void_p(U.data_ptr()), cols, C.c_void_p(d.data_ptr())))
+
+
+def st_rows():
+    e._check(e.call("lfb_hh_reconstruct_rows_dev_f64", C.c_void_p(A.data_ptr() + cols * 8), rows - cols, cols, rows,
+                    C.c_void_p(U.data_ptr()), cols))
+
+
+A.copy_(A0)
+out["stage_explicit_q_ms"] = stage(st_q, 1)
+out["stage_reconstruct_top_ms"] = stage(st_top, 1)
+out["stage_reconstruct_rows_ms"] = stage(st_rows, 1)
 fl = 2.0 * rows * cols * cols - 2.0 / 3.0 * cols ** 3
 out["qr_tsqr_hr_gflops_equiv"] = fl / (out["qr_tsqr_hr_ms"] * 1e-3) / 1e9
 out["qr_blocked_gflops"] = fl / (out["qr_blocked_ms"] * 1e-3) / 1e9
