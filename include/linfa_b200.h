@@ -152,6 +152,25 @@ int lfb_invc_f64(lfb_handle *h, const double *a, int64_t rows, int64_t cols, int
 int lfb_invc_f32(lfb_handle *h, const float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
                  float *inv, int64_t i_rs, int64_t i_cs, int64_t *fail_index);
 
+/* ---- the dense blocks of LOBPCG, one call each (lobpcg/algorithm.rs) -----------------
+ * lobpcg/algorithm.rs:81-97 orthonormalize(v) -> (u, gram_vv_fac): v (rows x cols) is overwritten with
+ * u = v L^-T where L = cholesky_into(v^T v) (:82-83; lower, strict upper zeroed) is written to l (cols x cols; may be
+ * NULL).  The Gram matrix and its factor never leave the device.  LFB_NOT_POSITIVE_DEFINITE (+ *fail_index, the
+ * failing pivot row) when v^T v is not numerically SPD, exactly where cholesky_into fails (:83); v, l untouched. */
+int lfb_orthonormalize_f64(lfb_handle *h, double *v, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                           double *l, int64_t l_rs, int64_t l_cs, int64_t *fail_index);
+int lfb_orthonormalize_f32(lfb_handle *h, float *v, int64_t rows, int64_t cols, int64_t rs, int64_t cs,
+                           float *l, int64_t l_rs, int64_t l_cs, int64_t *fail_index);
+/* lobpcg/algorithm.rs:63-76 apply_constraints(v, cholesky_yy, y): v (n x k) -= y u with u the solution of
+ * cholesky_yy u = y^T v (:68-75; cholesky_yy is m x m, its lower triangle is read; y is n x m).  A y that is not
+ * n x m is LFB_INVALID_ARGUMENT (ndarray panics on the shape mismatch). */
+int lfb_apply_constraints_f64(lfb_handle *h, double *v, int64_t n, int64_t k, int64_t rs, int64_t cs,
+                              const double *cholesky_yy, int64_t m, int64_t l_rs, int64_t l_cs,
+                              const double *y, int64_t y_rows, int64_t y_cols, int64_t y_rs, int64_t y_cs);
+int lfb_apply_constraints_f32(lfb_handle *h, float *v, int64_t n, int64_t k, int64_t rs, int64_t cs,
+                              const float *cholesky_yy, int64_t m, int64_t l_rs, int64_t l_cs,
+                              const float *y, int64_t y_rows, int64_t y_cols, int64_t y_rs, int64_t y_cs);
+
 /* ---- eigh.rs:202-268 EighInto / Eigh / EigValshInto / EigValsh (symmetric_eig, eigh.rs:10-129) ---------
  * a: n x n view (only read; the reference consumes `self`, nothing of it is observable afterwards).
  * vals: n contiguous entries, in the reference's own (unsorted) order -- EigSort stays host-side.
@@ -236,6 +255,12 @@ int lfb_tsqr_apply_q_dev_f64(lfb_handle *h, double *d_q, int64_t rows, int64_t c
 int lfb_hh_reconstruct_top_dev_f64(lfb_handle *h, double *d_qtop, int64_t n, int64_t ld, const double *d_r, int64_t ldr,
                                    double *d_u, int64_t ldu, double *d_diag);
 int lfb_hh_reconstruct_rows_dev_f64(lfb_handle *h, double *d_q, int64_t rows, int64_t n, int64_t ld, const double *d_u, int64_t ldu);
+/* LOBPCG blocks on device-resident column-major operands, async on the stream, so the iteration's blocks can stay in
+ * HBM across calls: d_info is a device int64 (0, or failing pivot row + 1 -- d_v is then unspecified). */
+int lfb_orthonormalize_dev_f64(lfb_handle *h, double *d_v, int64_t rows, int64_t cols, int64_t ld, double *d_l, int64_t ldl,
+                               int64_t *d_info);
+int lfb_apply_constraints_dev_f64(lfb_handle *h, double *d_v, int64_t n, int64_t k, int64_t ldv, const double *d_cholesky_yy,
+                                  int64_t m, int64_t ldl, const double *d_y, int64_t ldy);
 /* General column-major GEMM on the engine's own kernels (used by tests / yard-stick benches):
  * C = alpha op(A) op(B) + beta C,  ta/tb: 0 = N, 1 = T. */
 int lfb_gemm_dev_f64(lfb_handle *h, int ta, int tb, int64_t m, int64_t n, int64_t k, double alpha,

@@ -22,7 +22,7 @@ __all__ = [
     "Engine", "engine", "UPPER", "LOWER",
     "qr", "qr_into", "qr_tsqr", "qr_tsqr_into", "QRDecomp", "least_squares", "least_squares_into", "qr_batched", "cholesky_batched",
     "cholesky", "cholesky_dirty", "cholesky_into", "cholesky_into_dirty", "cholesky_inplace", "cholesky_inplace_dirty",
-    "solvec", "solvec_into", "solvec_inplace", "invc", "invc_inplace",
+    "solvec", "solvec_into", "solvec_inplace", "invc", "invc_inplace", "orthonormalize", "apply_constraints",
     "solve_triangular", "solve_triangular_into", "solve_triangular_inplace", "triangular_inplace", "into_triangular",
     "is_triangular", "sym_tridiagonal", "TridiagonalDecomp", "bidiagonal", "BidiagonalDecomp",
     "svd", "svd_into", "sort_svd", "sort_svd_asc", "sort_svd_desc",
@@ -403,6 +403,36 @@ def invc_inplace(a, eng=None):  # cholesky.rs:178-182 (the identity right-hand s
 
 def invc(a, eng=None):  # cholesky.rs:193-199
     return invc_inplace(_owned(a), eng)
+
+
+# ---- the dense blocks of LOBPCG: src/lobpcg/algorithm.rs ---------------------------------------------
+def orthonormalize(v: np.ndarray, eng=None):
+    """lobpcg/algorithm.rs:81-97 orthonormalize(v) -> (u, gram_vv_fac): Gram matrix, its Cholesky factor and the
+    triangular solve on the transposed block as ONE library call (lfb_orthonormalize); `v` is consumed (overwritten
+    with u, as the reference moves it).  NotPositiveDefinite where cholesky_into fails (:83)."""
+    e = eng or engine()
+    rows, cols = v.shape
+    l = np.zeros((cols, cols), dtype=v.dtype)
+    fail = C.c_int64(-1)
+    st = e.call("lfb_orthonormalize" + _sfx(v), *_view(v), *_view(l)[:1], *_view(l)[3:], C.byref(fail))
+    if st == _ffi.NOT_POSITIVE_DEFINITE:
+        raise NotPositiveDefinite(fail.value)
+    e._check(st)
+    return v, l
+
+
+def apply_constraints(v: np.ndarray, cholesky_yy: np.ndarray, y: np.ndarray, eng=None) -> np.ndarray:
+    """lobpcg/algorithm.rs:63-76: v -= y * solve_triangular(cholesky_yy, y^T v, Lower), in place, one library call."""
+    e = eng or engine()
+    m = _check_square(cholesky_yy)
+    if y.shape != (v.shape[0], m):
+        raise ValueError(f"y has shape {y.shape}, expected {(v.shape[0], m)}")   # ndarray panics on the mismatch
+    y = np.asarray(y, dtype=v.dtype)
+    cholesky_yy = np.asarray(cholesky_yy, dtype=v.dtype)
+    lv = _view(cholesky_yy)
+    st = e.call("lfb_apply_constraints" + _sfx(v), *_view(v), lv[0], m, lv[3], lv[4], *_view(y))
+    e._check(st)
+    return v
 
 
 # ---- triangular: src/triangular.rs ---------------------------------------------------------------

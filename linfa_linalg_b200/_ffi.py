@@ -52,6 +52,8 @@ _TYPED = {
     "lfb_solvec": [_vp] + _VIEW + [_int] + _VIEW + [C.POINTER(_i64)],
     "lfb_invc": [_vp] + _VIEW + [_vp, _i64, _i64, C.POINTER(_i64)],
     "lfb_svd": [_vp] + _VIEW + [_vp, _vp, _i64, _i64, _vp, _i64, _i64],
+    "lfb_orthonormalize": [_vp] + _VIEW + [_vp, _i64, _i64, C.POINTER(_i64)],
+    "lfb_apply_constraints": [_vp] + _VIEW + [_vp, _i64, _i64, _i64] + _VIEW,
     "lfb_qr_batched": [_vp, _vp, _i64, _i64, _i64, _vp],
     "lfb_cholesky_batched": [_vp, _vp, _i64, _i64, _int, C.POINTER(_i64), C.POINTER(_i64)],
     "lfb_qr_dev": [_vp, _vp, _i64, _i64, _i64, _vp],
@@ -74,6 +76,8 @@ SIGNATURES.update({
     "lfb_tsqr_apply_q_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
     "lfb_hh_reconstruct_top_dev_f64": [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp],
     "lfb_hh_reconstruct_rows_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
+    "lfb_orthonormalize_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp],
+    "lfb_apply_constraints_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64],
     "lfb_gemm_dev_f64": [_vp, _int, _int, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _dbl, _vp, _i64],
     "lfb_gemm_dev_f32": [_vp, _int, _int, _i64, _i64, _i64, _flt, _vp, _i64, _vp, _i64, _flt, _vp, _i64],
 })

@@ -442,6 +442,50 @@ int solvec_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int
     LFB_API_END(h)
 }
 
+// lobpcg/algorithm.rs:81-97 orthonormalize: v (rows x cols) <- v L^-T, l (cols x cols) <- L = chol(v^T v), one round trip.
+template <typename T>
+int orthonormalize_host(lfb_handle *h, T *v, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *l, int64_t l_rs, int64_t l_cs,
+                        int64_t *fail_index) {
+    if (rows < 0 || cols < 0) return fail(h, LFB_INVALID_ARGUMENT, "negative dimension");
+    if (fail_index) *fail_index = -1;
+    if (cols == 0) return LFB_OK;
+    int64_t info = 0;
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(std::max<int64_t>(rows, 1), 2), ldl = round_up(cols, 2);
+    DevBuf<T> dV(*h, (size_t)ld * cols), dL(*h, (size_t)ldl * cols);
+    DevBuf<int64_t> dInfo(*h, 1);
+    if (rows > 0) upload<T>(*h, v, rows, cols, rs, cs, dV, ld);
+    orthonormalize<T>(*h, dV, rows, cols, ld, dL, ldl, dInfo);
+    LFB_CUDA(cudaMemcpyAsync(&info, dInfo.get(), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    LFB_CUDA(cudaStreamSynchronize(h->stream));
+    if (info != 0) {
+        if (fail_index) *fail_index = info - 1;
+        h->err = "Matrix is not positive definite";
+        return LFB_NOT_POSITIVE_DEFINITE;
+    }
+    if (rows > 0) download<T>(*h, dV, ld, v, rows, cols, rs, cs);
+    if (l) download<T>(*h, dL, ldl, l, cols, cols, l_rs, l_cs);
+    LFB_API_END(h)
+}
+
+// lobpcg/algorithm.rs:63-76 apply_constraints: v (n x k) -= y (L_yy^-1 (y^T v)), one round trip.
+template <typename T>
+int apply_constraints_host(lfb_handle *h, T *v, int64_t n, int64_t k, int64_t rs, int64_t cs, const T *lyy, int64_t m, int64_t l_rs,
+                           int64_t l_cs, const T *y, int64_t y_rows, int64_t y_cols, int64_t y_rs, int64_t y_cs) {
+    if (n < 0 || k < 0 || m < 0) return fail(h, LFB_INVALID_ARGUMENT, "negative dimension");
+    if (y_rows != n || y_cols != m) return fail(h, LFB_INVALID_ARGUMENT, "y must be (rows of v) x (order of cholesky_yy)");
+    if (n == 0 || k == 0 || m == 0) return LFB_OK;
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(n, 2), ldl = round_up(m, 2);
+    DevBuf<T> dV(*h, (size_t)ld * k), dY(*h, (size_t)ld * m), dL(*h, (size_t)ldl * m);
+    upload<T>(*h, v, n, k, rs, cs, dV, ld);
+    upload<T>(*h, y, n, m, y_rs, y_cs, dY, ld);
+    upload<T>(*h, lyy, m, m, l_rs, l_cs, dL, ldl);
+    apply_constraints<T>(*h, dV, n, k, ld, dL, m, ldl, dY, ld);
+    download<T>(*h, dV, ld, v, n, k, rs, cs);
+    LFB_API_END(h)
+}
+
 template <typename T>
 int invc_host(lfb_handle *h, const T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *inv, int64_t i_rs, int64_t i_cs,
               int64_t *fail_index) {
@@ -752,6 +796,33 @@ int lfb_eigh_f32(lfb_handle *h, const float *a, int64_t r, int64_t c, int64_t rs
 LFB_SOLVE_ENTRIES(f64, double)
 LFB_SOLVE_ENTRIES(f32, float)
 #undef LFB_SOLVE_ENTRIES
+#define LFB_LOBPCG_ENTRIES(SFX, T)                                                                                         \
+    int lfb_orthonormalize_##SFX(lfb_handle *h, T *v, int64_t r, int64_t c, int64_t rs, int64_t cs, T *l, int64_t lrs,     \
+                                 int64_t lcs, int64_t *fail_index) {                                                       \
+        return orthonormalize_host<T>(h, v, r, c, rs, cs, l, lrs, lcs, fail_index);                                        \
+    }                                                                                                                      \
+    int lfb_apply_constraints_##SFX(lfb_handle *h, T *v, int64_t n, int64_t k, int64_t rs, int64_t cs, const T *lyy,       \
+                                    int64_t m, int64_t lrs, int64_t lcs, const T *y, int64_t yr, int64_t yc, int64_t yrs,  \
+                                    int64_t ycs) {                                                                         \
+        return apply_constraints_host<T>(h, v, n, k, rs, cs, lyy, m, lrs, lcs, y, yr, yc, yrs, ycs);                       \
+    }
+LFB_LOBPCG_ENTRIES(f64, double)
+LFB_LOBPCG_ENTRIES(f32, float)
+#undef LFB_LOBPCG_ENTRIES
+int lfb_orthonormalize_dev_f64(lfb_handle *h, double *d_v, int64_t rows, int64_t cols, int64_t ld, double *d_l, int64_t ldl,
+                               int64_t *d_info) {
+    if (rows < 0 || cols < 0 || !d_info) return fail(h, LFB_INVALID_ARGUMENT, "bad arguments");
+    LFB_API_BEGIN(h)
+    orthonormalize<double>(*h, d_v, rows, cols, ld, d_l, ldl, d_info);
+    LFB_API_END(h)
+}
+int lfb_apply_constraints_dev_f64(lfb_handle *h, double *d_v, int64_t n, int64_t k, int64_t ldv, const double *d_lyy, int64_t m,
+                                  int64_t ldl, const double *d_y, int64_t ldy) {
+    if (n < 0 || k < 0 || m < 0) return fail(h, LFB_INVALID_ARGUMENT, "negative dimension");
+    LFB_API_BEGIN(h)
+    apply_constraints<double>(*h, d_v, n, k, ldv, d_lyy, m, ldl, d_y, ldy);
+    LFB_API_END(h)
+}
 int lfb_svd_f64(lfb_handle *h, const double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *sv, double *u, int64_t urs, int64_t ucs, double *vt, int64_t vrs, int64_t vcs) { return svd_host<double>(h, a, r, c, rs, cs, sv, u, urs, ucs, vt, vrs, vcs); }
 int lfb_svd_f32(lfb_handle *h, const float *a, int64_t r, int64_t c, int64_t rs, int64_t cs, float *sv, float *u, int64_t urs, int64_t ucs, float *vt, int64_t vrs, int64_t vcs) { return svd_host<float>(h, a, r, c, rs, cs, sv, u, urs, ucs, vt, vrs, vcs); }
 int lfb_bidiagonal_f64(lfb_handle *h, double *a, int64_t r, int64_t c, int64_t rs, int64_t cs, double *d, double *e) { return bidiagonal_host<double>(h, a, r, c, rs, cs, d, e); }

@@ -238,6 +238,13 @@ template <typename T> void tsqr_explicit_q(lfb_handle &h, T *A, int64_t rows, in
 template <typename T> void tsqr_apply_q(lfb_handle &h, T *Q, int64_t rows, int64_t cols, int64_t ld, const T *Qs, int64_t ldqs);
 // X U = B in place on B (rows x n), U upper triangular n x n.
 template <typename T> void trsm_right_upper(lfb_handle &h, int64_t rows, int64_t n, const T *U, int64_t ldu, T *B, int64_t ldb);
+// X op(Tri) = B in place on B (rows x n): trans_lower = 0 -> Tri is upper, 1 -> Tri is lower and the system is X Tri^T = B.
+template <typename T> void trsm_right(lfb_handle &h, int64_t rows, int64_t n, const T *Tri, int64_t ldt, int trans_lower, T *B,
+                                      int64_t ldb, const int64_t *info);
+// LOBPCG's dense blocks kept on the device (lobpcg/algorithm.rs:63-97), lobpcg_blocks.cu.
+template <typename T> void orthonormalize(lfb_handle &h, T *V, int64_t rows, int64_t cols, int64_t ld, T *Lm, int64_t ldl, int64_t *d_info);
+template <typename T> void apply_constraints(lfb_handle &h, T *V, int64_t n, int64_t k, int64_t ldv, const T *Lyy, int64_t m, int64_t ldl,
+                                             const T *Y, int64_t ldy);
 // Householder reconstruction (tsqr_hr.cu): top n x n block of an explicit Q -> reference compact form; U' for the rows below.
 template <typename T> void hh_reconstruct_top(lfb_handle &h, T *Qtop, int64_t n, int64_t ld, const T *R, int64_t ldr, T *U, int64_t ldu, T *diag);
 // Tall-skinny thin QR in the reference's compact form (identical contract to qr_factor) via TSQR + reconstruction.

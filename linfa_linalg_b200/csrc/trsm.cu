@@ -170,24 +170,38 @@ void trsm_left(lfb_handle &h, int lower, int trans, int64_t n, int64_t nrhs, con
     }
 }
 
-// X U = B in place on B (rows x n, column-major), U n x n upper triangular (only that triangle is read): the
-// right-hand solve Y2 = Q2 U^-1 of the Householder reconstruction (tsqr_hr.cu).  Left-looking over 64-column
-// blocks: the finished block columns enter by one GEMM, the diagonal block by the base kernel with every ROW of B as
-// one right-hand side (element j of vector v at B[v + j*ldb]).
+// X U = B in place on B (rows x n, column-major) with U upper triangular, given either as U itself (trans_lower = 0:
+// U[i, j] = Tri[i + j*ldt], only the upper triangle is read) or as the transpose of a lower-triangular factor
+// (trans_lower = 1: U = L^T, U[i, j] = Tri[j + i*ldt], only the lower triangle is read).  The right-hand solves of the
+// Householder reconstruction (Y2 = Q2 U^-1, tsqr_hr.cu) and of LOBPCG's orthonormalize (V L^-T, lobpcg/algorithm.rs:91-94).
+// Left-looking over 64-column blocks: the finished block columns enter by one GEMM, the diagonal block by the base
+// kernel with every ROW of B as one right-hand side (element j of vector v at B[v + j*ldb]).  `info` (device, may be
+// null): a non-zero value skips the diagonal-block solves (the factor is not valid).
 template <typename T>
-void trsm_right_upper(lfb_handle &h, int64_t rows, int64_t n, const T *U, int64_t ldu, T *B, int64_t ldb) {
+void trsm_right(lfb_handle &h, int64_t rows, int64_t n, const T *Tri, int64_t ldt, int trans_lower, T *B, int64_t ldb,
+                const int64_t *info) {
     if (rows <= 0 || n <= 0) return;
     for (int64_t j0 = 0; j0 < n; j0 += CB) {
         const int nb = (int)std::min<int64_t>(CB, n - j0);
-        if (j0 > 0) gemm<T>(h, 0, 0, rows, nb, j0, T(-1), B, ldb, U + j0 * ldu, ldu, T(1), B + j0 * ldb, ldb);
-        // equation j: sum_{i <= j} x_i U[i, j] = b_j  ->  M(j, i) = U[i + j*ldu]: sj = ldu, si = 1, forward
-        trsv_block<T>(h, true, U + j0 + j0 * ldu, ldu, 1, nb, (const T *)nullptr, B + j0 * ldb, /*sv=*/1, /*sb=*/ldb, rows, nullptr);
+        if (j0 > 0) {
+            if (!trans_lower) gemm<T>(h, 0, 0, rows, nb, j0, T(-1), B, ldb, Tri + j0 * ldt, ldt, T(1), B + j0 * ldb, ldb);
+            else gemm<T>(h, 0, 1, rows, nb, j0, T(-1), B, ldb, Tri + j0, ldt, T(1), B + j0 * ldb, ldb);   // (L[j0.., ..j0])^T
+        }
+        // equation j: sum_{i <= j} x_i U[i, j] = b_j  ->  M(j, i) = U[i, j]; forward substitution
+        const int64_t sj = trans_lower ? 1 : ldt, si = trans_lower ? ldt : 1;
+        trsv_block<T>(h, true, Tri + j0 + j0 * ldt, sj, si, nb, (const T *)nullptr, B + j0 * ldb, /*sv=*/1, /*sb=*/ldb, rows, info);
     }
+}
+
+template <typename T>
+void trsm_right_upper(lfb_handle &h, int64_t rows, int64_t n, const T *U, int64_t ldu, T *B, int64_t ldb) {
+    trsm_right<T>(h, rows, n, U, ldu, 0, B, ldb, nullptr);
 }
 
 #define INST(T)                                                                                       \
     template void trsm_left<T>(lfb_handle &, int, int, int64_t, int64_t, const T *, int64_t, const T *, T *, int64_t); \
-    template void trsm_right_upper<T>(lfb_handle &, int64_t, int64_t, const T *, int64_t, T *, int64_t);
+    template void trsm_right_upper<T>(lfb_handle &, int64_t, int64_t, const T *, int64_t, T *, int64_t); \
+    template void trsm_right<T>(lfb_handle &, int64_t, int64_t, const T *, int64_t, int, T *, int64_t, const int64_t *);
 INST(float)
 INST(double)
 #undef INST

@@ -271,3 +271,25 @@ def cholesky_batched(a: np.ndarray, clean: bool = True):
         if st != 0:
             return b, fail
     return -1, -1
+
+
+def lobpcg_orthonormalize(v: np.ndarray):
+    """lobpcg/algorithm.rs:81-97 orthonormalize(v) -> (u, gram_vv_fac), composed from the restated routines:
+    gram = v^T v (:82, ndarray `dot`: third-party GEMM, restated by definition), cholesky_into (:83, clean lower),
+    u = solve_triangular_into(L, v^T, Lower)^T (:91-94).  Returns (status, fail_index, u, L); status 1 = NotPositiveDefinite."""
+    gram = np.ascontiguousarray(v.T @ v)
+    st, fi = cholesky(gram, clean=True)
+    if st != 0:
+        return st, fi, None, None
+    vt = np.ascontiguousarray(v.T)
+    solve_triangular(gram, vt, 1)
+    return 0, -1, np.ascontiguousarray(vt.T), gram
+
+
+def lobpcg_apply_constraints(v: np.ndarray, cholesky_yy: np.ndarray, y: np.ndarray):
+    """lobpcg/algorithm.rs:63-76 apply_constraints, in place on v: gram_yv = y^T v (:68); u = solve_triangular_into
+    (cholesky_yy, gram_yv, Lower) (:70-72); v -= y u (:75, general_mat_mul)."""
+    u = np.ascontiguousarray(y.T @ v)
+    solve_triangular(np.ascontiguousarray(cholesky_yy), u, 1)
+    v -= y @ u
+    return v

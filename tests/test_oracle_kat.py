@@ -258,3 +258,35 @@ def test_svd_kats():
         k = min(shape)
         np.testing.assert_allclose(vt @ vt.T, np.eye(k), atol=1e-10)
         np.testing.assert_allclose(u.T @ u if shape[0] >= shape[1] else u @ u.T, np.eye(k), atol=1e-10)
+
+
+def test_lobpcg_orthonormalize_properties():  # src/lobpcg/algorithm.rs:486-503 (test_orthonormalize), same tolerances
+    m = np.random.default_rng(0).uniform(0, 1, (10, 10)) * 10.0
+    st, fi, n, l = O.lobpcg_orthonormalize(m.copy())
+    assert st == 0 and fi == -1
+    np.testing.assert_allclose(n @ n.T, np.eye(10), atol=1e-2)
+    w = m.copy()
+    d = O.qr(w)
+    np.testing.assert_allclose(np.abs(O.qr_into_r(w, d)), np.abs(l.T), atol=1e-2)
+    assert np.all(np.triu(l, 1) == 0)                       # cholesky_into zeroes the strict upper (cholesky.rs:78-82)
+    # a rank-deficient block fails exactly where cholesky_into does (algorithm.rs:83 `?`)
+    bad = m.copy()
+    bad[:, 3] = 0.0
+    st, fi, _, _ = O.lobpcg_orthonormalize(bad)
+    assert st == 1 and fi == 3
+
+
+def test_lobpcg_apply_constraints_restatement():  # src/lobpcg/algorithm.rs:63-76
+    rng = np.random.default_rng(1)
+    y = np.linalg.qr(rng.uniform(-1, 1, (30, 4)))[0]        # orthonormal constraints: cholesky_yy = I and v becomes orthogonal to y
+    v = rng.uniform(-1, 1, (30, 5))
+    lyy = (y.T @ y).copy()
+    assert O.cholesky(lyy)[0] == 0
+    out = O.lobpcg_apply_constraints(v.copy(), lyy, y)
+    assert np.max(np.abs(y.T @ out)) <= 1e-13
+    # general y: exactly the composition the reference performs (one forward solve, no back solve)
+    y2 = rng.uniform(-1, 1, (30, 4))
+    l2 = (y2.T @ y2).copy()
+    assert O.cholesky(l2)[0] == 0
+    out2 = O.lobpcg_apply_constraints(v.copy(), l2, y2)
+    np.testing.assert_allclose(out2, v - y2 @ np.linalg.solve(np.tril(l2), y2.T @ v), atol=1e-12)
