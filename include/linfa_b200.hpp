@@ -186,6 +186,33 @@ void solvec_inplace(Engine &e, View<T> a, View<T> b) {
     solve_triangular_inplace(e, a.t(), b, UPLO::Upper);
 }
 
+// lobpcg/algorithm.rs:81-97  orthonormalize(v) -> (u, gram_vv_fac): v is overwritten with u, the factor is returned
+template <typename T>
+Matrix<T> orthonormalize(Engine &e, View<T> v) {
+    Matrix<T> l(v.cols, v.cols);
+    int64_t fail = -1;
+    int st;
+    if constexpr (detail::is64<T>) st = lfb_orthonormalize_f64(e.handle(), v.ptr, v.rows, v.cols, v.rs, v.cs, l.data.data(), l.cols, 1, &fail);
+    else st = lfb_orthonormalize_f32(e.handle(), v.ptr, v.rows, v.cols, v.rs, v.cs, l.data.data(), l.cols, 1, &fail);
+    if (st == LFB_NOT_POSITIVE_DEFINITE) throw NotPositiveDefinite(fail);
+    e.check(st);
+    return l;
+}
+
+// lobpcg/algorithm.rs:63-76  apply_constraints(v, cholesky_yy, y), in place on v
+template <typename T>
+void apply_constraints(Engine &e, View<T> v, View<T> cholesky_yy, View<T> y) {
+    if (cholesky_yy.rows != cholesky_yy.cols) throw NotSquare(cholesky_yy.rows, cholesky_yy.cols);
+    int st;
+    if constexpr (detail::is64<T>)
+        st = lfb_apply_constraints_f64(e.handle(), v.ptr, v.rows, v.cols, v.rs, v.cs, cholesky_yy.ptr, cholesky_yy.rows, cholesky_yy.rs,
+                                       cholesky_yy.cs, y.ptr, y.rows, y.cols, y.rs, y.cs);
+    else
+        st = lfb_apply_constraints_f32(e.handle(), v.ptr, v.rows, v.cols, v.rs, v.cs, cholesky_yy.ptr, cholesky_yy.rows, cholesky_yy.rs,
+                                       cholesky_yy.cs, y.ptr, y.rows, y.cols, y.rs, y.cs);
+    e.check(st);
+}
+
 // tridiagonal.rs:31-113
 template <typename T>
 struct TridiagonalDecomp {
