@@ -89,15 +89,20 @@ def tsqr_qr(block, ops, n: int, group=None):
         apply_q(x, qs)                x <- x * qs          (qs: contiguous (n, n) tensor, column-major n x n)
         reconstruct_top(x, r, u, diag)   first n rows of x -> top block of the compact factor; u <- U', diag
         reconstruct_rows(x, row0, u)  rows row0.. of x <- (those rows) U'^-1
-    Rank 0 must own at least n rows."""
+    Every rank must own at least n rows (checked collectively: ValueError on all ranks otherwise)."""
     import torch
     import torch.distributed as dist
     on = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size(group) if on else 1
     rank = dist.get_rank(group) if on else 0
     rows_local = block.shape[1]
-    if rank == 0 and rows_local < n:
-        raise ValueError(f"rank 0 owns {rows_local} rows, fewer than the {n} columns")
+    # every rank factors a thin block (qr.rs:34-36 NotThin per block) and rank 0 must hold the whole top n x n block:
+    # agree on that BEFORE the first data collective, so a short shard raises on every rank instead of hanging the others
+    ok = torch.tensor([1 if rows_local >= n else 0], dtype=torch.int32, device=block.device)
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
+        raise ValueError(f"tsqr_qr needs at least n = {n} rows on every rank (this rank owns {rows_local})")
     r = ops.explicit_q(block)
     if world > 1:
         r_all = torch.empty((world * n, n), dtype=r.dtype, device=r.device)

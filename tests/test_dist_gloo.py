@@ -179,3 +179,26 @@ def test_tsqr_qr_ranks_match_reference_compact_factor(world):
     rr = O.qr_into_r(factor.copy(), got[0][1])
     assert np.linalg.norm(q @ rr - full) <= tol * n
     assert np.linalg.norm(q.T @ q - np.eye(n)) <= 64 * rows * 2.2e-16
+
+
+def _tsqr_qr_short_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 6
+    rows = 40 if rank == 0 else 3                       # rank 1's shard is shorter than n
+    block = torch.from_numpy(np.random.default_rng(rank).uniform(-1, 1, (n, rows)))
+    try:
+        D.tsqr_qr(block, _CpuTsqrOps(), n)
+        out[rank] = "no error"
+    except ValueError as ex:
+        out[rank] = str(ex)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_tsqr_qr_short_shard_raises_on_every_rank():
+    """A shard with fewer rows than columns cannot be factored thin (qr.rs:34-36): both ranks raise, nobody hangs."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_tsqr_qr_short_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert "at least n = 6 rows" in out[0] and "at least n = 6 rows" in out[1]
