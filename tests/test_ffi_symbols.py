@@ -73,6 +73,30 @@ def test_shape_errors_raised_before_any_device_work():
     assert L.eigvalsh(np.zeros((0, 0)), eng=object()).shape == (0,)
     with pytest.raises(L.EmptyMatrix):                                   # svd.rs:23-25, :602-607
         L.svd(np.zeros((0, 1)), False, False, eng=object())
+    with pytest.raises(L.NotThin):                                       # qr.rs:34-36 on the tall-skinny route too
+        L.qr_tsqr_into(np.zeros((2, 3)), eng=object())
+    with pytest.raises(L.NotSquare):                                     # cholesky_yy must be square (lobpcg/algorithm.rs:70)
+        L.apply_constraints(np.zeros((5, 2)), np.zeros((2, 3)), np.zeros((5, 2)), eng=object())
+    with pytest.raises(ValueError):                                      # y is (rows of v) x (order of cholesky_yy)
+        L.apply_constraints(np.zeros((5, 2)), np.eye(3), np.zeros((4, 3)), eng=object())
+
+
+def test_null_handle_is_an_argument_error_not_a_crash():
+    """Every entry point validates the handle before touching CUDA (no device needed to see that)."""
+    import ctypes as C
+    from linfa_linalg_b200 import _ffi
+    lib = _ffi.load()
+    buf = (C.c_double * 16)()
+    p = C.cast(buf, C.c_void_p)
+    assert lib.lfb_qr_f64(None, p, 4, 4, 4, 1, p) == _ffi.INVALID_ARGUMENT
+    assert lib.lfb_qr_tsqr_f64(None, p, 4, 4, 4, 1, p) == _ffi.INVALID_ARGUMENT
+    assert lib.lfb_qr_tsqr_dev_f64(None, p, 4, 4, 4, p) == _ffi.INVALID_ARGUMENT
+    assert lib.lfb_tsqr_explicit_q_dev_f64(None, p, 4, 4, 4, p, 4) == _ffi.INVALID_ARGUMENT
+    assert lib.lfb_orthonormalize_f64(None, p, 4, 4, 4, 1, p, 4, 1, None) == _ffi.INVALID_ARGUMENT
+    assert lib.lfb_apply_constraints_dev_f64(None, p, 4, 2, 4, p, 2, 2, p, 4) == _ffi.INVALID_ARGUMENT
+    assert lib.lfb_set_option(None, b"qr_tsqr_auto", 1) == _ffi.INVALID_ARGUMENT
+    # shape errors come before the handle is used
+    assert lib.lfb_qr_tsqr_f64(None, p, 2, 3, 3, 1, p) == _ffi.NOT_THIN
 
 
 def test_sort_eig_host_side():
