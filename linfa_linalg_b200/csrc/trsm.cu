@@ -12,13 +12,6 @@ namespace {
 
 constexpr int CB = 64;  // diagonal block size of the base kernels
 
-template <typename T> __device__ __forceinline__ T t_sqrt(T x);
-template <> __device__ __forceinline__ double t_sqrt<double>(double x) { return sqrt(x); }
-template <> __device__ __forceinline__ float t_sqrt<float>(float x) { return sqrtf(x); }
-template <typename T> __device__ __forceinline__ T t_rsqrt(T x);
-template <> __device__ __forceinline__ double t_rsqrt<double>(double x) { return rsqrt(x); }
-template <> __device__ __forceinline__ float t_rsqrt<float>(float x) { return rsqrtf(x); }
-
 // Base triangular solve for independent vectors against an nb x nb (nb <= 64) coefficient matrix,
 // one vector per thread, blocked 8 x 8 with everything in shared memory and dynamic outer loops so
 // the code stays small (instruction-cache resident):
