@@ -22,7 +22,7 @@ __all__ = [
     "Engine", "engine", "UPPER", "LOWER",
     "qr", "qr_into", "qr_tsqr", "qr_tsqr_into", "QRDecomp", "least_squares", "least_squares_into", "qr_batched", "cholesky_batched",
     "cholesky", "cholesky_dirty", "cholesky_into", "cholesky_into_dirty", "cholesky_inplace", "cholesky_inplace_dirty",
-    "solvec", "solvec_into", "solvec_inplace", "invc", "invc_inplace", "orthonormalize", "apply_constraints",
+    "solvec", "solvec_into", "solvec_inplace", "invc", "invc_inplace", "orthonormalize", "apply_constraints", "generalized_eig", "sorted_eig",
     "solve_triangular", "solve_triangular_into", "solve_triangular_inplace", "triangular_inplace", "into_triangular",
     "is_triangular", "sym_tridiagonal", "TridiagonalDecomp", "bidiagonal", "BidiagonalDecomp",
     "svd", "svd_into", "sort_svd", "sort_svd_asc", "sort_svd_desc",
@@ -579,6 +579,29 @@ def sort_eig_asc(res):
 
 def sort_eig_desc(res):
     return sort_eig(res, LARGEST)
+
+
+# ---- lobpcg/algorithm.rs:16-44: the small dense eigenproblems of LOBPCG (host compositions over eigh) ----
+def generalized_eig(a: np.ndarray, b: np.ndarray, eng=None):
+    """lobpcg/algorithm.rs:16-25: pencil (A, B) through two `eigh_into` calls; the k x k products in between are
+    ndarray GEMMs in the reference and NumPy GEMMs here (k = a few block sizes)."""
+    vals_b, vecs_b = eigh_into(b, eng)
+    floor = a.dtype.type(np.float32(1e-10))                          # `A::from(1e-10f32)` (:18)
+    recip = 1.0 / np.sqrt(np.maximum(vals_b, floor))
+    vecs_b_tilde = vecs_b * recip                                    # Array2 * Array1: column j scaled by recip[j] (:19)
+    a_tilde = vecs_b_tilde.T @ (a @ vecs_b_tilde)                    # :20
+    vals_a, vecs_a = eigh_into(np.ascontiguousarray(a_tilde), eng)   # :21
+    return vals_a, vecs_b_tilde @ vecs_a                             # :22-24
+
+
+def sorted_eig(a: np.ndarray, b, size: int, order=LARGEST, eng=None):
+    """lobpcg/algorithm.rs:28-44: full (generalized) eigenproblem, sorted by `order`, signs made deterministic by the
+    first row (Rust's signum: the sign BIT), truncated to `size`.  `a` and `b` are consumed, as in the reference."""
+    res = generalized_eig(a, b, eng) if b is not None else eigh_into(a, eng)
+    vals, vecs = sort_eig(res, order)
+    s = np.where(np.signbit(vecs[0, :]), -1.0, 1.0).astype(vecs.dtype) if vecs.size else np.ones(0, dtype=vecs.dtype)
+    vecs = vecs * s
+    return vals[:size], vecs[:, :size]
 
 
 # ---- svd: src/svd.rs ---------------------------------------------------------------------------------

@@ -322,3 +322,35 @@ def test_svd_f32(L, eng):  # tests/svd.rs:66-72
     assert np.max(np.abs(s - np.array([3.0, 2.0]))) <= 1e-7
     assert np.max(np.abs(u - np.array([[1.0, 0], [0, -1.0]]))) <= 1e-7
     assert np.max(np.abs(vt - np.eye(2))) <= 1e-7
+
+
+# ---- src/lobpcg/algorithm.rs: the dense helpers of LOBPCG ---------------------------------------------------------------------
+def test_lobpcg_sorted_eigen(L, eng):  # src/lobpcg/algorithm.rs:457-472
+    m = np.random.default_rng(21).uniform(0, 1, (10, 10)) * 10.0
+    m = m.T @ m
+    vals, vecs = L.sorted_eig(m.copy(), None, 10, L.LARGEST, eng)
+    assert np.all(vals[:-1] >= vals[1:])
+    assert np.max(np.abs(vecs @ np.diag(vals) @ vecs.T - m)) <= 1e-5
+    assert not np.any(np.signbit(vecs[0, :]))                      # deterministic signs (:40-42)
+    v3, q3 = L.sorted_eig(m.copy(), None, 3, L.SMALLEST, eng)      # truncation (:43)
+    assert v3.shape == (3,) and q3.shape == (10, 3) and np.max(np.abs(v3 - vals[::-1][:3])) <= 1e-8 * vals[0]
+
+
+def test_lobpcg_generalized_eigenvalue(L, eng):  # src/lobpcg/algorithm.rs:505-522
+    m = np.random.default_rng(22).uniform(0, 1, (10, 10))
+    m = m.T @ m
+    ident = np.eye(10)
+    m_inv = L.qr(m, eng).inverse()
+    vals, _ = L.sorted_eig(m.copy(), m.copy(), 10, L.LARGEST, eng)
+    assert np.max(np.abs(vals - 1.0)) <= 1e-4
+    vals1, _ = L.sorted_eig(m.copy(), ident.copy(), 10, L.LARGEST, eng)
+    vals2, _ = L.sorted_eig(ident.copy(), m_inv, 10, L.LARGEST, eng)
+    assert np.max(np.abs(vals1 - vals2)) <= 1e-5
+
+
+def test_lobpcg_orthonormalize(L, eng):  # src/lobpcg/algorithm.rs:486-503
+    m = np.random.default_rng(23).uniform(0, 1, (10, 10)) * 10.0
+    n, l = L.orthonormalize(m.copy(), eng)
+    assert eye_err(n @ n.T) <= 1e-2
+    r = L.qr(m, eng).into_r()
+    assert np.max(np.abs(np.abs(r) - np.abs(l.T))) <= 1e-2
