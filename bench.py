@@ -137,6 +137,11 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+def workload_name(n):
+    """config.workload, identical on both arms (the driver pairs the lines by it)."""
+    return f"Cholesky {n}x{n} SPD f64, lower, in place (BASELINE configs[1])"
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm for the same metric/config, timed on the
     box's host cores.  The Rust crate cannot be built in this image (no rustc/cargo), so this runs
@@ -163,7 +168,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Cholesky {args.n}x{args.n} SPD f64 (configs[1])", "sample": sample},
+        "config": {"workload": workload_name(args.n), "parallelism": "host cores: 1 (the reference is single-threaded)", "sample": sample},
         "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -352,7 +357,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Cholesky {n}x{n} SPD f64, lower, in place (BASELINE configs[1])",
+            "config": {"workload": workload_name(n),
                        "parallelism": "replicas only (one matrix per GPU; the path does not shard)" if world > 1 else "single GPU",
                        "l2": f"input {n * n * 8 / 2**20:.0f} MiB > 126 MiB L2 (inputs larger than L2; restored by a device copy each step)",
                        "residual_block": resid},
