@@ -648,7 +648,8 @@ int lfb_create(lfb_handle **out, int device) {
         h->sm_count = prop.multiProcessorCount;
         h->smem_optin = prop.sharedMemPerBlockOptin;
     } catch (const std::exception &) {
-        delete h;
+        cudaGetLastError();
+        lfb_destroy(h);   // releases whatever was created before the failure
         return LFB_ERR_CUDA;
     }
     *out = h;
@@ -664,6 +665,8 @@ int lfb_destroy(lfb_handle *h) {
     for (auto *s : h->subs) lfb_destroy(s);
     h->subs.clear();
     for (auto &b : h->blocks) cudaFree(b.p);
+    for (auto &e : h->prof_ev) if (e) cudaEventDestroy(e);
+    if (h->panel_dbg) cudaFree(h->panel_dbg);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
