@@ -184,8 +184,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n", type=int, default=16384)
-    ap.add_argument("--ref-n", type=int, default=2048)
-    ap.add_argument("--cpu-n", type=int, default=3072)
+    ap.add_argument("--ref-n", type=int, default=3072)      # ~3 s per step on one host core
+    ap.add_argument("--cpu-n", type=int, default=5120)      # ~12 s of CPU work (the 10-30 s sample the contract asks for)
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
