@@ -182,10 +182,12 @@ class QRDecomp:
     def generate_q(self) -> np.ndarray:  # qr.rs:86-88
         return _assemble_q(self._e, self.qr, 0, self.diag)
 
-    def into_r(self) -> np.ndarray:  # qr.rs:91-98 (host-side slicing, as in the reference)
+    def into_r(self) -> np.ndarray:  # qr.rs:91-98
+        """R as a NEW n x n array (strict lower zeroed, |diag| on the diagonal).  In Rust `into_r(self)` consumes the
+        decomposition; a Python object cannot be moved out of, so the compact factor is left intact and the object stays
+        usable (`generate_q`, `qt_mul`, `solve*` after `into_r` keep giving the reference's results)."""
         n = self.qr.shape[1]
-        r = self.qr[:n, :n]
-        triangular_inplace(r, UPPER, eng=self._e) if n > 64 else _host_triangular(r, UPPER)
+        r = np.triu(self.qr[:n, :n], 1)
         r[np.arange(n), np.arange(n)] = np.abs(self.diag)
         return r
 

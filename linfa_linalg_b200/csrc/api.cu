@@ -180,7 +180,11 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
     int64_t hld = 0;
     const Layout lay = classify(n, n, rs, cs, &hld);
     const bool tri = lay != L_GEN && n >= 2048;
-    const int64_t BAND = 1024;
+    // Bands of the trapezoid upload.  A diagonal block of the factorisation (chol_nb wide, a multiple of 64) must lie
+    // inside ONE band: the overlapped D2H hook below copies whole block columns including the upper part of their
+    // diagonal block, which is only defined (= the caller's own data) if that block was uploaded as part of a band.
+    const int64_t NBc = std::max<int64_t>(64, round_up(h->opt.chol_nb, 64));
+    const int64_t BAND = round_up(std::max<int64_t>(1024, NBc), NBc);
     if (!tri) {
         upload<T>(*h, a, n, n, rs, cs, dA, ld);
     } else if (lay == L_COL) {   // column j holds rows j..n-1: bands of columns
@@ -248,6 +252,9 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
         cholesky_lower<T>(*h, dA, n, ld, clean, dInfo);
     } catch (...) {
         h->chol_panel_hook = nullptr;
+        // copies queued by the hook may still be reading dA / the staging buffer: drain before the DevBufs are released
+        if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->stream);
         for (auto e : pev) cudaEventDestroy(e);
         throw;
     }
@@ -693,17 +700,21 @@ extern "C" {
 
 const char *lfb_last_error(lfb_handle *h) { return h ? h->err.c_str() : "null handle"; }
 
-int lfb_set_stream(lfb_handle *h, void *s) {
+// The workspace pool is not stream-aware (a DevBuf released at the end of an async `_dev` call may still be in use by
+// kernels queued on the stream), which is safe as long as every later user is queued on the SAME stream.  Switching
+// streams therefore drains the outgoing one first.
+static int switch_stream(lfb_handle *h, cudaStream_t s) {
     if (!h) return LFB_INVALID_ARGUMENT;
-    h->stream = (cudaStream_t)s;   // verbatim: NULL is the legacy default stream
-    return LFB_OK;
+    if (s == h->stream) return LFB_OK;
+    LFB_API_BEGIN(h)
+    LFB_CUDA(cudaStreamSynchronize(h->stream));
+    h->stream = s;
+    LFB_API_END(h)
 }
 
-int lfb_use_own_stream(lfb_handle *h) {
-    if (!h) return LFB_INVALID_ARGUMENT;
-    h->stream = h->own_stream;
-    return LFB_OK;
-}
+int lfb_set_stream(lfb_handle *h, void *s) { return switch_stream(h, (cudaStream_t)s); }   // verbatim: NULL is the legacy default stream
+
+int lfb_use_own_stream(lfb_handle *h) { return h ? switch_stream(h, h->own_stream) : LFB_INVALID_ARGUMENT; }
 
 int lfb_synchronize(lfb_handle *h) {
     LFB_API_BEGIN(h)
@@ -715,34 +726,28 @@ int64_t lfb_launch_count(lfb_handle *h) { return h ? h->launches : 0; }
 
 int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     if (!h || !key) return LFB_INVALID_ARGUMENT;
-    std::string k(key);
-    if (k == "qr_nb") h->opt.qr_nb = value;
-    else if (k == "qr_sub") h->opt.qr_sub = value;
-    else if (k == "chol_base") h->opt.chol_base = value;
-    else if (k == "chol_nb") h->opt.chol_nb = value;
-    else if (k == "gemm_tma") h->opt.gemm_tma = value;
-    else if (k == "gemm_splitk") h->opt.gemm_splitk = value;
-    else if (k == "gemm_v2") h->opt.gemm_v2 = value;
-    else if (k == "gemm_split_waves") h->opt.gemm_split_waves = value;
-    else if (k == "panel_cluster") h->opt.panel_cluster = value;
-    else if (k == "panel_cluster_max") h->opt.panel_cluster_max = value;
-    else if (k == "lookahead") h->opt.lookahead = value;
-    else if (k == "tsqr_chunk") h->opt.tsqr_chunk = value;
-    else if (k == "batched_quad") h->opt.batched_quad = value;
-    else if (k == "tsqr_streams") h->opt.tsqr_streams = value;
-    else if (k == "tsqr_graph") h->opt.tsqr_graph = value;
-    else if (k == "qr_tsqr_auto") h->opt.qr_tsqr_auto = value;
-    else if (k == "trd_fused") h->opt.trd_fused = value;
-    else if (k == "chol_overlap_d2h") h->opt.chol_overlap_d2h = value;
-    else if (k == "rot_staged") h->opt.rot_staged = value;
-    else if (k == "eigh_stable_2x2") h->opt.eigh_stable_2x2 = value;
-    else if (k == "rot_serial") h->opt.rot_serial = value;
-    else if (k == "fast_hypot") h->opt.fast_hypot = value;
-    else if (k == "bd_blocked") h->opt.bd_blocked = value;
-    else if (k == "trd_profile") h->opt.trd_profile = value;
-    else if (k == "trd_symv_async") h->opt.trd_symv_async = value;
-    else return LFB_INVALID_ARGUMENT;
-    return LFB_OK;
+    lfb::Options &o = h->opt;
+    // name, field, smallest and largest accepted value (anything else: LFB_INVALID_ARGUMENT, option unchanged)
+    struct Opt { const char *name; int64_t *field; int64_t lo, hi; };
+    const int64_t BIG = int64_t(1) << 40;
+    const Opt table[] = {
+        {"qr_nb", &o.qr_nb, 32, 1024}, {"qr_sub", &o.qr_sub, 1, 32}, {"chol_base", &o.chol_base, 1, 64},
+        {"chol_nb", &o.chol_nb, 64, 8192}, {"gemm_tma", &o.gemm_tma, 0, 1}, {"gemm_splitk", &o.gemm_splitk, 0, 1},
+        {"gemm_v2", &o.gemm_v2, 0, 1}, {"gemm_split_waves", &o.gemm_split_waves, 1, 64}, {"panel_cluster", &o.panel_cluster, 0, 2},
+        {"panel_cluster_max", &o.panel_cluster_max, 1, 16}, {"lookahead", &o.lookahead, 0, 1}, {"tsqr_chunk", &o.tsqr_chunk, 64, BIG},
+        {"batched_quad", &o.batched_quad, 0, 4}, {"tsqr_streams", &o.tsqr_streams, 1, 64}, {"tsqr_graph", &o.tsqr_graph, 0, 1},
+        {"qr_tsqr_auto", &o.qr_tsqr_auto, 0, 1}, {"trd_fused", &o.trd_fused, 0, 1}, {"chol_overlap_d2h", &o.chol_overlap_d2h, 0, 1},
+        {"rot_staged", &o.rot_staged, 0, 1}, {"eigh_stable_2x2", &o.eigh_stable_2x2, 0, 1}, {"rot_serial", &o.rot_serial, 0, 1},
+        {"fast_hypot", &o.fast_hypot, 0, 1}, {"bd_blocked", &o.bd_blocked, 0, 1}, {"trd_profile", &o.trd_profile, 0, 1},
+        {"trd_symv_async", &o.trd_symv_async, 0, 1},
+    };
+    for (const Opt &e : table)
+        if (std::strcmp(e.name, key) == 0) {
+            if (value < e.lo || value > e.hi) return fail(h, LFB_INVALID_ARGUMENT, "option value out of range");
+            *e.field = value;
+            return LFB_OK;
+        }
+    return fail(h, LFB_INVALID_ARGUMENT, "unknown option");
 }
 
 #define DEF2(name, T, sfx, args, call) \

@@ -176,7 +176,8 @@ template <typename T> inline T h_signum(T x) { return std::signbit(x) ? T(-1) : 
 
 // x.hypot(y) (givens.rs:19).  The matrix was scaled to max|a| = 1, so x^2 + y^2 cannot overflow; the plain
 // square root is used unless the squares get close to underflow.
-static bool FAST_HYPOT = true;
+// thread_local: set from the handle's option at the start of every eigh / svd call; two handles on two threads do not share it
+static thread_local bool FAST_HYPOT = true;
 template <typename T>
 inline T h_hypot(T x, T y) {
     const T r2 = x * x + y * y;

@@ -111,3 +111,24 @@ def test_sort_eig_host_side():
     np.testing.assert_array_equal(L.sort_eig_desc(vals), [3, 2, -1])
     with pytest.raises(ValueError):
         L.sort_eig(np.array([1.0, np.nan]))
+
+
+def test_cpp_mirror_header_compiles(tmp_path):
+    """include/linfa_b200.hpp (the C++ host mirror) and examples/qr_kat.cpp compile and link against the in-tree library;
+    the program itself needs a GPU and runs in tests/test_gpu_parity_2048.py."""
+    import shutil
+    import subprocess
+    from linfa_linalg_b200 import _ffi
+    gxx = shutil.which("g++")
+    assert gxx
+    libdir = os.path.dirname(_ffi.LIB_PATH)
+    subprocess.check_call([gxx, "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "qr_kat.cpp"), "-L" + libdir, "-llinfa_b200",
+                           "-Wl,-rpath," + libdir, "-o", str(tmp_path / "qr_kat")])
+
+
+def test_set_option_validates_ranges():
+    """lfb_set_option rejects unknown keys and out-of-range values before touching the handle's state."""
+    from linfa_linalg_b200 import _ffi
+    lib = _ffi.load()
+    assert lib.lfb_set_option(None, b"chol_nb", 512) == _ffi.INVALID_ARGUMENT
