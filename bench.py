@@ -315,35 +315,53 @@ def main():
         "step_frac_of_nominal_peak": flops / (ms / args.steps * 1e-3) / 1e12 / FP64_NOMINAL_TFLOPS,
     }
 
-    # ---- end to end through the public host API (pinned host buffers, H2D + D2H inside) ----
+    # ---- end to end through the public host API: H2D + D2H inside the timed region.  `e2e.value` is the contract's
+    #      pinned-host number; `e2e.pageable` is the same call on ordinary (pageable) memory, which is what a drop-in
+    #      ndarray caller hands over ----
     e2e = None
     if not args.no_e2e:
+        eng.set_stream(None)
+        ksteps = max(1, min(args.steps, 3))
+        fail = C.c_int64(-1)
+        # only lower-triangular trapezoids (bands of 1024 rows) cross PCIe: csrc/api.cu cholesky_host
+        tri_bytes = sum(min(n, r0 + 1024) * (min(n, r0 + 1024) - r0) * 8 for r0 in range(0, n, 1024)) if n >= 2048 else n * n * 8
+
+        def e2e_leg(host_src, host_work):
+            t_acc = 0.0
+            for it in range(ksteps + 1):
+                host_work.copy_(host_src)
+                barrier()
+                t0 = time.perf_counter()
+                st = lib.lfb_cholesky_f64(eng.h, C.c_void_p(host_work.data_ptr()), n, n, n, 1, 0, C.byref(fail))
+                dt = time.perf_counter() - t0
+                if st != 0:
+                    raise RuntimeError(f"lfb_cholesky_f64 status {st}")
+                if it > 0:
+                    t_acc += dt
+            return max_over_ranks(t_acc * 1e3)
+
         host_src = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
         host_src.copy_(S)
         host_work = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
         torch.cuda.synchronize()
-        eng.set_stream(None)
-        ksteps = max(1, min(args.steps, 3))
-        t_e2e = 0.0
-        fail = C.c_int64(-1)
-        for it in range(ksteps + 1):
-            host_work.copy_(host_src)
-            barrier()
-            t0 = time.perf_counter()
-            st = lib.lfb_cholesky_f64(eng.h, C.c_void_p(host_work.data_ptr()), n, n, n, 1, 0, C.byref(fail))
-            dt = time.perf_counter() - t0
-            if st != 0:
-                raise RuntimeError(f"lfb_cholesky_f64 status {st}")
-            if it > 0:
-                t_e2e += dt
-        t_e2e_ms = max_over_ranks(t_e2e * 1e3)
-        # only lower-triangular trapezoids (bands of 1024 rows) cross PCIe: csrc/api.cu cholesky_host
-        tri_bytes = sum(min(n, r0 + 1024) * (min(n, r0 + 1024) - r0) * 8 for r0 in range(0, n, 1024)) if n >= 2048 else n * n * 8
+        t_e2e_ms = e2e_leg(host_src, host_work)
+        # residual of what came back (first 2048-block of the row-major lower factor)
+        Lh = torch.tril(host_work[:2048, :2048]).to(dev)
+        e2e_resid = float((Lh @ Lh.t() - S[:2048, :2048]).norm() / S[:2048, :2048].norm())
         e2e = {"value": world * flops * ksteps / (t_e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
                "h2d_bytes_per_step": tri_bytes, "d2h_bytes_per_step": tri_bytes + 8, "steps": ksteps,
-               "ms_per_step": t_e2e_ms / ksteps, "api": "lfb_cholesky_f64 (host view, pinned, in place)"}
+               "ms_per_step": t_e2e_ms / ksteps, "api": "lfb_cholesky_f64 (host view, pinned, in place)", "residual_block": e2e_resid}
+        del host_work
+        try:
+            page_work = torch.empty((n, n), dtype=torch.float64)          # ordinary malloc'ed memory
+            t_pg_ms = e2e_leg(host_src, page_work)
+            e2e["pageable"] = {"value": world * flops * ksteps / (t_pg_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": t_pg_ms / ksteps,
+                               "api": "lfb_cholesky_f64 (host view, pageable, in place)"}
+            del page_work
+        except Exception as ex:
+            e2e["pageable"] = {"error": str(ex)[:120]}
         eng.set_stream(stream.cuda_stream)
-        del host_src, host_work
+        del host_src
 
     del S, work
     torch.cuda.empty_cache()
@@ -375,9 +393,45 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "extras": extras,
         }
+        # The N-dependent numbers of the paths that SHARD (batch split / TSQR row split), compact and LAST so that they
+        # survive a truncated tail of this line; speed-ups are against the values the N = 1 run of the same box left
+        # behind in .bench_n1.json (null if that run did not happen here).
+        line["sharded"] = sharded_summary(extras, world)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+N1_FILE = os.path.join(ROOT, ".bench_n1.json")
+
+
+def sharded_summary(extras, world):
+    def g(key, field):
+        v = extras.get(key, {})
+        return v.get(field) if isinstance(v, dict) else None
+    cur = {"batched_mps": g("batched_qr_f32", "matrices_per_s"), "batched_chol_mps": g("batched_chol_f32", "matrices_per_s"),
+           "tsqr_r_ms": g("tsqr_f64", "ms_per_step"), "tsqr_qr_ms": g("tsqr_qr_f64", "ms_per_step")}
+    out = {"n": world}
+    out.update({k: (round(v, 4) if isinstance(v, float) and v < 1e4 else (float(f"{v:.4g}") if v is not None else None)) for k, v in cur.items()})
+    out["checks_ok"] = all(bool(g(k, "check_ok")) for k in ("batched_qr_f32", "tsqr_f64", "tsqr_qr_f64") if k in extras)
+    if world == 1:
+        try:
+            json.dump(cur, open(N1_FILE, "w"))
+        except OSError:
+            pass
+        out["speedup_vs_1gpu"] = None
+        return out
+    sp = None
+    try:
+        one = json.load(open(N1_FILE))
+        sp = {}
+        for k, v in cur.items():
+            if v and one.get(k):
+                sp[k.replace("_ms", "").replace("_mps", "")] = round((v / one[k]) if k.endswith("mps") else (one[k] / v), 3)
+    except (OSError, ValueError):
+        sp = None
+    out["speedup_vs_1gpu"] = sp
+    return out
 
 
 def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
@@ -387,6 +441,39 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
     import torch
     import torch.distributed as dist
     out = {}
+    # ---- C1 (BASELINE configs[0]): QR of a 512 x 512 random f64 matrix through the QR-trait mirror, GPU beside the CPU port ----
+    if rank == 0:
+        try:
+            import oracle as O
+            import linfa_linalg_b200 as L
+            n1 = 512
+            a0 = np.random.default_rng(0x1F2E3D4C).uniform(-1, 1, (n1, n1))
+            ref = a0.copy()
+            t0 = time.perf_counter(); dref = O.qr(ref); t_cpu = time.perf_counter() - t0     # qr.rs:32-44 on one core
+            eng.set_stream(None)
+            t_gpu = []
+            for _ in range(6):
+                a = a0.copy()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter(); dec = L.qr_into(a, eng=eng); t_gpu.append(time.perf_counter() - t0)
+            eng.set_stream(stream.cuda_stream)
+            c1_err = float(max(np.max(np.abs(a - ref)), np.max(np.abs(dec.diag - dref))))
+            d_a = torch.from_numpy(np.ascontiguousarray(a0.T)).to(dev)
+            d_w = torch.empty_like(d_a); d_d = torch.empty(n1, dtype=torch.float64, device=dev)
+
+            def c1_step():
+                d_w.copy_(d_a)
+                lib.lfb_qr_dev_f64(eng.h, C.c_void_p(d_w.data_ptr()), n1, n1, n1, C.c_void_p(d_d.data_ptr()))
+            ms_dev = timed(c1_step, 20, 3) / 20 if world == 1 else None
+            fl1 = 4.0 / 3.0 * n1 ** 3
+            t_best = min(t_gpu[1:])
+            out["c1_qr512_f64"] = {"workload": "QR 512x512 f64 via qr_into (C1, qr.rs:29-63)", "gpu_e2e_ms": t_best * 1e3,
+                                   "gpu_e2e_gflops": fl1 / t_best / 1e9, "gpu_device_ms": ms_dev,
+                                   "cpu_port_ms": t_cpu * 1e3, "cpu_port_gflops": fl1 / t_cpu / 1e9, "cpu_cores": 1,
+                                   "e2e_speedup_vs_cpu_port": t_cpu / t_best,
+                                   "check": {"max_abs_err_vs_oracle": c1_err}, "check_ok": c1_err <= 16 * n1 * 2.3e-16 * float(np.linalg.norm(a0))}
+        except Exception as ex:
+            out["c1_qr512_f64"] = {"error": str(ex)[:200]}
     # ---- C2': blocked Householder QR, n = 16384 f64 ----
     try:
         n = args.n
@@ -402,8 +489,37 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
                 raise RuntimeError(f"lfb_qr_dev_f64 status {st}")
         ms = timed(qr_step, 2, 1)
         fl = 4.0 / 3.0 * n ** 3
+        # correctness of the timed result (size-independent): the leading k x k block of R^T R equals that of A^T A
+        # (R upper triangular), diag(R) = |diag| and every reflector has unit norm (householder.rs:23)
+        k = min(2048, n)
+        Rk = torch.triu(A[:k, :k].t(), 1) + torch.diag(diag[:k].abs())
+        AtA = A0[:k, :] @ A0[:k, :].t()
+        rtr_err = float((Rk.t() @ Rk - AtA).norm() / AtA.norm())
+        vnorm = torch.triu(A[:k, :]).pow(2).sum(dim=1).sqrt()          # tensor row c = column c of the factor; triu keeps rows >= c
+        vn_err = float((vnorm - 1).abs().max())
+        ok = rtr_err <= 8 * n * 2.3e-16 and vn_err <= 1e-13 and bool(torch.isfinite(diag).all())
         out["qr_f64"] = {"workload": f"QR {n}x{n} f64 (C2')", "gflops": world * fl * 2 / (ms * 1e-3) / 1e9, "ms_per_step": ms / 2,
-                         "frac_of_nominal_fp64": fl * 2 / (ms * 1e-3) / 1e12 / FP64_NOMINAL_TFLOPS}
+                         "frac_of_nominal_fp64": fl * 2 / (ms * 1e-3) / 1e12 / FP64_NOMINAL_TFLOPS,
+                         "check": {"RtR_vs_AtA_block2048": rtr_err, "reflector_norm_err": vn_err}, "check_ok": ok}
+        # e2e through the host API (lfb_qr_f64, row-major pinned view, in place): upload, transpose, factor, download
+        if not args.no_e2e and world == 1:
+            hq = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
+            hd = np.zeros(n)
+            hq.copy_(A0)
+            eng.set_stream(None)
+            t_q = []
+            for it in range(2):
+                hq.copy_(A0)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                st = lib.lfb_qr_f64(eng.h, C.c_void_p(hq.data_ptr()), n, n, n, 1, C.c_void_p(hd.ctypes.data))
+                t_q.append(time.perf_counter() - t0)
+                if st != 0:
+                    raise RuntimeError(f"lfb_qr_f64 status {st}")
+            eng.set_stream(stream.cuda_stream)
+            out["qr_f64"]["e2e"] = {"gflops": fl / t_q[-1] / 1e9, "ms": t_q[-1] * 1e3, "h2d_bytes": n * n * 8, "d2h_bytes": n * n * 8 + n * 8,
+                                    "api": "lfb_qr_f64 (host view, pinned, in place)"}
+            del hq
         del A0, A
         torch.cuda.empty_cache()
     except Exception as ex:  # keep the headline line alive
@@ -430,9 +546,43 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         ms_k = max(ms_all - ms_copy, 1e-6)
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
         gbs = per * 8320 * 20 / (ms_k * 1e-3) / 1e9
+        # correctness of the timed result: 4096 sampled matrices of this rank's shard against the CPU oracle (qr.rs:32-44
+        # per matrix), elementwise + the sign bits of diag (householder.rs:50)
+        import oracle as O
+        idx = torch.randperm(per, device=dev, generator=gen)[:4096].sort().values
+        ref = M0[idx].cpu().numpy().copy()
+        dref = O.qr_batched(ref)
+        got, dgot = M[idx].cpu().numpy(), d[idx].cpu().numpy()
+        berr = float(max(np.max(np.abs(got - ref)), np.max(np.abs(dgot - dref))))
+        sign_ok = bool(np.array_equal(np.signbit(dgot), np.signbit(dref)))
+        ok_t = torch.tensor([1 if (berr <= 16 * 32 * 1.2e-7 * 32 ** 0.5 and sign_ok) else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
         out["batched_qr_f32"] = {"workload": f"{B} x (32x32) f32, {per} per GPU (C3)", "matrices_per_s": B * 20 / (ms_k * 1e-3),
                                  "ms_per_step": ms_k / 20, "kernel_GBps_per_gpu": gbs, "hbm_peak_GBps": hbm,
-                                 "frac_of_hbm": gbs / hbm, "scaling": "strong", "note": "restore copy timed separately and subtracted"}
+                                 "frac_of_hbm": gbs / hbm, "scaling": "strong", "note": "restore copy timed separately and subtracted",
+                                 "check": {"sampled": 4096, "max_abs_err_vs_oracle": berr, "diag_sign_bits_equal": sign_ok},
+                                 "check_ok": bool(ok_t.item())}
+        # batched Cholesky on the same shard (north star: "batched small-matrix QR/Cholesky is split by batch")
+        M0.copy_(torch.bmm(M0, M0.transpose(1, 2)))
+        M0.diagonal(dim1=1, dim2=2).add_(32.0)
+        fl_t = torch.empty(per, dtype=torch.int32, device=dev)
+
+        def bc_step():
+            M.copy_(M0)
+            st = lib.lfb_cholesky_batched_dev_f32(eng.h, C.c_void_p(M.data_ptr()), per, 32, 0, C.c_void_p(fl_t.data_ptr()))
+            if st != 0:
+                raise RuntimeError(f"lfb_cholesky_batched_dev_f32 status {st}")
+        ms_c = max(timed(bc_step, 20, 5) - ms_copy, 1e-6)
+        refc = M0[idx].cpu().numpy().copy()
+        fm, _ = O.cholesky_batched(refc, False)
+        gotc = M[idx].cpu().numpy()
+        cerr = float(np.max(np.abs(np.tril(gotc) - np.tril(refc))))
+        okc = fm == -1 and int(fl_t.max().item()) < 0 and cerr <= 16 * 32 * 1.2e-7 * 32 ** 0.5 * float(M0.abs().max())
+        gbc = per * (4096 + 4096) * 20 / (ms_c * 1e-3) / 1e9
+        out["batched_chol_f32"] = {"workload": f"{B} x (32x32) f32 SPD, {per} per GPU", "matrices_per_s": B * 20 / (ms_c * 1e-3),
+                                   "ms_per_step": ms_c / 20, "kernel_GBps_per_gpu": gbc, "frac_of_hbm": gbc / hbm, "scaling": "strong",
+                                   "check": {"sampled": 4096, "max_abs_err_vs_oracle": cerr}, "check_ok": bool(okc)}
         del M0, M
         torch.cuda.empty_cache()
     except Exception as ex:
@@ -449,14 +599,29 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         local_r = D.gpu_local_r(eng, Tw, rows, cols)
         final_r = D.gpu_final_r(eng, cols)
 
+        rres = {}
+
         def tsqr_step():
             Tw.copy_(T0)
             # local R per rank -> one NCCL all_gather of the 256x256 factors -> R of the stack (replicated)
-            D.tsqr_r(local_r, final_r, cols)
+            rres["r"] = D.tsqr_r(local_r, final_r, cols)
         ms = timed(tsqr_step, 2, 2)
         fl = 2.0 * rows_total * cols * cols - 2.0 / 3.0 * cols ** 3
+        # correctness of the timed result: R^T R = A^T A (all-reduced Gram matrix of the row shards), ||R||_F = ||A||_F,
+        # diag(R) >= 0 and strict lower triangle exactly zero (qr.rs:93-96)
+        Rm = rres["r"].t()                                    # math R (the tensor is its column-major storage)
+        gram = T0 @ T0.t()
+        if world > 1:
+            dist.all_reduce(gram)
+        g_err = float((Rm.t() @ Rm - gram).norm() / gram.norm())
+        nrm_err = float(abs(Rm.norm() / gram.diagonal().sum().sqrt() - 1))
+        struct_ok = bool((Rm.diagonal() >= 0).all()) and bool((torch.tril(Rm, -1) == 0).all())
         out["tsqr_f64"] = {"workload": f"TSQR {rows_total}x{cols} f64, {rows} rows per GPU (C4)", "gflops": fl * 2 / (ms * 1e-3) / 1e9,
-                           "ms_per_step": ms / 2, "scaling": "strong", "exchange": "NCCL all_gather of 256x256 R per rank" if world > 1 else "none"}
+                           "ms_per_step": ms / 2, "scaling": "strong", "exchange": "NCCL all_gather of 256x256 R per rank" if world > 1 else "none",
+                           "check": {"RtR_vs_AtA": g_err, "normR_over_normA_minus_1": nrm_err, "diag_nonneg_lower_zero": struct_ok},
+                           "check_ok": g_err <= 1e-12 and nrm_err <= 1e-13 and struct_ok}
+        del T0, Tw, gram
+        torch.cuda.empty_cache()
     except Exception as ex:
         out["tsqr_f64"] = {"error": str(ex)[:200]}
     # ---- C5a / C5b: phase 1 of eigh (tridiagonalisation + Q) and of SVD (bidiagonalisation); replicas ----
@@ -486,7 +651,12 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         symv_bytes = 4.0 * n ** 3 / 3.0       # ONE read of the lower triangle of the trailing matrix per column
         us_symv = C.c_double(0)
         lib.lfb_microbench_kernel(eng.h, b"trd_symv", n, 50, C.byref(us_symv))       # the SYMV alone, back to back, at the full size
+        # orthogonal-similarity invariants of the timed result: trace(T) = trace(A), ||T||_F = ||A||_F
+        td = Sw.diagonal()
+        tr_err = float(abs(td.sum() - S0.diagonal().sum()) / S0.norm())
+        fro_err = float(abs(torch.sqrt((td * td).sum() + 2 * (off[:n - 1] ** 2).sum()) / S0.norm() - 1))
         out["tridiag_f64"] = {"workload": f"sym_tridiagonal {n}x{n} f64 (C5a phase 1)", "ms": ms_t, "gflops": fl / (ms_t * 1e-3) / 1e9,
+                              "check": {"trace_err": tr_err, "fro_norm_err": fro_err}, "check_ok": tr_err <= 1e-12 and fro_err <= 1e-12,
                               "symv_GBps_lower_bound": symv_bytes / (ms_t * 1e-3) / 1e9, "hbm_peak_GBps": hbm,
                               "frac_of_hbm_lower_bound": symv_bytes / (ms_t * 1e-3) / 1e9 / hbm,
                               "symv_kernel_at_n": {"us": us_symv.value, "GBps": 4.0 * n * n / max(us_symv.value, 1e-9) / 1e3,
@@ -506,7 +676,7 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         Qt = Q.t()                                  # torch sees the column-major Q transposed
         resid = float((S0 @ Qt - Qt * torch.from_numpy(vals).to(dev)[None, :]).norm() / S0.norm())
         out["eigh_f64"] = {"workload": f"eigh {n}x{n} f64, eigenvalues + eigenvectors (C5a end to end)", "ms": t_eigh * 1e3,
-                           "relative_residual": resid, "timing": "wall clock around one call (host recurrence inside)"}
+                           "relative_residual": resid, "check_ok": resid <= 64 * n * 2.3e-16, "timing": "wall clock around one call (host recurrence inside)"}
         del S0, Sw, Q, Qt
         torch.cuda.empty_cache()
         m2, n2 = 16384, 4096
@@ -527,7 +697,9 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         lib.lfb_microbench_kernel(eng.h, b"bd_gemv_n", n2, 50, C.byref(us_n))     # the GEMVs alone at the full 16384 x 4096 size
         lib.lfb_microbench_kernel(eng.h, b"bd_gemv_t", n2, 50, C.byref(us_t))
         full = 8.0 * m2 * n2
+        bfro = float(abs(torch.sqrt((dd * dd).sum() + (ee[:n2 - 1] ** 2).sum()) / B0.norm() - 1))      # ||B||_F = ||A||_F
         out["bidiag_f64"] = {"workload": f"bidiagonal {m2}x{n2} f64 (C5b phase 1, blocked: deferred rank-1 updates)", "ms": ms_b,
+                             "check": {"fro_norm_err": bfro}, "check_ok": bfro <= 1e-12,
                              "gflops": flb / (ms_b * 1e-3) / 1e9, "gemv_GBps_lower_bound": gemv_bytes / (ms_b * 1e-3) / 1e9,
                              "hbm_peak_GBps": hbm, "frac_of_hbm_lower_bound": gemv_bytes / (ms_b * 1e-3) / 1e9 / hbm,
                              "gemv_kernels_at_full_size": {"n_us": us_n.value, "n_GBps": full / max(us_n.value, 1e-9) / 1e3,
@@ -549,7 +721,7 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         rec = (Vd.t() * torch.from_numpy(sv).to(dev)[None, :]) @ Ud                  # (U S Vt)^T = V S U^T
         resid = float((rec - B0).norm() / B0.norm())
         out["svd_f64"] = {"workload": f"svd {m2}x{n2} f64 with U and Vt (C5b end to end)", "ms": t_svd * 1e3,
-                          "relative_residual": resid, "timing": "wall clock around one call (host recurrence inside)"}
+                          "relative_residual": resid, "check_ok": resid <= 64 * m2 * 2.3e-16, "timing": "wall clock around one call (host recurrence inside)"}
         del B0, Bw, Ud, Vd, rec
         torch.cuda.empty_cache()
     except Exception as ex:
@@ -586,6 +758,8 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
                               "reflector_norm_err": float((ss.sqrt() - 1).abs().max()),
                               "diag_vs_r_err": float((res["diag"].abs() - torch.diagonal(r)).abs().max()),
                               "normR_over_normA_minus_1": float(r.norm() / a2.sqrt()[0] - 1),
+                              "check_ok": float((ss.sqrt() - 1).abs().max()) <= 1e-12 and float((res["diag"].abs() - torch.diagonal(r)).abs().max()) <= 1e-9
+                              and abs(float(r.norm() / a2.sqrt()[0] - 1)) <= 1e-12,
                               "exchange": "all_gather of R + broadcast of U' and diag" if world > 1 else "none"}
         del T0, Tw, low
         torch.cuda.empty_cache()

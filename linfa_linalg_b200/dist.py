@@ -52,12 +52,22 @@ def tsqr_r(local_r: Callable, final_r: Callable, n: int, group=None):
 
 
 # ---- GPU callables over the C ABI ---------------------------------------------------------------------
+def _bind_to_torch_stream(eng, device):
+    """torch.distributed collectives (and torch's allocator) order against torch's CURRENT stream only, while an Engine
+    runs on its own non-blocking stream by default.  Every GPU callable below therefore puts the engine on torch's
+    current stream of `device` before it launches, so that kernels, `torch.empty` buffers and NCCL calls are all ordered
+    on one stream (the switch drains the stream the engine was on before; a no-op when already bound)."""
+    import torch
+    eng.set_stream(torch.cuda.current_stream(device).cuda_stream)
+
+
 def gpu_local_r(eng, block_cm, rows: int, n: int):
     """block_cm: torch f64 tensor of shape (n, rows) (row-major) == column-major rows x n block. Overwritten."""
     import torch
     r = torch.empty((n, n), dtype=torch.float64, device=block_cm.device)
 
     def run():
+        _bind_to_torch_stream(eng, block_cm.device)
         st = eng.lib.lfb_tsqr_local_r_dev_f64(eng.h, C.c_void_p(block_cm.data_ptr()), rows, n, rows, C.c_void_p(r.data_ptr()), n)
         if st != 0:
             raise RuntimeError(f"lfb_tsqr_local_r_dev_f64 status {st}: {eng.lib.lfb_last_error(eng.h)}")
@@ -70,6 +80,7 @@ def gpu_final_r(eng, n: int):
 
     def run(stack):
         rows = stack.shape[1]
+        _bind_to_torch_stream(eng, stack.device)
         r = torch.empty((n, n), dtype=torch.float64, device=stack.device)
         st = eng.lib.lfb_tsqr_local_r_dev_f64(eng.h, C.c_void_p(stack.data_ptr()), rows, n, rows, C.c_void_p(r.data_ptr()), n)
         if st != 0:
@@ -89,7 +100,9 @@ def tsqr_qr(block, ops, n: int, group=None):
         apply_q(x, qs)                x <- x * qs          (qs: contiguous (n, n) tensor, column-major n x n)
         reconstruct_top(x, r, u, diag)   first n rows of x -> top block of the compact factor; u <- U', diag
         reconstruct_rows(x, row0, u)  rows row0.. of x <- (those rows) U'^-1
-    Every rank must own at least n rows (checked collectively: ValueError on all ranks otherwise)."""
+    Every rank must own at least n rows (checked collectively: ValueError on all ranks otherwise).
+    Stream contract: the collectives run on torch's current stream; `GpuTsqrOps` binds the engine to that stream on every
+    call, so no extra synchronisation is needed between the engine's kernels and NCCL."""
     import torch
     import torch.distributed as dist
     on = dist.is_available() and dist.is_initialized()
@@ -129,6 +142,8 @@ class GpuTsqrOps:
         self.eng = eng
 
     def _call(self, name, *args):
+        import torch
+        _bind_to_torch_stream(self.eng, torch.device("cuda", self.eng.device))
         st = getattr(self.eng.lib, name)(self.eng.h, *args)
         if st != 0:
             raise RuntimeError(f"{name} status {st}: {self.eng.lib.lfb_last_error(self.eng.h)}")
