@@ -369,6 +369,16 @@ def main():
     extras = {}
     if not args.no_extras:
         extras = run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier)
+        # the same sharded paths through the single-process multi-device C ABI (csrc/multi.cu): rank 0 drives all `world`
+        # devices of the box by itself while the other ranks wait at the barrier with their caches released
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            try:
+                extras["cabi_multi"] = run_multi_cabi(world)
+            except Exception as ex:
+                extras["cabi_multi"] = {"error": str(ex)[:300]}
+        barrier()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -402,6 +412,96 @@ def main():
         dist.destroy_process_group()
 
 
+def run_multi_cabi(world):
+    """C3 and C4 through `lfb_*_multi_dev_*`: ONE process, `world` devices, NCCL inside the library.  Device-timed
+    (start/stop events on every device's stream, max over devices); restore copies are outside the timed region."""
+    import numpy as np
+    import torch
+    from linfa_linalg_b200.dist import MultiEngine, shard_range
+    out = {"devices": world}
+    m = MultiEngine(n_devices=world)
+    out["nccl_ranks"] = m.nccl_ranks
+    devs = [torch.device("cuda", i) for i in range(world)]
+
+    def sync_all():
+        for d in devs:
+            torch.cuda.synchronize(d)
+
+    def timed_multi(restore, call, steps, warmup):
+        tot = 0.0
+        for it in range(warmup + steps):
+            restore()
+            sync_all()
+            m.time_begin()
+            call()
+            ms = m.time_end()
+            if it >= warmup:
+                tot += ms
+        return tot / steps
+    # ---- C4: 4,194,304 x 256 f64, rows sharded ----
+    rows_total, cols = 4194304, 256
+    spans = [shard_range(rows_total, world, i) for i in range(world)]
+    T0, Tw, Rs, Ds = [], [], [], []
+    for i, d in enumerate(devs):
+        g = torch.Generator(device=d).manual_seed(0x1F2E3D4C + 4 + i)
+        T0.append(torch.rand((cols, spans[i][1] - spans[i][0]), dtype=torch.float64, device=d, generator=g).mul_(2).sub_(1))
+        Tw.append(torch.empty_like(T0[-1]))
+        Rs.append(torch.zeros((cols, cols), dtype=torch.float64, device=d))
+        Ds.append(torch.zeros(cols, dtype=torch.float64, device=d))
+
+    def restore():
+        for a, b in zip(Tw, T0):
+            a.copy_(b)
+    ms_r = timed_multi(restore, lambda: m.tsqr_r_dev(Tw, Rs), 2, 1)
+    gram = sum((t @ t.t()).to(devs[0]) for t in T0)
+    Rm = Rs[0].t()
+    out["tsqr_r_ms"] = ms_r
+    out["tsqr_r_check"] = float((Rm.t() @ Rm - gram).norm() / gram.norm())
+    ms_q = timed_multi(restore, lambda: m.qr_tsqr_dev(Tw, Ds, Rs), 2, 1)
+    Rm = Rs[0].t()
+    vn = 0.0
+    for i, t in enumerate(Tw):
+        low = t.clone()
+        if i == 0:
+            low[:, :cols] = torch.triu(low[:, :cols])
+        ss = (low * low).sum(dim=1).to(devs[0])
+        vn = ss if i == 0 else vn + ss
+    out["tsqr_qr_ms"] = ms_q
+    out["tsqr_qr_check"] = {"RtR_vs_AtA": float((Rm.t() @ Rm - gram).norm() / gram.norm()),
+                            "reflector_norm_err": float((vn.sqrt() - 1).abs().max()),
+                            "diag_vs_r_err": float((Ds[0].abs() - torch.diagonal(Rs[0])).abs().max()),
+                            "diag_replicated": all(bool(torch.equal(Ds[0].cpu(), x.cpu())) for x in Ds)}
+    del T0, Tw, gram, low
+    for d in devs:
+        with torch.cuda.device(d):
+            torch.cuda.empty_cache()
+    # ---- C3: 262144 x (32 x 32) f32, batch sharded ----
+    B = 262144
+    bs = [shard_range(B, world, i) for i in range(world)]
+    M0, M, Dg = [], [], []
+    for i, d in enumerate(devs):
+        g = torch.Generator(device=d).manual_seed(0x1F2E3D4C + 3 + i)
+        M0.append(torch.rand((bs[i][1] - bs[i][0], 32, 32), dtype=torch.float32, device=d, generator=g).mul_(2).sub_(1))
+        M.append(torch.empty_like(M0[-1]))
+        Dg.append(torch.zeros((bs[i][1] - bs[i][0], 32), dtype=torch.float32, device=d))
+
+    def restore_b():
+        for a, b in zip(M, M0):
+            a.copy_(b)
+    ms_b = timed_multi(restore_b, lambda: m.qr_batched_dev_f32(M, Dg), 10, 3)
+    import oracle as O
+    ref = M0[-1][:1024].cpu().numpy().copy()
+    dref = O.qr_batched(ref)
+    out["batched_ms"] = ms_b
+    out["batched_mps"] = B / (ms_b * 1e-3)
+    out["batched_check"] = float(max(np.max(np.abs(M[-1][:1024].cpu().numpy() - ref)), np.max(np.abs(Dg[-1][:1024].cpu().numpy() - dref))))
+    out["check_ok"] = (out["tsqr_r_check"] <= 1e-12 and out["tsqr_qr_check"]["RtR_vs_AtA"] <= 1e-12 and out["tsqr_qr_check"]["reflector_norm_err"] <= 1e-12
+                       and out["tsqr_qr_check"]["diag_replicated"] and out["batched_check"] <= 16 * 32 * 1.2e-7 * 32 ** 0.5)
+    out["launches"] = m.launch_count
+    m.close()
+    return out
+
+
 N1_FILE = os.path.join(ROOT, ".bench_n1.json")
 
 
@@ -410,10 +510,14 @@ def sharded_summary(extras, world):
         v = extras.get(key, {})
         return v.get(field) if isinstance(v, dict) else None
     cur = {"batched_mps": g("batched_qr_f32", "matrices_per_s"), "batched_chol_mps": g("batched_chol_f32", "matrices_per_s"),
-           "tsqr_r_ms": g("tsqr_f64", "ms_per_step"), "tsqr_qr_ms": g("tsqr_qr_f64", "ms_per_step")}
+           "tsqr_r_ms": g("tsqr_f64", "ms_per_step"), "tsqr_qr_ms": g("tsqr_qr_f64", "ms_per_step"),
+           # the single-process C-ABI route (lfb_*_multi_dev_*), same workloads
+           "cabi_batched_mps": g("cabi_multi", "batched_mps"), "cabi_tsqr_r_ms": g("cabi_multi", "tsqr_r_ms"),
+           "cabi_tsqr_qr_ms": g("cabi_multi", "tsqr_qr_ms")}
     out = {"n": world}
     out.update({k: (round(v, 4) if isinstance(v, float) and v < 1e4 else (float(f"{v:.4g}") if v is not None else None)) for k, v in cur.items()})
-    out["checks_ok"] = all(bool(g(k, "check_ok")) for k in ("batched_qr_f32", "tsqr_f64", "tsqr_qr_f64") if k in extras)
+    out["checks_ok"] = all(bool(g(k, "check_ok")) for k in ("batched_qr_f32", "batched_chol_f32", "tsqr_f64", "tsqr_qr_f64", "cabi_multi") if k in extras)
+    out["cabi_nccl_ranks"] = g("cabi_multi", "nccl_ranks")
     if world == 1:
         try:
             json.dump(cur, open(N1_FILE, "w"))
@@ -549,6 +653,7 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         # correctness of the timed result: 4096 sampled matrices of this rank's shard against the CPU oracle (qr.rs:32-44
         # per matrix), elementwise + the sign bits of diag (householder.rs:50)
         import oracle as O
+        bq_step()                                   # the last timed call was the restore copy: factor once more for the check
         idx = torch.randperm(per, device=dev, generator=gen)[:4096].sort().values
         ref = M0[idx].cpu().numpy().copy()
         dref = O.qr_batched(ref)

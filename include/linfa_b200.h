@@ -33,6 +33,7 @@ extern "C" {
 #endif
 
 typedef struct lfb_handle lfb_handle;
+typedef struct lfb_multi lfb_multi;   /* several devices of one box behind one handle (see the end of this file) */
 
 typedef enum lfb_status {
     LFB_OK = 0,
@@ -45,7 +46,8 @@ typedef enum lfb_status {
     LFB_INVALID_ARGUMENT = 7,
     LFB_UNSUPPORTED = 8,
     LFB_ERR_CUDA = 100,
-    LFB_ERR_ALLOC = 101
+    LFB_ERR_ALLOC = 101,
+    LFB_ERR_NCCL = 102             /* libnccl.so.2 missing, or a communicator / collective failed */
 } lfb_status;
 
 /* triangular.rs:10-13  enum UPLO */
@@ -284,6 +286,55 @@ int lfb_microbench_fp64(lfb_handle *h, int kind, double *gflops);
  * problem: "trd_symv" (lower-triangle SYMV of the tridiagonalisation), "trd_head" (its cluster kernel),
  * "bd_gemv_n" / "bd_gemv_t" (streaming GEMVs of the bidiagonalisation on a 4n x n matrix). */
 int lfb_microbench_kernel(lfb_handle *h, const char *name, int64_t n, int reps, double *us_per_launch);
+
+/* ==== one box, several GPUs: the two paths that shard naturally behind the same boundary ===================
+ * ONE process: lfb_create_multi makes one engine handle and one host worker thread per listed device and, for more than one
+ * device, an NCCL communicator over them (ncclCommInitAll; libnccl.so.2 is resolved at run time -- the copy the host process
+ * already has mapped, if any -- so the library has no link-time NCCL dependency; LFB_ERR_NCCL if it cannot be had).
+ * These are the entry points the Rust shim binds for `QRInto::qr_into` (qr.rs:29-45) on a tall-skinny matrix and for loops
+ * over many small matrices; a Rust caller has one process and cannot use bench.py's one-process-per-GPU launch.
+ * devices == NULL means devices 0 .. n_devices-1.  Handles are used by one call at a time, like lfb_handle. */
+int lfb_create_multi(lfb_multi **out, const int *devices, int n_devices);
+int lfb_destroy_multi(lfb_multi *m);
+const char *lfb_multi_last_error(lfb_multi *m);
+int lfb_multi_device_count(lfb_multi *m);
+int lfb_multi_nccl_ranks(lfb_multi *m);     /* size of the NCCL communicator (0 with a single device: no collective exists) */
+int lfb_multi_nccl_version(lfb_multi *m);   /* ncclGetVersion code of the library in use, 0 if none */
+lfb_handle *lfb_multi_handle(lfb_multi *m, int i);            /* device i's engine handle (options, launch counts) */
+int lfb_multi_set_option(lfb_multi *m, const char *key, int64_t value);   /* lfb_set_option on every device's handle */
+int64_t lfb_multi_launch_count(lfb_multi *m);                 /* kernels + collectives launched on all devices so far */
+int lfb_multi_synchronize(lfb_multi *m);
+/* Device-side timing of whatever is enqueued between the two calls: start/stop events on every device's stream, result =
+ * MAX over devices of the elapsed time (ms). */
+int lfb_multi_time_begin(lfb_multi *m);
+int lfb_multi_time_end(lfb_multi *m, double *max_ms);
+
+/* qr.rs:29-45 QRInto::qr_into on a tall-skinny host view, ROWS SHARDED over the devices (device i owns the contiguous row
+ * block [i*rows/G ...), first rows%G blocks one row longer): same contract and results as lfb_qr_* / lfb_qr_tsqr_* -- the
+ * reference's compact factor written back in place, diag = signed pivots.  Per device: explicit-Q TSQR of its rows; ONE
+ * ncclAllGather of the n x n R factors; QR of the stacked R (replicated); Householder reconstruction of the top block on
+ * device 0; ONE ncclBroadcast of U' and diag; one right-hand TRSM per device.  No row data ever crosses NVLink.
+ * A matrix with fewer than G*cols rows is factored on device 0 alone. */
+int lfb_qr_tsqr_multi_f64(lfb_multi *m, double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double *diag);
+int lfb_qr_tsqr_multi_f32(lfb_multi *m, float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, float *diag);
+/* R only (qr.rs:91-98 into_r of the same factorisation; a is read, not written): r is cols x cols, upper, diag >= 0. */
+int lfb_tsqr_r_multi_f64(lfb_multi *m, const double *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, double *r, int64_t r_rs, int64_t r_cs);
+int lfb_tsqr_r_multi_f32(lfb_multi *m, const float *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, float *r, int64_t r_rs, int64_t r_cs);
+/* Device-resident variants: d_blocks[i] is device i's rows[i] x cols column-major block (leading dimension ld[i], rows[i] >=
+ * cols), overwritten with its rows of the compact factor (resp. destroyed for the R-only call); d_diag[i] (cols values) and
+ * d_r[i] (cols x cols column-major, ld = cols) receive the replicated results on every device whose pointer is not NULL
+ * (either array may itself be NULL).  Asynchronous on the handles' streams: finish with lfb_multi_synchronize. */
+int lfb_qr_tsqr_multi_dev_f64(lfb_multi *m, double *const *d_blocks, const int64_t *rows, int64_t cols, const int64_t *ld,
+                              double *const *d_diag, double *const *d_r);
+int lfb_tsqr_r_multi_dev_f64(lfb_multi *m, double *const *d_blocks, const int64_t *rows, int64_t cols, const int64_t *ld, double *const *d_r);
+/* Batched small factorisations, BATCH SHARDED (same split rule), no collective: contracts of lfb_qr_batched_* and
+ * lfb_cholesky_batched_* (the first failing matrix is reported in batch order, whichever device met it). */
+int lfb_qr_batched_multi_f32(lfb_multi *m, float *a, int64_t batch, int64_t mm, int64_t n, float *diag);
+int lfb_qr_batched_multi_f64(lfb_multi *m, double *a, int64_t batch, int64_t mm, int64_t n, double *diag);
+int lfb_cholesky_batched_multi_f32(lfb_multi *m, float *a, int64_t batch, int64_t n, int clean, int64_t *fail_matrix, int64_t *fail_index);
+int lfb_cholesky_batched_multi_f64(lfb_multi *m, double *a, int64_t batch, int64_t n, int clean, int64_t *fail_matrix, int64_t *fail_index);
+/* d_a[i]: device i's [batch[i]][mm][n] packed shard, d_diag[i]: [batch[i]][n]; asynchronous on the handles' streams. */
+int lfb_qr_batched_multi_dev_f32(lfb_multi *m, float *const *d_a, const int64_t *batch, int64_t mm, int64_t n, float *const *d_diag);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "liblinfa_b200.so")
 
 # status codes (include/linfa_b200.h)
 OK, NOT_POSITIVE_DEFINITE, NOT_THIN, NOT_SQUARE, EMPTY_MATRIX, WRONG_ROWS, NON_INVERTIBLE, INVALID_ARGUMENT, UNSUPPORTED = range(9)
-ERR_CUDA, ERR_ALLOC = 100, 101
+ERR_CUDA, ERR_ALLOC, ERR_NCCL = 100, 101, 102
 UPPER, LOWER = 0, 1
 
 _i64, _int, _vp, _dbl, _flt = C.c_int64, C.c_int, C.c_void_p, C.c_double, C.c_float
@@ -81,7 +81,35 @@ SIGNATURES.update({
     "lfb_gemm_dev_f64": [_vp, _int, _int, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _dbl, _vp, _i64],
     "lfb_gemm_dev_f32": [_vp, _int, _int, _i64, _i64, _i64, _flt, _vp, _i64, _vp, _i64, _flt, _vp, _i64],
 })
-_RESTYPES = {"lfb_last_error": C.c_char_p, "lfb_version": C.c_char_p, "lfb_launch_count": _i64}
+_PP = C.POINTER(_vp)          # array of device pointers
+_PI = C.POINTER(_i64)         # array of int64
+SIGNATURES.update({
+    "lfb_create_multi": [C.POINTER(_vp), C.POINTER(_int), _int],
+    "lfb_destroy_multi": [_vp],
+    "lfb_multi_last_error": [_vp],
+    "lfb_multi_device_count": [_vp],
+    "lfb_multi_nccl_ranks": [_vp],
+    "lfb_multi_nccl_version": [_vp],
+    "lfb_multi_handle": [_vp, _int],
+    "lfb_multi_set_option": [_vp, C.c_char_p, _i64],
+    "lfb_multi_launch_count": [_vp],
+    "lfb_multi_synchronize": [_vp],
+    "lfb_multi_time_begin": [_vp],
+    "lfb_multi_time_end": [_vp, C.POINTER(_dbl)],
+    "lfb_qr_tsqr_multi_f64": [_vp] + _VIEW + [_vp],
+    "lfb_qr_tsqr_multi_f32": [_vp] + _VIEW + [_vp],
+    "lfb_tsqr_r_multi_f64": [_vp] + _VIEW + [_vp, _i64, _i64],
+    "lfb_tsqr_r_multi_f32": [_vp] + _VIEW + [_vp, _i64, _i64],
+    "lfb_qr_tsqr_multi_dev_f64": [_vp, _PP, _PI, _i64, _PI, _PP, _PP],
+    "lfb_tsqr_r_multi_dev_f64": [_vp, _PP, _PI, _i64, _PI, _PP],
+    "lfb_qr_batched_multi_f32": [_vp, _vp, _i64, _i64, _i64, _vp],
+    "lfb_qr_batched_multi_f64": [_vp, _vp, _i64, _i64, _i64, _vp],
+    "lfb_cholesky_batched_multi_f32": [_vp, _vp, _i64, _i64, _int, C.POINTER(_i64), C.POINTER(_i64)],
+    "lfb_cholesky_batched_multi_f64": [_vp, _vp, _i64, _i64, _int, C.POINTER(_i64), C.POINTER(_i64)],
+    "lfb_qr_batched_multi_dev_f32": [_vp, _PP, _PI, _i64, _i64, _PP],
+})
+_RESTYPES = {"lfb_last_error": C.c_char_p, "lfb_version": C.c_char_p, "lfb_launch_count": _i64,
+             "lfb_multi_last_error": C.c_char_p, "lfb_multi_handle": _vp, "lfb_multi_launch_count": _i64}
 
 _lib = None
 

@@ -10,8 +10,8 @@ One process per GPU (torch.distributed, NCCL over NVLink on the GPU box, gloo in
 * tall-skinny QR delivered as the reference's QRDecomp (`tsqr_qr`): the same row blocks; every rank
   keeps its explicit Q_r, the all-gathered R factors are reduced (replicated) to (Qs, R), Q_r <- Q_r Qs[r], the rank
   that owns the first n rows runs the Householder reconstruction of the top block (LU of Q - S) and broadcasts U' and
-  diag (n*n + n values), and every rank turns its rows into reflector rows with one right-hand TRSM.  Two collectives
-  in all, both O(n^2) bytes.
+  diag (n*n + n values, one buffer), and every rank turns its rows into reflector rows with one right-hand TRSM.  Two
+  collectives in all, both O(n^2) bytes.
 
 Everything here is host-side plumbing; the arithmetic is behind the callables (`local_r`, `final_r`)
 so that the same code path is exercised by the gloo tests with CPU stand-ins.
@@ -123,14 +123,13 @@ def tsqr_qr(block, ops, n: int, group=None):
         stack = stack_r_factors(r_all, world, n)
         r = ops.explicit_q(stack)                                   # stack <- Qs, replicated
         ops.apply_q(block, stack[:, rank * n:(rank + 1) * n].contiguous())
-    u = torch.empty((n, n), dtype=block.dtype, device=block.device)
-    diag = torch.empty((n,), dtype=block.dtype, device=block.device)
+    ud = torch.empty((n + 1, n), dtype=block.dtype, device=block.device)     # U' and diag share one buffer: ONE broadcast
+    u, diag = ud[:n], ud[n]
     if rank == 0:
         ops.reconstruct_top(block, r, u, diag)
     if world > 1:
         src = dist.get_global_rank(group, 0) if group is not None else 0
-        dist.broadcast(u, src=src, group=group)
-        dist.broadcast(diag, src=src, group=group)
+        dist.broadcast(ud, src=src, group=group)
     ops.reconstruct_rows(block, n if rank == 0 else 0, u)
     return diag, r
 
@@ -170,3 +169,138 @@ class GpuTsqrOps:
             return
         self._call("lfb_hh_reconstruct_rows_dev_f64", C.c_void_p(x.data_ptr() + row0 * x.element_size()), rows - row0, n, rows,
                    C.c_void_p(u.data_ptr()), n)
+
+
+# ---- single-process multi-GPU over the C ABI (csrc/multi.cu) ------------------------------------------------
+class MultiEngine:
+    """One `lfb_multi` handle: several devices of one box driven from ONE process (one host thread + one engine handle
+    per device inside the library, ncclCommInitAll for the R-factor exchange).  This is the launch mode a Rust caller of
+    the shim has; the torch.distributed functions above are the one-process-per-GPU mode of bench.py and use the same
+    split (`shard_range`).  The methods mirror linfa_linalg_b200's single-device functions."""
+
+    def __init__(self, devices=None, n_devices=None):
+        from . import _ffi
+        self.lib = _ffi.load()
+        if devices is None:
+            if n_devices is None:
+                raise ValueError("give a device list or n_devices")
+            devices = list(range(n_devices))
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        hp = C.c_void_p()
+        st = self.lib.lfb_create_multi(C.byref(hp), arr, len(self.devices))
+        if st != 0:
+            raise RuntimeError(f"lfb_create_multi({self.devices}) failed with status {st} (100 = CUDA, 102 = NCCL; no CPU fallback)")
+        self.h = hp
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lfb_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != 0:
+            raise RuntimeError(f"liblinfa_b200 (multi) status {st}: {(self.lib.lfb_multi_last_error(self.h) or b'').decode()}")
+
+    @property
+    def nccl_ranks(self) -> int:
+        return int(self.lib.lfb_multi_nccl_ranks(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.lfb_multi_launch_count(self.h))
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.lfb_multi_set_option(self.h, key.encode(), int(value)))
+
+    def synchronize(self):
+        self._check(self.lib.lfb_multi_synchronize(self.h))
+
+    @staticmethod
+    def _sfx(a):
+        import numpy as np
+        if a.dtype == np.float64:
+            return "_f64"
+        if a.dtype == np.float32:
+            return "_f32"
+        raise TypeError(f"A: NdFloat means f32 or f64, got {a.dtype}")
+
+    # -- host views (numpy arrays of any strides), results in place like the `*_into` trait methods --
+    def qr_tsqr_into(self, a):
+        """qr.rs:29-45 on a tall-skinny `a`, rows sharded over the devices: `a` becomes the reference's compact factor;
+        returns the signed pivots `diag`."""
+        import numpy as np
+        rows, cols = a.shape
+        diag = np.zeros(cols, dtype=a.dtype)
+        it = a.itemsize
+        st = getattr(self.lib, "lfb_qr_tsqr_multi" + self._sfx(a))(self.h, C.c_void_p(a.ctypes.data), rows, cols, a.strides[0] // it,
+                                                                   a.strides[1] // it, C.c_void_p(diag.ctypes.data))
+        self._check(st)
+        return diag
+
+    def tsqr_r(self, a):
+        """R (cols x cols, upper, diag >= 0; qr.rs:91-98) of the row-sharded `a`; `a` is not modified."""
+        import numpy as np
+        rows, cols = a.shape
+        r = np.zeros((cols, cols), dtype=a.dtype)
+        it = a.itemsize
+        st = getattr(self.lib, "lfb_tsqr_r_multi" + self._sfx(a))(self.h, C.c_void_p(a.ctypes.data), rows, cols, a.strides[0] // it,
+                                                                  a.strides[1] // it, C.c_void_p(r.ctypes.data), cols, 1)
+        self._check(st)
+        return r
+
+    def qr_batched(self, a):
+        """qr.rs:32-44 over a C-contiguous [batch][m][n] array, batch split over the devices; returns diag [batch][n]."""
+        import numpy as np
+        assert a.ndim == 3 and a.flags.c_contiguous
+        batch, m, n = a.shape
+        diag = np.zeros((batch, n), dtype=a.dtype)
+        st = getattr(self.lib, "lfb_qr_batched_multi" + self._sfx(a))(self.h, C.c_void_p(a.ctypes.data), batch, m, n, C.c_void_p(diag.ctypes.data))
+        self._check(st)
+        return diag
+
+    def cholesky_batched(self, a, clean: bool = True):
+        """cholesky.rs:51-83 over a C-contiguous [batch][n][n] array, batch split over the devices.  Returns
+        (fail_matrix, fail_index): (-1, -1) on success, else the first failing matrix in batch order and its row."""
+        assert a.ndim == 3 and a.flags.c_contiguous and a.shape[1] == a.shape[2]
+        fm, fi = C.c_int64(-1), C.c_int64(-1)
+        st = getattr(self.lib, "lfb_cholesky_batched_multi" + self._sfx(a))(self.h, C.c_void_p(a.ctypes.data), a.shape[0], a.shape[1],
+                                                                            int(clean), C.byref(fm), C.byref(fi))
+        if st == 1:
+            return fm.value, fi.value
+        self._check(st)
+        return -1, -1
+
+    # -- device-resident blocks (one torch tensor per device, (n, rows_i) row-major == column-major rows_i x n) --
+    def _ptrs(self, tensors):
+        return (C.c_void_p * len(tensors))(*[C.c_void_p(t.data_ptr()) if t is not None else None for t in tensors])
+
+    def qr_tsqr_dev(self, blocks, diags=None, rs=None):
+        n = blocks[0].shape[0]
+        rows = (C.c_int64 * len(blocks))(*[b.shape[1] for b in blocks])
+        self._check(self.lib.lfb_qr_tsqr_multi_dev_f64(self.h, self._ptrs(blocks), rows, n, rows,
+                                                       self._ptrs(diags) if diags else None, self._ptrs(rs) if rs else None))
+
+    def tsqr_r_dev(self, blocks, rs):
+        n = blocks[0].shape[0]
+        rows = (C.c_int64 * len(blocks))(*[b.shape[1] for b in blocks])
+        self._check(self.lib.lfb_tsqr_r_multi_dev_f64(self.h, self._ptrs(blocks), rows, n, rows, self._ptrs(rs)))
+
+    def qr_batched_dev_f32(self, mats, diags):
+        m, n = mats[0].shape[1], mats[0].shape[2]
+        batch = (C.c_int64 * len(mats))(*[t.shape[0] for t in mats])
+        self._check(self.lib.lfb_qr_batched_multi_dev_f32(self.h, self._ptrs(mats), batch, m, n, self._ptrs(diags)))
+
+    def time_begin(self):
+        self._check(self.lib.lfb_multi_time_begin(self.h))
+
+    def time_end(self) -> float:
+        ms = C.c_double(0)
+        self._check(self.lib.lfb_multi_time_end(self.h, C.byref(ms)))
+        return ms.value
