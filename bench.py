@@ -725,6 +725,16 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
                            "ms_per_step": ms / 2, "scaling": "strong", "exchange": "NCCL all_gather of 256x256 R per rank" if world > 1 else "none",
                            "check": {"RtR_vs_AtA": g_err, "normR_over_normA_minus_1": nrm_err, "diag_nonneg_lower_zero": struct_ok},
                            "check_ok": g_err <= 1e-12 and nrm_err <= 1e-13 and struct_ok}
+        out["tsqr_f64"]["leaf"] = "Cholesky-QR leaf (Gram GEMM + 256x256 Cholesky, cond guard; csrc/cholqr.cu)"
+        if world == 1:      # the Householder leaf (round 1's path; still the fallback for ill-conditioned blocks) beside it
+            eng.set_option("tsqr_cholqr_cond", 0)
+            try:
+                ms_h = timed(tsqr_step, 1, 1)
+                out["tsqr_f64"]["householder_leaf_ms"] = ms_h
+                Rh = rres["r"].t()
+                out["tsqr_f64"]["leaf_vs_householder_max_rel_diff"] = float((Rh - Rm).abs().max() / Rm.abs().max())
+            finally:
+                eng.set_option("tsqr_cholqr_cond", 16)
         del T0, Tw, gram
         torch.cuda.empty_cache()
     except Exception as ex:

@@ -253,6 +253,13 @@ int lfb_qr_tsqr_dev_f32(lfb_handle *h, float *d_a, int64_t rows, int64_t cols, i
  *                     d_u <- U' (n x n) for everybody else's rows, d_diag <- signed pivots
  *   reconstruct_rows: d_q (rows x n, any rows below the top block) <- d_q * U'^-1  == the reflector rows */
 int lfb_tsqr_explicit_q_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_r, int64_t ldr);
+/* The Cholesky-QR leaf on its own (csrc/cholqr.cu): R (cols x cols upper, diag >= 0) and R^-1 of a tall block from its Gram
+ * matrix, d_a NOT modified.  *ok = 1 if the leaf accepted the block (Cholesky succeeded and cond_1(R) <= option
+ * "tsqr_cholqr_cond"), else 0 and nothing is written: the caller then takes lfb_tsqr_explicit_q_dev_f64.  Synchronises the
+ * stream (the decision is made on the host).  With it a row-sharded caller folds everything after the leaf into n x n
+ * products: rows <- rows * (R_i^-1 Qs_i U'^-1)  (linfa_linalg_b200/dist.py: tsqr_qr, csrc/multi.cu). */
+int lfb_tsqr_leaf_dev_f64(lfb_handle *h, const double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_r, int64_t ldr,
+                          double *d_rinv, int64_t ldri, int *ok);
 int lfb_tsqr_apply_q_dev_f64(lfb_handle *h, double *d_q, int64_t rows, int64_t cols, int64_t ld, const double *d_qs, int64_t ldqs);
 int lfb_hh_reconstruct_top_dev_f64(lfb_handle *h, double *d_qtop, int64_t n, int64_t ld, const double *d_r, int64_t ldr,
                                    double *d_u, int64_t ldu, double *d_diag);
@@ -284,7 +291,8 @@ int lfb_debug_panel_phases(lfb_handle *h, long long *out4);
 int lfb_microbench_fp64(lfb_handle *h, int kind, double *gflops);
 /* Device time (us per launch, CUDA events, back-to-back launches) of one internal kernel on an n x n f64
  * problem: "trd_symv" (lower-triangle SYMV of the tridiagonalisation), "trd_head" (its cluster kernel),
- * "bd_gemv_n" / "bd_gemv_t" (streaming GEMVs of the bidiagonalisation on a 4n x n matrix). */
+ * "bd_gemv_n" / "bd_gemv_t" (streaming GEMVs of the bidiagonalisation on a 4n x n matrix); "potf2" (the 64 x 64 diagonal
+ * block kernel of Cholesky; here n selects the variant: 0 left-looking, 1 right-looking, +2 without the inverse). */
 int lfb_microbench_kernel(lfb_handle *h, const char *name, int64_t n, int reps, double *us_per_launch);
 
 /* ==== one box, several GPUs: the two paths that shard naturally behind the same boundary ===================

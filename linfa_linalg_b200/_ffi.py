@@ -74,6 +74,7 @@ SIGNATURES.update({
     "lfb_tsqr_local_r_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
     "lfb_tsqr_explicit_q_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
     "lfb_tsqr_apply_q_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
+    "lfb_tsqr_leaf_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, C.POINTER(_int)],
     "lfb_hh_reconstruct_top_dev_f64": [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp],
     "lfb_hh_reconstruct_rows_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
     "lfb_orthonormalize_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp],

@@ -662,7 +662,7 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     const int64_t BIG = int64_t(1) << 40;
     const Opt table[] = {
         {"qr_nb", &o.qr_nb, 32, 1024}, {"qr_sub", &o.qr_sub, 1, 32}, {"chol_base", &o.chol_base, 1, 64},
-        {"chol_nb", &o.chol_nb, 64, 8192}, {"gemm_tma", &o.gemm_tma, 0, 1}, {"gemm_splitk", &o.gemm_splitk, 0, 1},
+        {"chol_nb", &o.chol_nb, 64, 8192}, {"chol_tn", &o.chol_tn, 0, 1}, {"chol_potf2_rl", &o.chol_potf2_rl, 0, 1}, {"gemm_tma", &o.gemm_tma, 0, 1}, {"gemm_splitk", &o.gemm_splitk, 0, 1}, {"gemm_deterministic", &o.gemm_deterministic, 0, 1}, {"tsqr_cholqr_cond", &o.tsqr_cholqr_cond, 0, 1 << 20},
         {"gemm_v2", &o.gemm_v2, 0, 1}, {"gemm_split_waves", &o.gemm_split_waves, 1, 64}, {"panel_cluster", &o.panel_cluster, 0, 2},
         {"panel_cluster_max", &o.panel_cluster_max, 1, 16}, {"lookahead", &o.lookahead, 0, 1}, {"tsqr_chunk", &o.tsqr_chunk, 64, BIG},
         {"batched_quad", &o.batched_quad, 0, 4}, {"tsqr_streams", &o.tsqr_streams, 1, 64}, {"tsqr_graph", &o.tsqr_graph, 0, 1},
@@ -866,6 +866,15 @@ int lfb_tsqr_explicit_q_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_
     tsqr_explicit_q<double>(*h, d_a, rows, cols, ld, Wk, ldw, d_r, ldr);
     LFB_API_END(h)
 }
+int lfb_tsqr_leaf_dev_f64(lfb_handle *h, const double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_r, int64_t ldr,
+                          double *d_rinv, int64_t ldri, int *ok) {
+    if (!ok) return fail(h, LFB_INVALID_ARGUMENT, "ok is null");
+    *ok = 0;
+    if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
+    LFB_API_BEGIN(h)
+    *ok = (rows >= 4 * cols && cols <= 512 && cholqr_factor<double>(*h, d_a, rows, cols, ld, d_r, ldr, d_rinv, ldri)) ? 1 : 0;
+    LFB_API_END(h)
+}
 int lfb_tsqr_apply_q_dev_f64(lfb_handle *h, double *d_q, int64_t rows, int64_t cols, int64_t ld, const double *d_qs, int64_t ldqs) {
     if (rows < 0 || cols < 0) return fail(h, LFB_INVALID_ARGUMENT, "negative dimension");
     LFB_API_BEGIN(h)
@@ -938,13 +947,14 @@ int lfb_microbench_fp64(lfb_handle *h, int kind, double *gflops) {
 }
 
 int lfb_microbench_kernel(lfb_handle *h, const char *name, int64_t n, int reps, double *us_per_launch) {
-    if (!us_per_launch || !name || n < 2 || reps < 1) return LFB_INVALID_ARGUMENT;
+    if (!us_per_launch || !name || n < 0 || reps < 1) return LFB_INVALID_ARGUMENT;
     LFB_API_BEGIN(h)
     const std::string k(name);
     if (k == "trd_symv") *us_per_launch = microbench_trd(*h, 0, n, reps);
     else if (k == "trd_head") *us_per_launch = microbench_trd(*h, 1, n, reps);
     else if (k == "bd_gemv_n") *us_per_launch = microbench_bd_gemv(*h, 0, 4 * n, n, reps);   // the 4:1 aspect of configs[4]
     else if (k == "bd_gemv_t") *us_per_launch = microbench_bd_gemv(*h, 1, 4 * n, n, reps);
+    else if (k == "potf2") *us_per_launch = microbench_potf2(*h, (int)(n & 3), reps);      // n: 0 old, 1 new, +2 = factor only
     else return fail(h, LFB_INVALID_ARGUMENT, "unknown kernel name");
     LFB_API_END(h)
 }

@@ -44,8 +44,11 @@ struct Options {
     int64_t qr_sub = 32;     // inner BLAS-2 sub-panel width (<= 32)
     int64_t chol_base = 64;  // recursion base of Cholesky / TRSM (<= 64)
     int64_t chol_nb = 512;   // right-looking panel width of Cholesky (K of the trailing SYRK)
+    int64_t chol_tn = 1;     // f64: trailing SYRK in TN form on a transposed copy of the panel (K-major TMA tiles on both sides)
+    int64_t chol_potf2_rl = 1; // diagonal 64 x 64 blocks: right-looking register-blocked kernel (0 = first-generation left-looking)
     int64_t gemm_tma = 1;    // use the TMA-fed DGEMM when operands are 16-byte aligned
     int64_t gemm_splitk = 1; // allow split-K for skinny-output GEMMs
+    int64_t gemm_deterministic = 1; // split-K partial tiles summed in a fixed order by a reduce kernel (0 = atomicAdd epilogue)
     int64_t gemm_split_waves = 6; // target waves of (tile, split-K) work items for skinny outputs
     int64_t gemm_v2 = 1;     // 16-warp cp.async DGEMM when operands are 16-byte aligned
     int64_t panel_cluster = 2; // cluster/DSMEM panel kernel: 2 = second generation, 1 = first, 0 = per-column launches
@@ -65,6 +68,7 @@ struct Options {
     int64_t chol_overlap_d2h = 1;   // host Cholesky (dirty, n >= 2048): finished block columns go back to the host during the factorisation
     int64_t tsqr_streams = 8;       // chunks in flight (each panel kernel occupies one 16-SM cluster)
     int64_t qr_tsqr_auto = 0;       // 1: lfb_qr_* takes the TSQR + Householder-reconstruction route for tall-skinny inputs (rows >= 2 chunks, cols <= 512)
+    int64_t tsqr_cholqr_cond = 16;  // tall-skinny leaf: Cholesky-QR (Gram GEMM + n x n Cholesky) when cond_1(R) <= this; 0 = always Householder
     int64_t tsqr_graph = 0;         // 1: replay the local TSQR stage of a (buffer, shape) seen before as one CUDA graph
                                     // (measured: 145 vs 147 ms -- the stage is GPU bound, not launch bound -- so off by default)
 };
@@ -249,9 +253,13 @@ template <typename T> void apply_constraints(lfb_handle &h, T *V, int64_t n, int
 template <typename T> void hh_reconstruct_top(lfb_handle &h, T *Qtop, int64_t n, int64_t ld, const T *R, int64_t ldr, T *U, int64_t ldu, T *diag);
 // Tall-skinny thin QR in the reference's compact form (identical contract to qr_factor) via TSQR + reconstruction.
 template <typename T> void qr_tsqr(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *diag);
+// Cholesky-QR leaf (cholqr.cu): R (n x n upper, diag >= 0) and optionally R^-1 of a tall block WITHOUT touching A; returns
+// false (nothing written) when the Gram matrix is not safely positive definite -- the caller then takes the Householder route.
+template <typename T> bool cholqr_factor(lfb_handle &h, const T *A, int64_t rows, int64_t n, int64_t ld, T *R, int64_t ldr, T *Rinv, int64_t ldri);
 template <typename T> void triangular_zero(lfb_handle &h, T *A, int64_t n, int64_t ld, int keep_lower);
 double microbench_fp64(lfb_handle &h, int kind);
 double microbench_trd(lfb_handle &h, int kind, int64_t n, int reps);
+double microbench_potf2(lfb_handle &h, int kind, int reps);
 double microbench_bd_gemv(lfb_handle &h, int kind, int64_t m, int64_t n, int reps);
 
 }  // namespace lfb

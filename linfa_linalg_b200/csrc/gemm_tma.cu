@@ -18,6 +18,8 @@
 // 128B swizzle (chunk index ^= row%8).
 #include <cuda.h>
 
+#include <memory>
+
 #include "common.cuh"
 
 namespace lfb {
@@ -36,6 +38,8 @@ struct TmaP {
     double *C;
     double alpha, beta;
     int lower_only, ksplit, atomic, vecC;
+    int partial;        // deterministic split-K: split z writes alpha * (its partial product) to C + z * zstride (ld = ldc), no atomics
+    int64_t zstride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -211,7 +215,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     constexpr int LDT = BM + 2;
     double *tile = reinterpret_cast<double *>(smem);   // [BN][LDT], element (m, n) at n*LDT + m
     asm volatile("bar.sync 1, %0;" ::"n"(NCONS * 32) : "memory");   // every consumer is done with the ring
-    const double alpha = p.alpha, beta = p.beta;
+    const double alpha = p.alpha, beta = p.partial ? 0.0 : p.beta;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int nl = wn0 + frag_row<BKm>(j, gid);
@@ -221,7 +225,7 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             for (int e = 0; e < 2; ++e) tile[nl * LDT + wm0 + frag_row<AK>(i, 2 * tig + e)] = alpha * acc[j][i][e];
     }
     asm volatile("bar.sync 1, %0;" ::"n"(NCONS * 32) : "memory");
-    double *__restrict__ C = p.C;
+    double *__restrict__ C = p.C + (p.partial ? (int64_t)blockIdx.z * p.zstride : 0);
     if (p.vecC && !p.atomic) {
         constexpr int PER = 8;   // double2 chunks in flight per thread (2 rounds of 8 cover the tile)
         for (int round = 0; round < (BM / 2) * BN / (NCONS * 32 * PER); ++round) {
@@ -274,18 +278,15 @@ typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, voi
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeFn get_encode() {
-    static EncodeFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // resolved once (thread-safe: C++11 static initialisation); several host threads drive several devices in multi.cu
+    static const EncodeFn fn = [] {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeFn)p;
-        else
-            cudaGetLastError();
-    }
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            return (EncodeFn)p;
+        cudaGetLastError();
+        return (EncodeFn) nullptr;
+    }();
     return fn;
 }
 
@@ -310,6 +311,21 @@ __global__ void scale_kernel_d(K *C, int64_t M, int64_t N, int64_t ldc, K beta, 
         if (lower_only && m < n) continue;
         K *c = C + m + n * ldc;
         *c = beta == K(0) ? K(0) : beta * *c;
+    }
+}
+
+// C = beta C + sum_z W_z in the fixed order z = 0, 1, ...: the deterministic second stage of split-K.
+__global__ void splitk_reduce_kernel(const double *__restrict__ W, int64_t ldw, int64_t zstride, int splits, double *__restrict__ C,
+                                     int64_t M, int64_t N, int64_t ldc, double beta, int lower_only) {
+    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    for (int64_t n = blockIdx.y; n < N; n += gridDim.y) {
+        if (lower_only && m < n) continue;
+        const double *w = W + m + n * ldw;
+        double acc = 0.0;
+        for (int z = 0; z < splits; ++z) acc += w[(int64_t)z * zstride];
+        double *c = C + m + n * ldc;
+        *c = beta == 0.0 ? acc : fma(beta, *c, acc);
     }
 }
 
@@ -353,17 +369,40 @@ bool dgemm_tma_try(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int64_t 
     }
     p.ksplit = (int)round_up(cdiv(K, splits), BK);
     splits = (int)cdiv(K, p.ksplit);
-    p.atomic = splits > 1;
-    if (p.atomic && beta != 1.0) {
-        dim3 g((unsigned)cdiv(M, 256), (unsigned)(N < 65535 ? N : 65535));
-        scale_kernel_d<double><<<g, 256, 0, h.stream>>>(C, M, N, ldc, beta, lower_only);
-        LFB_LAUNCH_CHECK(h);
+    p.partial = 0;
+    p.zstride = 0;
+    // Split-K, second stage.  Default (gemm_deterministic): every split writes its partial tile to a workspace slice and a
+    // reduce kernel sums the slices in a fixed order, so results are bit-reproducible run to run like the reference's
+    // sequential loops; the slices cost 2 * splits * M * N * 8 B of extra traffic on outputs that are skinny by construction
+    // (< 148 tiles).  gemm_deterministic = 0 restores the atomicAdd epilogue.
+    std::unique_ptr<DevBuf<double>> work;
+    const int64_t ldw = round_up(M, 2);
+    if (splits > 1 && h.opt.gemm_deterministic) {
+        work.reset(new DevBuf<double>(h, (size_t)ldw * N * splits));
+        p.partial = 1;
+        p.zstride = ldw * N;
+        p.C = work->get();
+        p.ldc = ldw;
+        p.vecC = 1;
+        p.atomic = 0;
+    } else {
+        p.atomic = splits > 1;
+        if (p.atomic && beta != 1.0) {
+            dim3 g((unsigned)cdiv(M, 256), (unsigned)(N < 65535 ? N : 65535));
+            scale_kernel_d<double><<<g, 256, 0, h.stream>>>(C, M, N, ldc, beta, lower_only);
+            LFB_LAUNCH_CHECK(h);
+        }
     }
     dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)splits);
     if (AK && BKm) launch<1, 1>(h, ma, mb, p, grid);
     else if (AK && !BKm) launch<1, 0>(h, ma, mb, p, grid);
     else if (!AK && BKm) launch<0, 1>(h, ma, mb, p, grid);
     else launch<0, 0>(h, ma, mb, p, grid);
+    if (p.partial) {
+        dim3 g((unsigned)cdiv(M, 128), (unsigned)(N < 65535 ? N : 65535));
+        splitk_reduce_kernel<<<g, 128, 0, h.stream>>>(work->get(), ldw, p.zstride, splits, C, M, N, ldc, beta, lower_only);
+        LFB_LAUNCH_CHECK(h);
+    }
     return true;
 }
 

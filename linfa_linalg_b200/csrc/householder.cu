@@ -783,6 +783,9 @@ static void tsqr_local_chunks(lfb_handle &h, T *A, int64_t rows, int64_t cols, i
 template <typename T>
 void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *R, int64_t ldr) {
     if (cols <= 0) return;
+    // Tall and well conditioned: the Cholesky-QR leaf (cholqr.cu) -- one Gram GEMM over all the rows + an n x n Cholesky.
+    // Guarded; when it declines, A is untouched and the Householder leaf below runs as before.
+    if (!h.is_sub && rows >= 4 * cols && cols <= 512 && cholqr_factor<T>(h, A, rows, cols, ld, R, ldr, (T *)nullptr, 0)) return;
     const int64_t CH = std::max<int64_t>(h.opt.tsqr_chunk, 2 * cols);
     if (rows < 2 * CH || h.is_sub) {
         DevBuf<T> diag(h, cols);
@@ -870,6 +873,16 @@ void tsqr_local_r(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T
 template <typename T>
 void tsqr_explicit_q(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *Wk, int64_t ldw, T *R, int64_t ldr) {
     if (cols <= 0 || rows <= 0) return;
+    if (!h.is_sub && rows >= 4 * cols && cols <= 512) {
+        // Cholesky-QR leaf: R and R^-1 from the Gram matrix, Q = A R^-1 as ONE tensor-core GEMM (K = n) through the scratch
+        const int64_t ldi = round_up(cols, 2);
+        DevBuf<T> Rinv(h, (size_t)ldi * cols);
+        if (cholqr_factor<T>(h, A, rows, cols, ld, R, ldr, Rinv.get(), ldi)) {
+            gemm<T>(h, 0, 0, rows, cols, cols, T(1), A, ld, Rinv.get(), ldi, T(0), Wk, ldw);
+            copy2d<T>(h, Wk, ldw, A, ld, rows, cols);
+            return;
+        }
+    }
     const int64_t CH = std::max<int64_t>(h.opt.tsqr_chunk, 2 * cols);
     if (rows < 2 * CH || h.is_sub) {
         DevBuf<T> diag(h, cols);

@@ -203,25 +203,54 @@ struct TsqrDev {
 // (qr_into contract) in the blocks + diag; otherwise R only.  On return (asynchronous on every handle's stream):
 //   st[i].R  : n x n column-major (ld n) final R (diag >= 0), on every device
 //   st[i].UD : (want_q) U' (ldu x n) followed by diag (n values), on every device
+//
+// want_q takes the FOLDED route when the Cholesky-QR leaf (cholqr.cu) accepts every device's block: with
+// Q_i = A_i R_i^-1 Qs_i (Qs = the Q of the stacked R factors) the reflector rows are Y_i = Q_i U'^-1 = A_i W_i,
+// W_i = R_i^-1 Qs_i U'^-1 (n x n), so each device touches its rows with ONE Gram GEMM and ONE GEMM by W_i; only device 0
+// forms the n x n top block Q_top = A_top M_0 for the reconstruction.  If any block is declined (ill-conditioned / rank
+// deficient) every device takes the Householder route: explicit-Q TSQR, Q_i <- Q_i Qs_i, right-hand TRSM.
 template <typename T>
 int tsqr_core(lfb_multi *m, std::vector<TsqrDev<T>> &st, int64_t n, bool want_q) {
     const int G = (int)m->hs.size();
     const int64_t ldu = round_up(n, 2);
+    const int64_t srows = (int64_t)G * n, lds = round_up(srows, 2);
+    std::vector<int> leaf_ok(G, 0);
+    std::vector<std::unique_ptr<DevBuf<T>>> Rinv(G), Qt(G);
     int rc = m->run_all([&](int i) {
         lfb_handle &h = *m->hs[i];
         TsqrDev<T> &d = st[i];
         d.R.reset(new DevBuf<T>(h, (size_t)n * n));
         if (G > 1) d.Rall.reset(new DevBuf<T>(h, (size_t)G * n * n));
         if (want_q) {
-            const int64_t ldw = round_up(d.rows, 2);
-            d.Wk.reset(new DevBuf<T>(h, (size_t)ldw * n));
-            tsqr_explicit_q<T>(h, d.A, d.rows, n, d.ld, d.Wk->get(), ldw, d.R->get(), n);
-            d.Wk.reset();      // stream-ordered reuse: every later user of this handle's pool runs on the same stream
+            Rinv[i].reset(new DevBuf<T>(h, (size_t)ldu * n));
+            leaf_ok[i] = (d.rows >= 4 * n && n <= 512 && cholqr_factor<T>(h, d.A, d.rows, n, d.ld, d.R->get(), n, Rinv[i]->get(), ldu)) ? 1 : 0;
         } else {
             tsqr_local_r<T>(h, d.A, d.rows, n, d.ld, d.R->get(), n);
         }
     });
     if (rc != LFB_OK) return rc;
+    bool folded = want_q;
+    for (int i = 0; i < G; ++i) folded = folded && leaf_ok[i];
+    if (want_q && !folded) {
+        // Householder route for everybody; the leaf attempt is switched off meanwhile so that it is not repeated per block
+        rc = m->run_all([&](int i) {
+            lfb_handle &h = *m->hs[i];
+            TsqrDev<T> &d = st[i];
+            const int64_t keep = h.opt.tsqr_cholqr_cond;
+            h.opt.tsqr_cholqr_cond = 0;
+            try {
+                const int64_t ldw = round_up(d.rows, 2);
+                d.Wk.reset(new DevBuf<T>(h, (size_t)ldw * n));
+                tsqr_explicit_q<T>(h, d.A, d.rows, n, d.ld, d.Wk->get(), ldw, d.R->get(), n);
+                d.Wk.reset();      // stream-ordered reuse: every later user of this handle's pool runs on the same stream
+            } catch (...) {
+                h.opt.tsqr_cholqr_cond = keep;
+                throw;
+            }
+            h.opt.tsqr_cholqr_cond = keep;
+        });
+        if (rc != LFB_OK) return rc;
+    }
     if (G > 1) {
         std::vector<T *> send(G), all(G);
         for (int i = 0; i < G; ++i) { send[i] = st[i].R->get(); all[i] = st[i].Rall->get(); }
@@ -231,21 +260,35 @@ int tsqr_core(lfb_multi *m, std::vector<TsqrDev<T>> &st, int64_t n, bool want_q)
     rc = m->run_all([&](int i) {
         lfb_handle &h = *m->hs[i];
         TsqrDev<T> &d = st[i];
-        const int64_t srows = (int64_t)G * n, lds = round_up(srows, 2);
         if (G > 1) {
             d.stack.reset(new DevBuf<T>(h, (size_t)lds * n));
             for (int g = 0; g < G; ++g) copy2d<T>(h, d.Rall->get() + (size_t)g * n * n, n, d.stack->get() + (size_t)g * n, lds, n, n);
             if (want_q) {
                 d.Ws.reset(new DevBuf<T>(h, (size_t)lds * n));
                 tsqr_explicit_q<T>(h, d.stack->get(), srows, n, lds, d.Ws->get(), lds, d.R->get(), n);   // stack <- Qs
-                tsqr_apply_q<T>(h, d.A, d.rows, n, d.ld, d.stack->get() + (size_t)i * n, lds);
+                if (folded) {   // M_i = R_i^-1 Qs_i, kept in Ws (its head is free again)
+                    gemm<T>(h, 0, 0, n, n, n, T(1), Rinv[i]->get(), ldu, d.stack->get() + (size_t)i * n, lds, T(0), d.Ws->get(), ldu);
+                    LFB_CUDA(cudaMemcpyAsync(Rinv[i]->get(), d.Ws->get(), sizeof(T) * ldu * n, cudaMemcpyDeviceToDevice, h.stream));
+                } else {
+                    tsqr_apply_q<T>(h, d.A, d.rows, n, d.ld, d.stack->get() + (size_t)i * n, lds);
+                }
             } else {
                 tsqr_local_r<T>(h, d.stack->get(), srows, n, lds, d.R->get(), n);
             }
         }
         if (want_q) {
             d.UD.reset(new DevBuf<T>(h, (size_t)ldu * n + n));
-            if (i == 0) hh_reconstruct_top<T>(h, d.A, n, d.ld, d.R->get(), n, d.UD->get(), ldu, d.UD->get() + (size_t)ldu * n);
+            if (i == 0) {
+                T *top = d.A;
+                int64_t ldtop = d.ld;
+                if (folded) {   // Q_top = A_top M_0, out of place: A's rows stay intact until the final GEMM
+                    Qt[0].reset(new DevBuf<T>(h, (size_t)ldu * n));
+                    gemm<T>(h, 0, 0, n, n, n, T(1), d.A, d.ld, Rinv[0]->get(), ldu, T(0), Qt[0]->get(), ldu);
+                    top = Qt[0]->get();
+                    ldtop = ldu;
+                }
+                hh_reconstruct_top<T>(h, top, n, ldtop, d.R->get(), n, d.UD->get(), ldu, d.UD->get() + (size_t)ldu * n);
+            }
         }
     });
     if (rc != LFB_OK || !want_q) return rc;
@@ -259,7 +302,13 @@ int tsqr_core(lfb_multi *m, std::vector<TsqrDev<T>> &st, int64_t n, bool want_q)
         lfb_handle &h = *m->hs[i];
         TsqrDev<T> &d = st[i];
         const int64_t off = i == 0 ? n : 0;
-        trsm_right_upper<T>(h, d.rows - off, n, d.UD->get(), ldu, d.A + off, d.ld);
+        if (folded) {
+            trsm_right_upper<T>(h, n, n, d.UD->get(), ldu, Rinv[i]->get(), ldu);                      // W_i = M_i U'^-1
+            tsqr_apply_q<T>(h, d.A + off, d.rows - off, n, d.ld, Rinv[i]->get(), ldu);                // rows <- rows W_i
+            if (i == 0) copy2d<T>(h, Qt[0]->get(), ldu, d.A, d.ld, n, n);
+        } else {
+            trsm_right_upper<T>(h, d.rows - off, n, d.UD->get(), ldu, d.A + off, d.ld);
+        }
     });
 }
 

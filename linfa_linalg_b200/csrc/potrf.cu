@@ -12,6 +12,8 @@
 // block is NOT a substitution (a 2000-instruction dependent chain per row) but a multiplication by
 // the explicitly inverted 64x64 block (recursive doubling, 6 levels), which is throughput-bound.
 // Only the lower triangle is read or written (the `dirty` contract, cholesky.rs:17-19).
+#include <memory>
+
 #include "common.cuh"
 
 namespace lfb {
@@ -38,7 +40,7 @@ template <> __device__ __forceinline__ double fast_rsqrt<double>(double d) {
 // In:  A (n x n lower block at (row0,row0) of the big matrix).  Out: L in place, Linv (64 x 64,
 // column-major ld 64, identity padded beyond n) = L^-1.  256 threads: thread t -> row t/4, part t%4.
 template <typename T>
-__global__ void __launch_bounds__(256) potf2_inv_kernel(T *A, int64_t ld, int n, int64_t row0, int64_t *info, T *Linv) {
+__global__ void __launch_bounds__(256) potf2_inv_kernel(T *A, int64_t ld, int n, int64_t row0, int64_t *info, T *Linv, int do_inv = 1) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s = reinterpret_cast<T *>(smem_raw);   // L   [CB][SP]
     T *x = s + CB * SP;                       // L^-1 [CB][SP]
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(T *A, int64_t ld, int n,
         const int i = e % n, k = e / n;
         if (k <= i) A[i + (int64_t)k * ld] = s[i * SP + k];
     }
-    if (fail) return;
+    if (fail || !do_inv) return;
 
     // ---- X = L^-1 by recursive doubling: inv([A 0; B C]) = [A^-1 0; -C^-1 B A^-1, C^-1] ----
     for (int e = tid; e < CB * CB; e += 256) {
@@ -110,6 +112,142 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(T *A, int64_t ld, int n,
         }
         __syncthreads();
         // X21 = -C^-1 * tmp   (C^-1 = x[o+b.., o+b..) lower)
+        for (int e = tid; e < npair * per; e += 256) {
+            const int p = e / per, i = (e % per) / b, jj = e % b, o = p * 2 * b;
+            T acc = T(0);
+            for (int k = 0; k <= i; ++k) acc += x[(o + b + i) * SP + o + b + k] * tmp[(p * b + k) * SP + jj];
+            x[(o + b + i) * SP + o + jj] = -acc;
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < CB * CB; e += 256) {
+        const int i = e % CB, k = e / CB;
+        Linv[i + k * CB] = x[i * SP + k];
+    }
+}
+
+// Second generation of the diagonal-block kernel: RIGHT-LOOKING with the block in registers.
+// The 64 x 64 lower triangle is 136 blocks of 4 x 4; thread p < 136 owns block (bi >= bj) in 16 registers.  Step j:
+// every thread reads the (unscaled) column j that its owners published in shared memory one step earlier, takes
+// inv = 1/sqrt(a_jj) itself (no broadcast of the pivot: it is colbuf[j]), scales the 4 + 4 entries it needs and applies
+// the rank-1 update to its columns > j -- 16 independent FMAs -- then the owners of column j+1 publish it.  ONE barrier per
+// step (two column buffers), ~250 cycles per pivot instead of the ~2000 of the left-looking kernel above, whose per-step
+// dot products grow with j.  Same outputs: L in place, L^-1 in Linv, *info = first non-positive pivot (cholesky.rs:69-71).
+template <typename T>
+__global__ void __launch_bounds__(256) potf2_rl_inv_kernel(T *A, int64_t ld, int n, int64_t row0, int64_t *info, T *Linv, int do_inv = 1) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s = reinterpret_cast<T *>(smem_raw);   // L   [CB][SP]
+    T *x = s + CB * SP;                       // L^-1 [CB][SP]
+    T *tmp = x + CB * SP;                     // scratch [32][SP]; its head doubles as the two column buffers of the factor phase
+    T *colbuf = tmp;                          // [2][CB]
+    if (*info != 0) return;
+    const int tid = threadIdx.x;
+    const bool active = tid < 136;
+    int bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= tid) ++bi;
+    const int bj = tid - bi * (bi + 1) / 2;
+    const int r0 = 4 * bi, c0 = 4 * bj;
+    T a[4][4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = r0 + rr, c = c0 + cc;
+            T v = (r == c) ? T(1) : T(0);                       // identity padding beyond n, zeros above the diagonal
+            if (active && r < n && c <= r) v = A[r + (int64_t)c * ld];
+            a[rr][cc] = v;
+        }
+    if (active && bj == 0) {
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) colbuf[r0 + rr] = a[rr][0];
+    }
+    __syncthreads();
+    int fail = 0;
+    for (int j = 0; j < n; ++j) {
+        const T *cur = colbuf + (j & 1) * CB;
+        T *nxt = colbuf + ((j + 1) & 1) * CB;
+        const T d = cur[j];                                    // identical in every thread
+        if (d <= T(0)) {                                       // cholesky.rs:69-71 (false for NaN)
+            fail = j + 1;
+            break;
+        }
+        const int cj = j >> 2, jj = j & 3;
+        if (active && bj >= cj) {
+            const T inv = fast_rsqrt(d);
+            T lr[4], lc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                lr[k] = cur[r0 + k] * inv;
+                lc[k] = cur[c0 + k] * inv;
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+                if (c0 + cc > j) {
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) a[rr][cc] = fma(-lr[rr], lc[cc], a[rr][cc]);
+                }
+            // column j itself (owners: bj == cj): final values of L.  Written as selects over compile-time (rr, cc) so that
+            // the 4 x 4 block stays in registers (a branchy version sent it to local memory: 61 us per block instead of ~15)
+            T sq = d * inv;                                    // sqrt(d) with one correction step
+            sq = fma(T(0.5) * inv, fma(-sq, sq, d), sq);
+            const bool own = bj == cj;
+            const int jn = j + 1;
+            const bool pub = jn < n && bj == (jn >> 2);        // publish the updated, unscaled column j+1
+            const int jnn = jn & 3;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const int r = r0 + rr;
+                    const T v = a[rr][cc];
+                    a[rr][cc] = (own && cc == jj && r >= j) ? (r == j ? sq : lr[rr]) : v;
+                }
+            }
+            if (pub) {
+                T o0, o1, o2, o3;
+                o0 = jnn == 0 ? a[0][0] : (jnn == 1 ? a[0][1] : (jnn == 2 ? a[0][2] : a[0][3]));
+                o1 = jnn == 0 ? a[1][0] : (jnn == 1 ? a[1][1] : (jnn == 2 ? a[1][2] : a[1][3]));
+                o2 = jnn == 0 ? a[2][0] : (jnn == 1 ? a[2][1] : (jnn == 2 ? a[2][2] : a[2][3]));
+                o3 = jnn == 0 ? a[3][0] : (jnn == 1 ? a[3][1] : (jnn == 2 ? a[3][2] : a[3][3]));
+                nxt[r0] = o0; nxt[r0 + 1] = o1; nxt[r0 + 2] = o2; nxt[r0 + 3] = o3;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && fail) *info = row0 + fail;
+    __syncthreads();                                           // the column buffers alias tmp: nobody reads them any more
+    if (active) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int r = r0 + rr, c = c0 + cc;
+                s[r * SP + c] = c <= r ? a[rr][cc] : T(0);
+                if (bi != bj) s[c * SP + r] = T(0);
+            }
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += 256) {
+        const int i = e % n, k = e / n;
+        if (k <= i) A[i + (int64_t)k * ld] = s[i * SP + k];
+    }
+    if (fail || !do_inv) return;
+
+    // ---- X = L^-1 by recursive doubling, as in potf2_inv_kernel ----
+    for (int e = tid; e < CB * CB; e += 256) {
+        const int i = e / CB, k = e % CB;
+        x[i * SP + k] = (i == k) ? T(1) / s[i * SP + i] : T(0);
+    }
+    __syncthreads();
+    for (int b = 1; b < CB; b <<= 1) {
+        const int npair = CB / (2 * b), per = b * b;
+        for (int e = tid; e < npair * per; e += 256) {
+            const int p = e / per, i = (e % per) / b, jj = e % b, o = p * 2 * b;
+            T acc = T(0);
+            for (int k = jj; k < b; ++k) acc += s[(o + b + i) * SP + o + k] * x[(o + k) * SP + o + jj];
+            tmp[(p * b + i) * SP + jj] = acc;
+        }
+        __syncthreads();
         for (int e = tid; e < npair * per; e += 256) {
             const int p = e / per, i = (e % per) / b, jj = e % b, o = p * 2 * b;
             T acc = T(0);
@@ -186,6 +324,7 @@ void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64
     static DeviceOnce cfg;   // function attributes are per device
     cfg.run(h.device, [&] {
         LFB_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+        LFB_CUDA(cudaFuncSetAttribute(potf2_rl_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
         LFB_CUDA(cudaFuncSetAttribute(trsm_mult_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
     });
     DevBuf<T> Linv(h, CB * CB);
@@ -196,7 +335,8 @@ void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64
         for (int64_t j0 = k0; j0 < pend; j0 += CB) {
             const int jb = (int)std::min<int64_t>(CB, pend - j0);
             T *Ajj = A + j0 + j0 * ld;
-            potf2_inv_kernel<T><<<1, 256, smem_p, h.stream>>>(Ajj, ld, jb, j0, d_info, Linv.get());
+            if (h.opt.chol_potf2_rl) potf2_rl_inv_kernel<T><<<1, 256, smem_p, h.stream>>>(Ajj, ld, jb, j0, d_info, Linv.get());
+            else potf2_inv_kernel<T><<<1, 256, smem_p, h.stream>>>(Ajj, ld, jb, j0, d_info, Linv.get());
             LFB_LAUNCH_CHECK(h);
             const int64_t below = n - (j0 + jb);
             if (below <= 0) continue;
@@ -211,44 +351,104 @@ void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64
     // Look-ahead: the trailing SYRK of panel k is split into the block column of panel k+1 (done
     // first) and the rest; panel k+1 is factored on a high-priority side stream while the rest of
     // the SYRK runs, so the latency-bound diagonal kernels leave the critical path.
+    //
+    // TN form of the trailing update (f64, option chol_tn): the finished panel P (rows x nb, column-major = "MN-major"
+    // for both operands of P P^T, which costs the TMA GEMM 16 box loads per stage and its slower fragment path) is
+    // transposed ONCE into Pt (nb x rows, K contiguous): the SYRK becomes C -= Pt^T Pt, K-major on both sides -- the
+    // kernel's fastest variant (2 TMA loads per stage; 35.8 vs 31.3 TFLOP/s at K = 512 on this shape,
+    // profiles/r1_gemm_bench.jsonl).  O(n nb) extra traffic per panel; two buffers because panel k+1 is transposed on the
+    // side stream while the main stream still reads panel k's copy.
     cudaStream_t sm = h.stream, sp = h.aux_stream;
     const bool la = h.opt.lookahead && sp != nullptr && !h.prof_on && n >= 4 * NB;
+    const bool tn = sizeof(T) == 8 && h.opt.chol_tn && n >= 2 * NB;
+    const int64_t ldpt = NB;
+    std::unique_ptr<DevBuf<T>> PtBuf[2];
+    if (tn)
+        for (auto &b : PtBuf) b.reset(new DevBuf<T>(h, (size_t)ldpt * (n > NB ? n - NB : 1)));
+    // C (rows x cols, lower part) -= P[0:rows, :] * P[0:cols, :]^T with P = panel rows r_off.. (and the matching slice of Pt)
+    auto syrk = [&](const T *P, const T *Pt, int64_t r_off, int64_t rows_, int64_t cols_, int64_t nb, T *Cp) {
+        if (tn) gemm<T>(h, 1, 0, rows_, cols_, nb, T(-1), Pt + r_off * ldpt, ldpt, Pt + r_off * ldpt, ldpt, T(1), Cp, ld, /*lower_only=*/1);
+        else gemm<T>(h, 0, 1, rows_, cols_, nb, T(-1), P + r_off, ld, P + r_off, ld, T(1), Cp, ld, /*lower_only=*/1);
+    };
     factor_panel(0, std::min<int64_t>(NB, n));
     if (h.chol_panel_hook) h.chol_panel_hook(0, std::min<int64_t>(NB, n));
-    for (int64_t k0 = 0; k0 < n; k0 += NB) {
+    if (tn && n > NB) transpose<T>(h, A + NB, n - NB, NB, ld, PtBuf[0]->get(), ldpt);
+    int cur = 0;
+    for (int64_t k0 = 0; k0 < n; k0 += NB, cur ^= 1) {
         const int64_t nb = std::min<int64_t>(NB, n - k0);
         const int64_t pend = k0 + nb;
         const int64_t rows = n - pend;
         if (rows <= 0) break;
         const int64_t nbn = std::min<int64_t>(NB, rows);
         T *P = A + pend + k0 * ld;
+        const T *Pt = tn ? PtBuf[cur]->get() : nullptr;
+        T *PtNext = tn ? PtBuf[cur ^ 1]->get() : nullptr;
+        const int64_t rows2 = rows - nbn;
         if (la) {
-            gemm<T>(h, 0, 1, rows, nbn, nb, T(-1), P, ld, P, ld, T(1), A + pend + pend * ld, ld, /*lower_only=*/1);
+            syrk(P, Pt, 0, rows, nbn, nb, A + pend + pend * ld);
             LFB_CUDA(cudaEventRecord(h.ev[0], sm));
             LFB_CUDA(cudaStreamWaitEvent(sp, h.ev[0], 0));
             h.stream = sp;
             try {
                 factor_panel(pend, nbn);
                 if (h.chol_panel_hook) h.chol_panel_hook(pend, nbn);     // h.stream is the side stream here
+                if (tn && rows2 > 0) transpose<T>(h, A + (pend + nbn) + pend * ld, rows2, nbn, ld, PtNext, ldpt);
             } catch (...) {
                 h.stream = sm;
                 throw;
             }
             LFB_CUDA(cudaEventRecord(h.ev[1], sp));
             h.stream = sm;
-            const int64_t rows2 = rows - nbn;
-            if (rows2 > 0) {
-                T *P2 = P + nbn;
-                gemm<T>(h, 0, 1, rows2, rows2, nb, T(-1), P2, ld, P2, ld, T(1), A + (pend + nbn) + (pend + nbn) * ld, ld, /*lower_only=*/1);
-            }
+            if (rows2 > 0) syrk(P, Pt, nbn, rows2, rows2, nb, A + (pend + nbn) + (pend + nbn) * ld);
             LFB_CUDA(cudaStreamWaitEvent(sm, h.ev[1], 0));
         } else {
-            gemm<T>(h, 0, 1, rows, rows, nb, T(-1), P, ld, P, ld, T(1), A + pend + pend * ld, ld, /*lower_only=*/1);
+            syrk(P, Pt, 0, rows, rows, nb, A + pend + pend * ld);
             factor_panel(pend, nbn);
             if (h.chol_panel_hook) h.chol_panel_hook(pend, nbn);
+            if (tn && rows2 > 0) transpose<T>(h, A + (pend + nbn) + pend * ld, rows2, nbn, ld, PtNext, ldpt);
         }
     }
     if (clean) triangular_zero<T>(h, A, n, ld, /*keep_lower=*/1);
+}
+
+// Device time (us per launch) of one diagonal-block kernel on a 64 x 64 SPD block: kind 0 = left-looking (first
+// generation), 1 = right-looking register-blocked; +2 = factor only (no inverse).  The input is restored before every
+// launch by a 32 KiB device copy, which is part of the measured time (< 2 us).
+double microbench_potf2(lfb_handle &h, int kind, int reps) {
+    using T = double;
+    const size_t smem_p = sizeof(T) * (2 * CB * SP + 32 * SP);
+    static DeviceOnce cfg;
+    cfg.run(h.device, [&] {
+        LFB_CUDA(cudaFuncSetAttribute(potf2_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+        LFB_CUDA(cudaFuncSetAttribute(potf2_rl_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+    });
+    std::vector<T> host((size_t)CB * CB);
+    for (int c = 0; c < CB; ++c)
+        for (int r = 0; r < CB; ++r) host[r + c * CB] = r == c ? T(CB) : T(1) / T(1 + r + c);
+    DevBuf<T> A0(h, CB * CB), A(h, CB * CB), Linv(h, CB * CB);
+    DevBuf<int64_t> info(h, 1);
+    LFB_CUDA(cudaMemcpyAsync(A0.get(), host.data(), sizeof(T) * CB * CB, cudaMemcpyHostToDevice, h.stream));
+    LFB_CUDA(cudaMemsetAsync(info.get(), 0, sizeof(int64_t), h.stream));
+    const int do_inv = (kind & 2) ? 0 : 1;
+    auto once = [&]() {
+        LFB_CUDA(cudaMemcpyAsync(A.get(), A0.get(), sizeof(T) * CB * CB, cudaMemcpyDeviceToDevice, h.stream));
+        if (kind & 1) potf2_rl_inv_kernel<T><<<1, 256, smem_p, h.stream>>>(A.get(), CB, CB, 0, info.get(), Linv.get(), do_inv);
+        else potf2_inv_kernel<T><<<1, 256, smem_p, h.stream>>>(A.get(), CB, CB, 0, info.get(), Linv.get(), do_inv);
+        LFB_LAUNCH_CHECK(h);
+    };
+    cudaEvent_t e0, e1;
+    LFB_CUDA(cudaEventCreate(&e0));
+    LFB_CUDA(cudaEventCreate(&e1));
+    for (int r = 0; r < 3; ++r) once();
+    LFB_CUDA(cudaEventRecord(e0, h.stream));
+    for (int r = 0; r < reps; ++r) once();
+    LFB_CUDA(cudaEventRecord(e1, h.stream));
+    LFB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    LFB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return (double)ms * 1e3 / reps;
 }
 
 template void cholesky_lower<float>(lfb_handle &, float *, int64_t, int64_t, int, int64_t *);

@@ -119,6 +119,22 @@ void qr_tsqr(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *dia
     if (cols <= 0 || rows <= 0) return;
     const int64_t ldw = round_up(rows, 2), ldu = round_up(cols, 2);
     DevBuf<T> R(h, (size_t)ldu * cols), U(h, (size_t)ldu * cols);
+    // Folded route on top of the Cholesky-QR leaf: the explicit Q is never formed below the top block.  With Q = A R^-1,
+    //   Q_top = A_top R^-1 (n^3)  ->  LU of (Q_top - S) gives U' and diag  ->  rows below: Y2 = Q2 U'^-1 = A2 (R^-1 U'^-1),
+    // so the tall part is touched by exactly ONE GEMM (m n^2 * 2 flops) after the Gram GEMM: 3.5 m n^2 flops in all against
+    // 7 m n^2 for factor + assemble + combine + solve, all of it on the tensor pipe with K >= n.
+    if (rows >= 4 * cols && cols <= 512) {
+        DevBuf<T> Rinv(h, (size_t)ldu * cols);
+        if (cholqr_factor<T>(h, A, rows, cols, ld, R.get(), ldu, Rinv.get(), ldu)) {
+            DevBuf<T> Qt(h, (size_t)ldu * cols);
+            gemm<T>(h, 0, 0, cols, cols, cols, T(1), A, ld, Rinv.get(), ldu, T(0), Qt.get(), ldu);       // Q_top
+            hh_reconstruct_top<T>(h, Qt.get(), cols, ldu, R.get(), ldu, U.get(), ldu, diag);             // Qt <- top block of the factor
+            trsm_right_upper<T>(h, cols, cols, U.get(), ldu, Rinv.get(), ldu);                           // Rinv <- R^-1 U'^-1
+            tsqr_apply_q<T>(h, A + cols, rows - cols, cols, ld, Rinv.get(), ldu);                        // A2 <- A2 (R^-1 U'^-1)
+            copy2d<T>(h, Qt.get(), ldu, A, ld, cols, cols);
+            return;
+        }
+    }
     {
         DevBuf<T> Wk(h, (size_t)ldw * cols);
         tsqr_explicit_q<T>(h, A, rows, cols, ld, Wk, ldw, R, ldu);

@@ -97,7 +97,9 @@ def tsqr_qr(block, ops, n: int, group=None):
     (n) and the column-major R (diag >= 0) as an (n, n) tensor, both replicated.  `ops` supplies the arithmetic
     (GpuTsqrOps over the C ABI; CPU stand-ins in the gloo tests):
         explicit_q(x) -> r            x (n, rows) <- explicit thin Q of x, r = its column-major R
-        apply_q(x, qs)                x <- x * qs          (qs: contiguous (n, n) tensor, column-major n x n)
+        apply_q(x, qs, row0=0)        rows row0.. of x <- (those rows) * qs     (qs: (n, n) tensor, column-major n x n)
+        leaf(x) -> (r, rinv) | None   optional: Cholesky-QR leaf, x untouched; None when the block is declined
+        matmul(a, b) -> c             optional (with leaf): column-major product of two small column-major operands
         reconstruct_top(x, r, u, diag)   first n rows of x -> top block of the compact factor; u <- U', diag
         reconstruct_rows(x, row0, u)  rows row0.. of x <- (those rows) U'^-1
     Every rank must own at least n rows (checked collectively: ValueError on all ranks otherwise).
@@ -116,21 +118,50 @@ def tsqr_qr(block, ops, n: int, group=None):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
     if int(ok.item()) == 0:
         raise ValueError(f"tsqr_qr needs at least n = {n} rows on every rank (this rank owns {rows_local})")
-    r = ops.explicit_q(block)
+    # The Cholesky-QR leaf (csrc/cholqr.cu) leaves the block untouched and returns R_i, R_i^-1: if EVERY rank's block is
+    # accepted, everything after it folds into n x n products and the rows are touched by one more GEMM only:
+    #   rows <- rows W_i,  W_i = R_i^-1 Qs_i U'^-1       (otherwise: explicit Q, Q_i <- Q_i Qs_i, right-hand TRSM)
+    folded, rinv = False, None
+    if hasattr(ops, "leaf"):
+        got = ops.leaf(block)
+        flag = torch.tensor([1 if got is not None else 0], dtype=torch.int32, device=block.device)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        folded = int(flag.item()) == 1
+        if folded:
+            r, rinv = got
+    if not folded:
+        r = ops.explicit_q(block, householder_only=True) if hasattr(ops, "leaf") else ops.explicit_q(block)
+    m_i = rinv                                                          # M_i = R_i^-1 Qs_i (world 1: Qs = I)
     if world > 1:
         r_all = torch.empty((world * n, n), dtype=r.dtype, device=r.device)
         dist.all_gather_into_tensor(r_all, r.contiguous(), group=group)
         stack = stack_r_factors(r_all, world, n)
         r = ops.explicit_q(stack)                                   # stack <- Qs, replicated
-        ops.apply_q(block, stack[:, rank * n:(rank + 1) * n].contiguous())
+        qs_i = stack[:, rank * n:(rank + 1) * n].contiguous()
+        if folded:
+            m_i = ops.matmul(rinv, qs_i)
+        else:
+            ops.apply_q(block, qs_i)
     ud = torch.empty((n + 1, n), dtype=block.dtype, device=block.device)     # U' and diag share one buffer: ONE broadcast
     u, diag = ud[:n], ud[n]
+    top = None
     if rank == 0:
-        ops.reconstruct_top(block, r, u, diag)
+        if folded:
+            top = ops.matmul(block[:, :n], m_i)                     # Q_top = A_top M_0 (n x n), out of place
+            ops.reconstruct_top(top, r, u, diag)
+        else:
+            ops.reconstruct_top(block, r, u, diag)
     if world > 1:
         src = dist.get_global_rank(group, 0) if group is not None else 0
         dist.broadcast(ud, src=src, group=group)
-    ops.reconstruct_rows(block, n if rank == 0 else 0, u)
+    if folded:
+        ops.reconstruct_rows(m_i, 0, u)                             # W_i = M_i U'^-1 (n x n)
+        ops.apply_q(block, m_i, row0=n if rank == 0 else 0)         # rows <- rows W_i
+        if rank == 0:
+            block[:, :n].copy_(top)
+    else:
+        ops.reconstruct_rows(block, n if rank == 0 else 0, u)
     return diag, r
 
 
@@ -147,16 +178,48 @@ class GpuTsqrOps:
         if st != 0:
             raise RuntimeError(f"{name} status {st}: {self.eng.lib.lfb_last_error(self.eng.h)}")
 
-    def explicit_q(self, x):
+    def explicit_q(self, x, householder_only=False):
         import torch
         n, rows = x.shape
         r = torch.empty((n, n), dtype=torch.float64, device=x.device)
-        self._call("lfb_tsqr_explicit_q_dev_f64", C.c_void_p(x.data_ptr()), rows, n, rows, C.c_void_p(r.data_ptr()), n)
+        keep = None
+        if householder_only:          # the leaf has just declined one of the blocks: do not repeat the attempt
+            keep = 16
+            self.eng.set_option("tsqr_cholqr_cond", 0)
+        try:
+            self._call("lfb_tsqr_explicit_q_dev_f64", C.c_void_p(x.data_ptr()), rows, n, rows, C.c_void_p(r.data_ptr()), n)
+        finally:
+            if keep is not None:
+                self.eng.set_option("tsqr_cholqr_cond", keep)
         return r
 
-    def apply_q(self, x, qs):
+    def leaf(self, x):
+        import torch
         n, rows = x.shape
-        self._call("lfb_tsqr_apply_q_dev_f64", C.c_void_p(x.data_ptr()), rows, n, rows, C.c_void_p(qs.data_ptr()), n)
+        r = torch.empty((n, n), dtype=torch.float64, device=x.device)
+        rinv = torch.empty((n, n), dtype=torch.float64, device=x.device)
+        ok = C.c_int(0)
+        self._call("lfb_tsqr_leaf_dev_f64", C.c_void_p(x.data_ptr()), rows, n, rows, C.c_void_p(r.data_ptr()), n,
+                   C.c_void_p(rinv.data_ptr()), n, C.byref(ok))
+        return (r, rinv) if ok.value == 1 else None
+
+    def matmul(self, a, b):
+        """c = a b for column-major operands held as row-major tensors: a is (k, m) [column-major m x k, leading dimension
+        a.stride(0)], b is (n, k) contiguous [column-major k x n]; returns the (n, m) tensor of the column-major m x n product."""
+        import torch
+        k, m = a.shape
+        n = b.shape[0]
+        c = torch.empty((n, m), dtype=torch.float64, device=b.device)
+        self._call("lfb_gemm_dev_f64", 0, 0, m, n, k, 1.0, C.c_void_p(a.data_ptr()), a.stride(0), C.c_void_p(b.data_ptr()), b.stride(0),
+                   0.0, C.c_void_p(c.data_ptr()), m)
+        return c
+
+    def apply_q(self, x, qs, row0=0):
+        n, rows = x.shape
+        if rows - row0 <= 0:
+            return
+        self._call("lfb_tsqr_apply_q_dev_f64", C.c_void_p(x.data_ptr() + row0 * x.element_size()), rows - row0, n, rows,
+                   C.c_void_p(qs.data_ptr()), n)
 
     def reconstruct_top(self, x, r, u, diag):
         n, rows = x.shape

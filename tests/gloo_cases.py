@@ -138,20 +138,54 @@ class _CpuTsqrOps:
         a[row0:] = np.linalg.solve(U.T, a[row0:].T).T
 
 
-def _tsqr_qr_worker(rank, world, port, rows, n, out):
+class _CpuFoldedOps(_CpuTsqrOps):
+    """The same stand-ins plus the optional Cholesky-QR leaf (csrc/cholqr.cu) and the small column-major product, so that
+    the FOLDED route of dist.tsqr_qr (rows <- rows R_i^-1 Qs_i U'^-1) runs under gloo too.  `decline_on_rank` makes one
+    rank's leaf refuse its block: every rank must then fall back together."""
+
+    def __init__(self, decline_on_rank=None):
+        self.decline_on_rank = decline_on_rank
+        self.leaf_calls = 0
+
+    def explicit_q(self, x, householder_only=False):
+        return super().explicit_q(x)
+
+    def leaf(self, x):
+        self.leaf_calls += 1
+        if self.decline_on_rank is not None and dist.is_initialized() and dist.get_rank() == self.decline_on_rank:
+            return None
+        a = self._cm(x)
+        l = np.linalg.cholesky(a.T @ a)
+        r = l.T
+        return torch.from_numpy(np.ascontiguousarray(r.T)), torch.from_numpy(np.ascontiguousarray(np.linalg.inv(r).T))
+
+    def matmul(self, a, b):
+        return torch.from_numpy(np.ascontiguousarray((a.numpy().T @ b.numpy().T).T))
+
+    def apply_q(self, x, qs, row0=0):
+        a = self._cm(x)
+        a[row0:] = a[row0:] @ qs.numpy().T
+
+
+def _make_ops(kind):
+    return {"plain": _CpuTsqrOps, "folded": _CpuFoldedOps, "declined": lambda: _CpuFoldedOps(decline_on_rank=1)}[kind]()
+
+
+def _tsqr_qr_worker(rank, world, port, rows, n, out, kind="plain"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     full = np.random.default_rng(11).uniform(-100, 100, (rows, n))
     b, e = D.shard_range(rows, world, rank)
     block = torch.from_numpy(np.ascontiguousarray(full[b:e].T))     # (n, rows_local) row-major == column-major block
-    diag, r = D.tsqr_qr(block, _CpuTsqrOps(), n)
+    diag, r = D.tsqr_qr(block, _make_ops(kind), n)
     out[rank] = (block.numpy().T.copy(), diag.numpy().copy(), r.numpy().T.copy())
     dist.destroy_process_group()
 
 
-@pytest.mark.timeout(120)
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("kind", ["plain", "folded", "declined"])
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_tsqr_qr_ranks_match_reference_compact_factor(world):
+def test_tsqr_qr_ranks_match_reference_compact_factor(world, kind):
     """The row blocks returned by tsqr_qr, stacked, are the reference's compact QR factor of the whole matrix
     (qr.rs:29-45 via the oracle): reflectors, R rows and signed pivots, elementwise."""
     import oracle as O
@@ -159,12 +193,12 @@ def test_tsqr_qr_ranks_match_reference_compact_factor(world):
     full = np.random.default_rng(11).uniform(-100, 100, (rows, n))
     if world == 1:
         block = torch.from_numpy(np.ascontiguousarray(full.T))
-        diag, r = D.tsqr_qr(block, _CpuTsqrOps(), n)
+        diag, r = D.tsqr_qr(block, _make_ops(kind), n)
         got = {0: (block.numpy().T.copy(), diag.numpy().copy(), r.numpy().T.copy())}
     else:
         mgr = mp.Manager()
         got = mgr.dict()
-        mp.spawn(_tsqr_qr_worker, args=(world, _free_port(), rows, n, got), nprocs=world, join=True)
+        mp.spawn(_tsqr_qr_worker, args=(world, _free_port(), rows, n, got, kind), nprocs=world, join=True)
     ref = full.copy()
     dref = O.qr(ref)
     tol = 64 * rows * 2.2e-16 * np.linalg.norm(full, 2)

@@ -1,0 +1,53 @@
+"""Option sweeps of one device-resident factorisation in ONE process (min of `reps` timed runs per setting, CUDA events).
+usage: python tools/sweep.py {chol|qr} n reps "opt=val,opt=val" "opt=val" ...      ("-" = defaults)"""
+import ctypes as C
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import linfa_linalg_b200 as L  # noqa: E402
+
+kind, n, reps = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+dev = torch.device("cuda")
+g = torch.Generator(device=dev).manual_seed(1)
+p = lambda t: C.c_void_p(t.data_ptr())
+S = torch.rand((n, n), dtype=torch.float64, device=dev, generator=g) * 2 - 1
+if kind == "chol":
+    S = (S + S.t()) / 2
+    S.diagonal().add_(float(n))
+W = torch.empty_like(S)
+aux = torch.zeros(n, dtype=torch.int64 if kind == "chol" else torch.float64, device=dev)
+flops = n ** 3 / 3 if kind == "chol" else 4.0 / 3.0 * n ** 3
+for spec in sys.argv[4:]:
+    eng = L.Engine(0)
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    if spec != "-":
+        for kv in spec.split(","):
+            k, v = kv.split("=")
+            eng.set_option(k, int(v))
+
+    def step():
+        W.copy_(S)
+        if kind == "chol":
+            st = eng.lib.lfb_cholesky_dev_f64(eng.h, p(W), n, n, 0, p(aux))
+        else:
+            st = eng.lib.lfb_qr_dev_f64(eng.h, p(W), n, n, n, p(aux))
+        assert st == 0
+    step(); step()
+    best = 1e30
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step(); e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    res = {"kind": kind, "n": n, "opts": spec, "ms": round(best, 3), "tflops": round(flops / best / 1e9, 2)}
+    if kind == "chol":
+        Lf = torch.triu(W[:2048, :2048]).t()
+        res["resid"] = float((Lf @ Lf.t() - S[:2048, :2048]).norm() / S[:2048, :2048].norm())
+    print(json.dumps(res), flush=True)
+    eng.set_stream(None)
+    eng.close()
