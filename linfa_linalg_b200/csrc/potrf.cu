@@ -40,7 +40,7 @@ template <> __device__ __forceinline__ double fast_rsqrt<double>(double d) {
 // In:  A (n x n lower block at (row0,row0) of the big matrix).  Out: L in place, Linv (64 x 64,
 // column-major ld 64, identity padded beyond n) = L^-1.  256 threads: thread t -> row t/4, part t%4.
 template <typename T>
-__global__ void __launch_bounds__(256) potf2_inv_kernel(T *A, int64_t ld, int n, int64_t row0, int64_t *info, T *Linv, int do_inv = 1) {
+__global__ void __launch_bounds__(256) potf2_inv_kernel(T *A, int64_t ld, int n, int64_t row0, int64_t *info, T *Linv, int do_inv = 1, int ldinv = CB) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s = reinterpret_cast<T *>(smem_raw);   // L   [CB][SP]
     T *x = s + CB * SP;                       // L^-1 [CB][SP]
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(T *A, int64_t ld, int n,
     }
     for (int e = tid; e < CB * CB; e += 256) {
         const int i = e % CB, k = e / CB;
-        Linv[i + k * CB] = x[i * SP + k];
+        Linv[i + k * ldinv] = x[i * SP + k];
     }
 }
 
@@ -130,11 +130,60 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(T *A, int64_t ld, int n,
 // The 64 x 64 lower triangle is 136 blocks of 4 x 4; thread p < 136 owns block (bi >= bj) in 16 registers.  Step j:
 // every thread reads the (unscaled) column j that its owners published in shared memory one step earlier, takes
 // inv = 1/sqrt(a_jj) itself (no broadcast of the pivot: it is colbuf[j]), scales the 4 + 4 entries it needs and applies
-// the rank-1 update to its columns > j -- 16 independent FMAs -- then the owners of column j+1 publish it.  ONE barrier per
-// step (two column buffers), ~250 cycles per pivot instead of the ~2000 of the left-looking kernel above, whose per-step
-// dot products grow with j.  Same outputs: L in place, L^-1 in Linv, *info = first non-positive pivot (cholesky.rs:69-71).
+// the rank-1 update to its columns > j -- at most 16 independent FMAs -- the owners of column j store its final values
+// into the shared copy of L, and the owners of column j+1 publish it.  ONE barrier per step (two column buffers).  The j
+// loop is unrolled by 4 (the column inside its block is a compile-time constant), so every register index is static and
+// a step is ~60 instructions: the first version kept the block in local memory / behind 64 selects (~260 instructions per
+// step, 39 us per block, profiles/r2_potf2.md).  Same outputs as potf2_inv_kernel: L in place, L^-1 in Linv,
+// *info = first non-positive pivot (cholesky.rs:69-71).
+template <typename T, int JJ>
+__device__ __forceinline__ bool potf2_rl_step(T (&a)[4][4], int j, bool active, int bi, int bj, int r0, int c0, T *colbuf, T *s) {
+    const T *cur = colbuf + (j & 1) * CB;
+    T *nxt = colbuf + ((j + 1) & 1) * CB;
+    const T d = cur[j];                                        // identical in every thread
+    if (d <= T(0)) return false;                               // cholesky.rs:69-71 (false for NaN)
+    const int cj = j >> 2;
+    if (active && bj >= cj) {
+        const T inv = fast_rsqrt(d);
+        T lr[4], lc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            lr[k] = cur[r0 + k] * inv;
+            lc[k] = cur[c0 + k] * inv;
+        }
+        if (bj > cj) {                                         // the whole block lies right of column j
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) a[rr][cc] = fma(-lr[rr], lc[cc], a[rr][cc]);
+            if (JJ == 3 && bj == cj + 1) {                     // publish the updated, unscaled column j+1 (first of the next block column)
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) nxt[r0 + rr] = a[rr][0];
+            }
+        } else {                                               // bj == cj: column j is column JJ of this block
+#pragma unroll
+            for (int cc = JJ + 1; cc < 4; ++cc)
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) a[rr][cc] = fma(-lr[rr], lc[cc], a[rr][cc]);
+            T sq = d * inv;                                    // sqrt(d) with one correction step
+            sq = fma(T(0.5) * inv, fma(-sq, sq, d), sq);
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int r = r0 + rr;
+                if (r >= j) s[r * SP + j] = r == j ? sq : lr[rr];
+            }
+            if (JJ < 3) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) nxt[r0 + rr] = a[rr][JJ < 3 ? JJ + 1 : 0];
+            }
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256) potf2_rl_inv_kernel(T *A, int64_t ld, int n, int64_t row0, int64_t *info, T *Linv, int do_inv = 1) {
+__global__ void __launch_bounds__(256) potf2_rl_inv_kernel(T *A, int64_t ld, int n, int64_t row0, int64_t *info, T *Linv, int do_inv = 1, int ldinv = CB) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s = reinterpret_cast<T *>(smem_raw);   // L   [CB][SP]
     T *x = s + CB * SP;                       // L^-1 [CB][SP]
@@ -157,75 +206,26 @@ __global__ void __launch_bounds__(256) potf2_rl_inv_kernel(T *A, int64_t ld, int
             if (active && r < n && c <= r) v = A[r + (int64_t)c * ld];
             a[rr][cc] = v;
         }
+    for (int e = tid; e < CB * CB; e += 256) {                  // shared L starts as the identity; finished columns overwrite it
+        const int i = e / CB, k = e % CB;
+        s[i * SP + k] = (i == k) ? T(1) : T(0);
+    }
     if (active && bj == 0) {
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) colbuf[r0 + rr] = a[rr][0];
     }
     __syncthreads();
     int fail = 0;
-    for (int j = 0; j < n; ++j) {
-        const T *cur = colbuf + (j & 1) * CB;
-        T *nxt = colbuf + ((j + 1) & 1) * CB;
-        const T d = cur[j];                                    // identical in every thread
-        if (d <= T(0)) {                                       // cholesky.rs:69-71 (false for NaN)
-            fail = j + 1;
-            break;
-        }
-        const int cj = j >> 2, jj = j & 3;
-        if (active && bj >= cj) {
-            const T inv = fast_rsqrt(d);
-            T lr[4], lc[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                lr[k] = cur[r0 + k] * inv;
-                lc[k] = cur[c0 + k] * inv;
-            }
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-                if (c0 + cc > j) {
-#pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) a[rr][cc] = fma(-lr[rr], lc[cc], a[rr][cc]);
-                }
-            // column j itself (owners: bj == cj): final values of L.  Written as selects over compile-time (rr, cc) so that
-            // the 4 x 4 block stays in registers (a branchy version sent it to local memory: 61 us per block instead of ~15)
-            T sq = d * inv;                                    // sqrt(d) with one correction step
-            sq = fma(T(0.5) * inv, fma(-sq, sq, d), sq);
-            const bool own = bj == cj;
-            const int jn = j + 1;
-            const bool pub = jn < n && bj == (jn >> 2);        // publish the updated, unscaled column j+1
-            const int jnn = jn & 3;
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
-                    const int r = r0 + rr;
-                    const T v = a[rr][cc];
-                    a[rr][cc] = (own && cc == jj && r >= j) ? (r == j ? sq : lr[rr]) : v;
-                }
-            }
-            if (pub) {
-                T o0, o1, o2, o3;
-                o0 = jnn == 0 ? a[0][0] : (jnn == 1 ? a[0][1] : (jnn == 2 ? a[0][2] : a[0][3]));
-                o1 = jnn == 0 ? a[1][0] : (jnn == 1 ? a[1][1] : (jnn == 2 ? a[1][2] : a[1][3]));
-                o2 = jnn == 0 ? a[2][0] : (jnn == 1 ? a[2][1] : (jnn == 2 ? a[2][2] : a[2][3]));
-                o3 = jnn == 0 ? a[3][0] : (jnn == 1 ? a[3][1] : (jnn == 2 ? a[3][2] : a[3][3]));
-                nxt[r0] = o0; nxt[r0 + 1] = o1; nxt[r0 + 2] = o2; nxt[r0 + 3] = o3;
-            }
-        }
-        __syncthreads();
+    for (int j = 0; j < n; j += 4) {
+        if (!potf2_rl_step<T, 0>(a, j, active, bi, bj, r0, c0, colbuf, s)) { fail = j + 1; break; }
+        if (j + 1 >= n) break;
+        if (!potf2_rl_step<T, 1>(a, j + 1, active, bi, bj, r0, c0, colbuf, s)) { fail = j + 2; break; }
+        if (j + 2 >= n) break;
+        if (!potf2_rl_step<T, 2>(a, j + 2, active, bi, bj, r0, c0, colbuf, s)) { fail = j + 3; break; }
+        if (j + 3 >= n) break;
+        if (!potf2_rl_step<T, 3>(a, j + 3, active, bi, bj, r0, c0, colbuf, s)) { fail = j + 4; break; }
     }
     if (tid == 0 && fail) *info = row0 + fail;
-    __syncthreads();                                           // the column buffers alias tmp: nobody reads them any more
-    if (active) {
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                const int r = r0 + rr, c = c0 + cc;
-                s[r * SP + c] = c <= r ? a[rr][cc] : T(0);
-                if (bi != bj) s[c * SP + r] = T(0);
-            }
-    }
     __syncthreads();
     for (int e = tid; e < n * n; e += 256) {
         const int i = e % n, k = e / n;
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) potf2_rl_inv_kernel(T *A, int64_t ld, int
     }
     for (int e = tid; e < CB * CB; e += 256) {
         const int i = e % CB, k = e / CB;
-        Linv[i + k * CB] = x[i * SP + k];
+        Linv[i + k * ldinv] = x[i * SP + k];
     }
 }
 
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) potf2_rl_inv_kernel(T *A, int64_t ld, int
 // 4 (rows) x 8 (cols) register block.
 template <typename T>
 __global__ void __launch_bounds__(256) trsm_mult_kernel(T *B, int64_t ldb, int64_t rows, int nb, const T *__restrict__ Linv,
-                                                        const int64_t *info) {
+                                                        const int64_t *info, int ldinv = CB) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *sB = reinterpret_cast<T *>(smem_raw);  // [64 k][132]  sB[k*132 + row]
     T *sL = sB + CB * 132;                    // [64 k][68]   sL[k*68 + j] = Linv[j][k]  (j >= k)
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) trsm_mult_kernel(T *B, int64_t ldb, int64
 #pragma unroll 4
     for (int e = tid; e < CB * CB; e += 256) {
         const int j = e % CB, k = e / CB;   // Linv[j + k*64]
-        sL[k * 68 + j] = Linv[j + k * CB];
+        sL[k * 68 + j] = Linv[j + k * ldinv];
     }
 #pragma unroll 8
     for (int e = tid; e < CB * 128; e += 256) {
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) trsm_mult_kernel(T *B, int64_t ldb, int64
 }  // namespace
 
 template <typename T>
-void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64_t *d_info) {
+static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64_t *d_info) {
     LFB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int64_t), h.stream));
     if (n <= 0) return;
     const size_t smem_p = sizeof(T) * (2 * CB * SP + 32 * SP);
@@ -409,6 +409,16 @@ void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64
         }
     }
     if (clean) triangular_zero<T>(h, A, n, ld, /*keep_lower=*/1);
+}
+
+template <typename T>
+void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64_t *d_info) {
+    // A "diagonal first" driver (side stream factors only the nb x nb diagonal block and builds L11^-1 by block doubling,
+    // rows below solved by one GEMM with the explicit inverse) was built and measured in round 2: 64.4 ms against 58.0 ms
+    // for this driver at n = 16384 (18.7 vs 13.5 ms at 8192) -- its diagonal chain is 8 potf2 + 30 tiny GEMMs of 19-39 us
+    // each, ~1 ms per 512 columns, longer than what it removes.  Numbers in profiles/r2_chol_analysis.md; the code was
+    // dropped rather than kept as a slower option.
+    cholesky_lower_v1<T>(h, A, n, ld, clean, d_info);
 }
 
 // Device time (us per launch) of one diagonal-block kernel on a 64 x 64 SPD block: kind 0 = left-looking (first
