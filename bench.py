@@ -628,6 +628,67 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         torch.cuda.empty_cache()
     except Exception as ex:  # keep the headline line alive
         out["qr_f64"] = {"error": str(ex)[:200]}
+    # ---- f32 engine: Cholesky / QR 16384^2 f32, trailing updates on tcgen05 3xTF32 (csrc/gemm_tf32.cu); replicas ----
+    try:
+        n = args.n
+        pk = C.c_double(0)
+        lib.lfb_microbench_fp64(eng.h, 2, C.byref(pk))
+        ffma_peak = pk.value / 1e3
+        gen = torch.Generator(device=dev).manual_seed(0x1F2E3D4C + 6 + rank)
+        F0 = torch.rand((n, n), dtype=torch.float32, device=dev, generator=gen).mul_(2).sub_(1)
+        Fw = torch.empty_like(F0)
+        fd = torch.empty(n, dtype=torch.float32, device=dev)
+        finfo = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def qrf_step():
+            Fw.copy_(F0)
+            st = lib.lfb_qr_dev_f32(eng.h, C.c_void_p(Fw.data_ptr()), n, n, n, C.c_void_p(fd.data_ptr()))
+            if st != 0:
+                raise RuntimeError(f"lfb_qr_dev_f32 status {st}")
+        ms = timed(qrf_step, 2, 1) / 2
+        k = min(2048, n)
+        Rk = (torch.triu(Fw[:k, :k].t(), 1) + torch.diag(fd[:k].abs())).double()
+        AtA = F0[:k, :].double() @ F0[:k, :].double().t()
+        rtr = float((Rk.t() @ Rk - AtA).norm() / AtA.norm())
+        fl = 4.0 / 3.0 * n ** 3
+        out["qr_f32"] = {"workload": f"QR {n}x{n} f32", "ms_per_step": ms, "gflops": world * fl / (ms * 1e-3) / 1e9,
+                         "ffma_peak_tflops": ffma_peak, "frac_of_ffma_peak": fl / (ms * 1e-3) / 1e12 / ffma_peak,
+                         "trailing_update": "tcgen05.mma.kind::tf32, 3xTF32 split, TMEM accumulator promoted every 64 k (csrc/gemm_tf32.cu)",
+                         "check": {"RtR_vs_AtA_block2048": rtr}, "check_ok": rtr <= 8 * n * 1.2e-7}
+        F0.copy_((F0 + F0.t()) * 0.5)
+        F0.diagonal().add_(float(n))
+
+        def cholf_step():
+            Fw.copy_(F0)
+            st = lib.lfb_cholesky_dev_f32(eng.h, C.c_void_p(Fw.data_ptr()), n, n, 0, C.c_void_p(finfo.data_ptr()))
+            if st != 0:
+                raise RuntimeError(f"lfb_cholesky_dev_f32 status {st}")
+        ms = timed(cholf_step, 3, 1) / 3
+        Lf = torch.triu(Fw[:k, :k]).t().double()
+        Sd = F0[:k, :k].double()
+        cres = float((Lf @ Lf.t() - Sd).norm() / Sd.norm())
+        fl = n ** 3 / 3.0
+        out["chol_f32"] = {"workload": f"Cholesky {n}x{n} f32", "ms_per_step": ms, "gflops": world * fl / (ms * 1e-3) / 1e9,
+                           "ffma_peak_tflops": ffma_peak, "frac_of_ffma_peak": fl / (ms * 1e-3) / 1e12 / ffma_peak,
+                           "check": {"residual_block2048": cres}, "check_ok": cres <= 8 * n * 1.2e-7 and int(finfo.item()) == 0}
+        # the trailing-update kernel alone on the SYRK shape of the factorisation (TN, K = 512)
+        kk = 512
+        Pa = torch.rand((n, kk), dtype=torch.float32, device=dev, generator=gen).sub_(0.5)
+        Cc = torch.zeros((n, n), dtype=torch.float32, device=dev)
+
+        def gemm_step():
+            lib.lfb_gemm_dev_f32(eng.h, 1, 0, n, n, kk, 1.0, C.c_void_p(Pa.data_ptr()), kk, C.c_void_p(Pa.data_ptr()), kk, 0.0,
+                                 C.c_void_p(Cc.data_ptr()), n)
+        ms_g = timed(gemm_step, 5, 2) / 5
+        tf = 2.0 * n * n * kk / (ms_g * 1e-3) / 1e12
+        ref = Pa[:256].double() @ Pa[:256].double().t()
+        gerr = float((Cc[:256, :256].double() - ref).abs().max())
+        out["sgemm_tc"] = {"workload": f"f32 TN GEMM {n}x{n}x{kk} (3xTF32 on tcgen05)", "tflops": tf, "frac_of_ffma_peak": tf / ffma_peak,
+                           "check": {"max_abs_err_vs_f64": gerr}, "check_ok": gerr <= 2e-6 * kk}
+        del F0, Fw, Pa, Cc
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["f32_engine"] = {"error": str(ex)[:200]}
     # ---- C3: batched 32x32 f32 QR, batch-sharded (strong scaling) ----
     try:
         B = 262144

@@ -287,7 +287,7 @@ int lfb_profile_end(lfb_handle *h, double *gemm_ms, double *gemm_flops, int64_t 
 int lfb_debug_panel_phases(lfb_handle *h, long long *out4);
 
 /* ---- micro-benchmarks used by bench.py to measure the FP64 pipe ceiling in the same run ------- */
-/* kind: 0 = DFMA register chain, 1 = DMMA.8x8x4 (mma.sync f64).  Returns achieved GFLOP/s. */
+/* kind: 0 = DFMA register chain, 1 = DMMA.8x8x4 (mma.sync f64), 2 = FP32 FFMA register chain.  Returns achieved GFLOP/s. */
 int lfb_microbench_fp64(lfb_handle *h, int kind, double *gflops);
 /* Device time (us per launch, CUDA events, back-to-back launches) of one internal kernel on an n x n f64
  * problem: "trd_symv" (lower-triangle SYMV of the tridiagonalisation), "trd_head" (its cluster kernel),

@@ -50,7 +50,7 @@ int qr_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t
     if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");           // qr.rs:34-36
     if (cols == 0) return LFB_OK;                                                            // 0x0 legal, qr.rs:383-388
     LFB_API_BEGIN(h)
-    const int64_t ld = round_up(rows, 2);
+    const int64_t ld = round_up(rows, 4);     // 16-byte columns for TMA in both precisions
     DevBuf<T> dA(*h, (size_t)ld * cols), dD(*h, cols);
     upload<T>(*h, a, rows, cols, rs, cs, dA, ld);
     if (tsqr_route(*h, rows, cols, force_tsqr)) qr_tsqr<T>(*h, dA, rows, cols, ld, dD);
@@ -102,7 +102,7 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
     if (n == 0) return LFB_OK;                                                               // cholesky.rs:270-272
     int64_t info = 0;
     LFB_API_BEGIN(h)
-    const int64_t ld = round_up(n, 2);
+    const int64_t ld = round_up(n, 4);      // 16-byte columns for TMA in both precisions
     DevBuf<T> dA(*h, (size_t)ld * n);
     DevBuf<int64_t> dInfo(*h, 1);
     // The reference reads (and, for the dirty variant, writes) ONLY the lower triangle
@@ -663,7 +663,7 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     const Opt table[] = {
         {"qr_nb", &o.qr_nb, 32, 1024}, {"qr_sub", &o.qr_sub, 1, 32}, {"chol_base", &o.chol_base, 1, 64},
         {"chol_nb", &o.chol_nb, 64, 8192}, {"chol_tn", &o.chol_tn, 0, 1}, {"chol_potf2_rl", &o.chol_potf2_rl, 0, 1}, {"gemm_tma", &o.gemm_tma, 0, 1}, {"gemm_splitk", &o.gemm_splitk, 0, 1}, {"gemm_deterministic", &o.gemm_deterministic, 0, 1}, {"tsqr_cholqr_cond", &o.tsqr_cholqr_cond, 0, 1 << 20},
-        {"gemm_v2", &o.gemm_v2, 0, 1}, {"gemm_split_waves", &o.gemm_split_waves, 1, 64}, {"panel_cluster", &o.panel_cluster, 0, 2},
+        {"gemm_v2", &o.gemm_v2, 0, 1}, {"sgemm_tc", &o.sgemm_tc, 0, 2}, {"gemm_split_waves", &o.gemm_split_waves, 1, 64}, {"panel_cluster", &o.panel_cluster, 0, 2},
         {"panel_cluster_max", &o.panel_cluster_max, 1, 16}, {"lookahead", &o.lookahead, 0, 1}, {"tsqr_chunk", &o.tsqr_chunk, 64, BIG},
         {"batched_quad", &o.batched_quad, 0, 4}, {"tsqr_streams", &o.tsqr_streams, 1, 64}, {"tsqr_graph", &o.tsqr_graph, 0, 1},
         {"qr_tsqr_auto", &o.qr_tsqr_auto, 0, 1}, {"trd_fused", &o.trd_fused, 0, 1}, {"chol_overlap_d2h", &o.chol_overlap_d2h, 0, 1},

@@ -50,6 +50,7 @@ struct Options {
     int64_t gemm_splitk = 1; // allow split-K for skinny-output GEMMs
     int64_t gemm_deterministic = 1; // split-K partial tiles summed in a fixed order by a reduce kernel (0 = atomicAdd epilogue)
     int64_t gemm_split_waves = 6; // target waves of (tile, split-K) work items for skinny outputs
+    int64_t sgemm_tc = 1;    // f32 TN products >= 128 x 128 x 32: 1 = tcgen05 3xTF32 (TMEM accumulator), 2 = single-pass TF32 (yard-stick only), 0 = FFMA kernel
     int64_t gemm_v2 = 1;     // 16-warp cp.async DGEMM when operands are 16-byte aligned
     int64_t panel_cluster = 2; // cluster/DSMEM panel kernel: 2 = second generation, 1 = first, 0 = per-column launches
     int64_t lookahead = 1;     // factor the next panel on a side stream while the trailing update runs

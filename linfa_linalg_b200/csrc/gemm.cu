@@ -519,6 +519,10 @@ static void dgemm_impl(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int6
     else launch_dgemm<1, 1>(h, p, grid);
 }
 
+// Defined in gemm_tf32.cu (tcgen05 / TMEM, 3xTF32): returns true if it handled the call.
+bool sgemm_tc_try(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t lda,
+                  const float *B, int64_t ldb, float beta, float *C, int64_t ldc, int lower_only);
+
 template <>
 void gemm<float>(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
                  int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc, int lower_only) {
@@ -531,6 +535,17 @@ void gemm<float>(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int64_t K,
         }
         return;
     }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h.prof_on) {
+        e0 = h.prof_event(); e1 = h.prof_event();
+        LFB_CUDA(cudaEventRecord(e0, h.stream));
+        h.prof_flops += (lower_only ? 1.0 : 2.0) * (double)M * (double)N * (double)K;
+    }
+    struct ProfEnd {   // closes the profiler's event pair on every exit path
+        lfb_handle &h; cudaEvent_t e;
+        ~ProfEnd() { if (e) cudaEventRecord(e, h.stream); }
+    } prof_end{h, e1};
+    if (sgemm_tc_try(h, ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower_only)) return;
     SgemmP p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.a_sm = ta ? lda : 1; p.a_sk = ta ? 1 : lda;

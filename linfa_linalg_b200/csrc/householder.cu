@@ -537,13 +537,16 @@ void build_t(lfb_handle &h, const T *V, int64_t ldv, int64_t rows, int nb, T *G,
 }
 
 // C (rows x ncols, ldc) <- (I - V op(T) V^T) C,  op(T) = T^T if trans_t.  W1/W2: nb x ncols scratch.
+// Vt (optional): V^T stored nb x rows (leading dimension ldvt), so that the rank-nb update is a K-major ("TN") product
+// on both sides -- the only operand layout of the f32 tensor-core kernel (gemm_tf32.cu).
 template <typename T>
 void apply_block_reflector(lfb_handle &h, const T *V, int64_t ldv, int64_t rows, int nb, const T *Tm, int64_t ldt,
-                           int trans_t, T *C, int64_t ldc, int64_t ncols, T *W1, T *W2) {
+                           int trans_t, T *C, int64_t ldc, int64_t ncols, T *W1, T *W2, const T *Vt = nullptr, int64_t ldvt = 0) {
     if (ncols <= 0 || rows <= 0) return;
     gemm<T>(h, 1, 0, nb, ncols, rows, T(1), V, ldv, C, ldc, T(0), W1, nb);          // W1 = V^T C
     gemm<T>(h, trans_t, 0, nb, ncols, nb, T(1), Tm, ldt, W1, nb, T(0), W2, nb);     // W2 = op(T) W1
-    gemm<T>(h, 0, 0, rows, ncols, nb, T(-1), V, ldv, W2, nb, T(1), C, ldc);         // C -= V W2
+    if (Vt) gemm<T>(h, 1, 0, rows, ncols, nb, T(-1), Vt, ldvt, W2, nb, T(1), C, ldc);   // C -= (V^T)^T W2
+    else gemm<T>(h, 0, 0, rows, ncols, nb, T(-1), V, ldv, W2, nb, T(1), C, ldc);    // C -= V W2
 }
 
 // Unblocked-in-sub-panel Householder on columns [c0, c0+w) of A (m x ., ld), rows >= c0.
@@ -626,7 +629,11 @@ template <typename T>
 static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld, T *beta) {
     const int NB = (int)std::max<int64_t>(W, std::min<int64_t>(h.opt.qr_nb, 256));
     const int SUB = (int)std::max<int64_t>(1, std::min<int64_t>(h.opt.qr_sub, W));
-    const int64_t ldv = round_up(m, 2);
+    const int64_t ldv = round_up(m, 4);     // 16-byte columns for TMA in both precisions
+    // f32 with the tensor-core GEMM: a transposed copy of every finished panel's V (nb x rows, K-major) for C -= V W
+    const bool use_vt = sizeof(T) == 4 && h.opt.sgemm_tc != 0 && m >= 256 && n > NB;
+    DevBuf<T> Vt0(h, use_vt ? (size_t)NB * ldv : 1), Vt1(h, use_vt ? (size_t)NB * ldv : 1);
+    T *Vtbuf[2] = {use_vt ? Vt0.get() : nullptr, use_vt ? Vt1.get() : nullptr};
     // two generations of the panel workspaces (V, T): with look-ahead panel k+1 is factored while the
     // trailing update of panel k still reads V_k / T_k
     DevBuf<T> Vb0(h, (size_t)ldv * NB), Vb1(h, (size_t)ldv * NB);
@@ -639,7 +646,7 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
 
     // Factors panel [k0, k0+nb) on the handle's current stream; stages V (rows from k0) and, if the
     // panel has a trailing matrix, builds its compact-WY T.
-    auto factor_panel = [&](int64_t k0, int nb, T *V, T *Tm) {
+    auto factor_panel = [&](int64_t k0, int nb, T *V, T *Tm, T *Vt) {
         bool v_staged = true;   // the cluster kernels stage V as they go
         for (int s0 = 0; s0 < nb;) {
             const int64_t c0 = k0 + s0;
@@ -677,12 +684,13 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
             const int64_t rows = m - k0;
             if (!v_staged) copy_v<T>(h, A, ld, k0, k0, rows, nb, beta, V, ldv);
             build_t<T>(h, V, ldv, rows, nb, G, Tm, NB);
+            if (Vt) transpose<T>(h, V, rows, nb, ldv, Vt, NB);
         }
     };
 
     cudaStream_t sm = h.stream, sp = h.aux_stream;
     const bool la = h.opt.lookahead && sp != nullptr && !h.prof_on && n >= 4 * NB;
-    factor_panel(0, (int)std::min<int64_t>(NB, n), Vbuf[0], Tbuf[0]);
+    factor_panel(0, (int)std::min<int64_t>(NB, n), Vbuf[0], Tbuf[0], Vtbuf[0]);
     int cur = 0;
     for (int64_t k0 = 0; k0 < n; k0 += NB, cur ^= 1) {
         const int nb = (int)std::min<int64_t>(NB, n - k0);
@@ -694,12 +702,12 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
         if (la) {
             // trailing update of the NEXT panel's columns first, then factor that panel on the side
             // stream while the rest of the trailing matrix is updated here
-            apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C, ld, nbn, W1, W2);
+            apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C, ld, nbn, W1, W2, Vtbuf[cur], NB);
             LFB_CUDA(cudaEventRecord(h.ev[2], sm));
             LFB_CUDA(cudaStreamWaitEvent(sp, h.ev[2], 0));
             h.stream = sp;
             try {
-                factor_panel(k0 + nb, nbn, Vbuf[cur ^ 1], Tbuf[cur ^ 1]);
+                factor_panel(k0 + nb, nbn, Vbuf[cur ^ 1], Tbuf[cur ^ 1], Vtbuf[cur ^ 1]);
             } catch (...) {
                 h.stream = sm;
                 throw;
@@ -707,11 +715,11 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
             LFB_CUDA(cudaEventRecord(h.ev[3], sp));
             h.stream = sm;
             if (trail > nbn)
-                apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C + (int64_t)nbn * ld, ld, trail - nbn, W1, W2);
+                apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C + (int64_t)nbn * ld, ld, trail - nbn, W1, W2, Vtbuf[cur], NB);
             LFB_CUDA(cudaStreamWaitEvent(sm, h.ev[3], 0));
         } else {
-            apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C, ld, trail, W1, W2);
-            factor_panel(k0 + nb, nbn, Vbuf[cur ^ 1], Tbuf[cur ^ 1]);
+            apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C, ld, trail, W1, W2, Vtbuf[cur], NB);
+            factor_panel(k0 + nb, nbn, Vbuf[cur ^ 1], Tbuf[cur ^ 1], Vtbuf[cur ^ 1]);
         }
     }
 }

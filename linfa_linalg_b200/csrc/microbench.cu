@@ -38,6 +38,21 @@ __global__ void __launch_bounds__(256) dmma_kernel(double *out, int iters, doubl
     if (s == 123.456) out[0] = s;
 }
 
+// kind 2: the FP32 FFMA ceiling (the denominator the f32 trailing updates are reported against)
+__global__ void __launch_bounds__(256) ffma_kernel(float *out, int iters, float a, float b) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 1e-3f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 123.456f) out[0] = s;
+}
+
 }  // namespace
 
 double microbench_fp64(lfb_handle &h, int kind) {
@@ -51,6 +66,7 @@ double microbench_fp64(lfb_handle &h, int kind) {
     for (int rep = 0; rep < 4; ++rep) {
         LFB_CUDA(cudaEventRecord(e0, h.stream));
         if (kind == 0) dfma_kernel<<<blocks, 256, 0, h.stream>>>(out, iters, 0.999999, 1e-9);
+        else if (kind == 2) ffma_kernel<<<blocks, 256, 0, h.stream>>>(reinterpret_cast<float *>(out.get()), iters * 4, 0.999999f, 1e-9f);
         else dmma_kernel<<<blocks, 256, 0, h.stream>>>(out, iters, 0.999999, 1e-9);
         LFB_LAUNCH_CHECK(h);
         LFB_CUDA(cudaEventRecord(e1, h.stream));
@@ -63,6 +79,7 @@ double microbench_fp64(lfb_handle &h, int kind) {
     cudaEventDestroy(e1);
     double flops;
     if (kind == 0) flops = 2.0 * 16 * (double)iters * 256.0 * blocks;            // 1 FMA per lane per op
+    else if (kind == 2) flops = 2.0 * 16 * (double)iters * 4 * 256.0 * blocks;
     else flops = 2.0 * 256.0 * 16 * (double)iters * 8.0 * blocks;               // 8x8x4 MACs per warp-op, 8 warps/CTA
     return flops / (best * 1e-3) / 1e9;
 }

@@ -360,7 +360,7 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
     // side stream while the main stream still reads panel k's copy.
     cudaStream_t sm = h.stream, sp = h.aux_stream;
     const bool la = h.opt.lookahead && sp != nullptr && !h.prof_on && n >= 4 * NB;
-    const bool tn = sizeof(T) == 8 && h.opt.chol_tn && n >= 2 * NB;
+    const bool tn = (sizeof(T) == 8 || h.opt.sgemm_tc != 0) && h.opt.chol_tn && n >= 2 * NB;   // f32: the tcgen05 kernel is TN only
     const int64_t ldpt = NB;
     std::unique_ptr<DevBuf<T>> PtBuf[2];
     if (tn)
