@@ -41,6 +41,7 @@ struct CudaError : std::runtime_error {
 
 struct Options {
     int64_t qr_nb = 128;     // outer panel width of blocked compact-WY QR
+    int64_t qr_nb_f32 = 256; // same for f32 when the trailing updates run on the tcgen05 kernel (n >= 2048)
     int64_t qr_sub = 32;     // inner BLAS-2 sub-panel width (<= 32)
     int64_t chol_base = 64;  // recursion base of Cholesky / TRSM (<= 64)
     int64_t chol_nb = 512;   // right-looking panel width of Cholesky (K of the trailing SYRK)

@@ -297,15 +297,29 @@ sgemm_tf32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
         const int m = m0 + 32 * q + lane;
         const float alpha = p.alpha, beta = p.zstride ? 0.f : p.beta;
-        float *__restrict__ C = p.C + (int64_t)blockIdx.z * p.zstride;
+        float *C = p.C + (int64_t)blockIdx.z * p.zstride;
         if (m < p.M) {
+            // lanes = consecutive rows: every access below is a coalesced 128-byte line per warp.  The old values of C are
+            // fetched 32 columns at a time BEFORE any store of the group: a load-store-load chain (the compiler cannot
+            // prove that the columns do not alias) made the epilogue 128 dependent DRAM round trips per thread, 90 us per
+            // tile with beta = 1 (profiles/r2_f32_tc.md).
 #pragma unroll
-            for (int j = 0; j < BN; ++j) {
-                const int n = n0 + j;
-                if (n < p.N && (!p.lower_only || m >= n)) {
-                    float *cp = C + m + (int64_t)n * p.ldc;       // lanes = consecutive rows: coalesced
-                    const float r = alpha * acc[j];
-                    *cp = beta == 0.f ? r : fmaf(beta, *cp, r);
+            for (int g = 0; g < BN / 32; ++g) {
+                float old[32];
+                if (beta != 0.f) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + 32 * g + j;
+                        old[j] = (n < p.N && (!p.lower_only || m >= n)) ? C[m + (int64_t)n * p.ldc] : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + 32 * g + j;
+                    if (n < p.N && (!p.lower_only || m >= n)) {
+                        const float r = alpha * acc[32 * g + j];
+                        C[m + (int64_t)n * p.ldc] = beta == 0.f ? r : fmaf(beta, old[j], r);
+                    }
                 }
             }
         }

@@ -32,6 +32,12 @@ if kind == "chol":
     info = torch.zeros(1, dtype=torch.int64, device=dev)
     step = lambda: (W.copy_(S), lib.lfb_cholesky_dev_f64(eng.h, p(W), n, n, 0, p(info)))
     flops = n ** 3 / 3
+elif kind == "qrf":
+    A = torch.rand((n, m), dtype=torch.float32, device=dev, generator=g) * 2 - 1   # column-major m x n
+    W = torch.empty_like(A)
+    d = torch.zeros(n, dtype=torch.float32, device=dev)
+    step = lambda: (W.copy_(A), lib.lfb_qr_dev_f32(eng.h, p(W), m, n, m, p(d)))
+    flops = 2.0 * m * n * n - 2.0 / 3.0 * n ** 3
 elif kind in ("qr", "tsqr"):
     A = torch.rand((n, m), dtype=torch.float64, device=dev, generator=g) * 2 - 1   # column-major m x n
     W = torch.empty_like(A)
