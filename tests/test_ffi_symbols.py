@@ -132,3 +132,15 @@ def test_set_option_validates_ranges():
     from linfa_linalg_b200 import _ffi
     lib = _ffi.load()
     assert lib.lfb_set_option(None, b"chol_nb", 512) == _ffi.INVALID_ARGUMENT
+
+
+def test_rust_shim_declares_only_exported_symbols():
+    """rust/src/ffi.rs (the shim a linfa-linalg maintainer adds; not compiled here: no rustc in the image) must only name
+    symbols that the header declares and the library exports."""
+    from linfa_linalg_b200 import _ffi
+    src = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    names = set(re.findall(r"\b(lfb_[a-z0-9_]+)\b", src)) - {"lfb_handle", "lfb_multi"}
+    declared = set(_declared())
+    assert names and names <= declared, sorted(names - declared)
+    lib = C.CDLL(_ffi.LIB_PATH)
+    assert all(hasattr(lib, n) for n in names)
