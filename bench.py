@@ -775,7 +775,7 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         fl = 2.0 * rows_total * cols * cols - 2.0 / 3.0 * cols ** 3
         # correctness of the timed result: R^T R = A^T A (all-reduced Gram matrix of the row shards), ||R||_F = ||A||_F,
         # diag(R) >= 0 and strict lower triangle exactly zero (qr.rs:93-96)
-        Rm = rres["r"].t()                                    # math R (the tensor is its column-major storage)
+        Rm = rres["r"].t().clone()                            # math R (the tensor is its column-major storage; the callable reuses it)
         gram = T0 @ T0.t()
         if world > 1:
             dist.all_reduce(gram)
