@@ -254,7 +254,7 @@ int lfb_qr_tsqr_dev_f32(lfb_handle *h, float *d_a, int64_t rows, int64_t cols, i
  *   reconstruct_rows: d_q (rows x n, any rows below the top block) <- d_q * U'^-1  == the reflector rows */
 int lfb_tsqr_explicit_q_dev_f64(lfb_handle *h, double *d_a, int64_t rows, int64_t cols, int64_t ld, double *d_r, int64_t ldr);
 /* The Cholesky-QR leaf on its own (csrc/cholqr.cu): R (cols x cols upper, diag >= 0) and R^-1 of a tall block from its Gram
- * matrix, d_a NOT modified.  *ok = 1 if the leaf accepted the block (Cholesky succeeded and cond_1(R) <= option
+ * matrix, d_a NOT modified.  *ok = 1 if the leaf accepted the block (Cholesky succeeded and the cond_2(R) bound <= option
  * "tsqr_cholqr_cond"), else 0 and nothing is written: the caller then takes lfb_tsqr_explicit_q_dev_f64.  Synchronises the
  * stream (the decision is made on the host).  With it a row-sharded caller folds everything after the leaf into n x n
  * products: rows <- rows * (R_i^-1 Qs_i U'^-1)  (linfa_linalg_b200/dist.py: tsqr_qr, csrc/multi.cu). */

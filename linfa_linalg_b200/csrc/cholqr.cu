@@ -8,7 +8,7 @@
 //     G = L L^T   (n x n Cholesky, potrf.cu),   R = L^T,   R^-1 = (L^-1)^T
 //
 // with forward error ~ cond(A)^2 eps instead of cond(A) eps.  So the leaf is GUARDED: it is taken only when the Cholesky
-// succeeds and cond_1(L) = ||L||_1 ||L^-1||_1 <= `tsqr_cholqr_cond` (default 16: a loss of at most 256 eps, inside every
+// succeeds and the bound sqrt(||L||_1 ||L||_inf ||L^-1||_1 ||L^-1||_inf) >= cond_2(A) is <= `tsqr_cholqr_cond` (default 16: a loss of at most 256 eps, inside every
 // parity tolerance of the suite); anything else -- rank deficiency, graded columns, ill-conditioning -- goes to the
 // Householder leaf unchanged (A is not modified by the attempt).  The guard costs one 32-byte D2H copy and a stream sync.
 // What the callers build on top (explicit Q = A R^-1, the reconstruction of the reference's reflectors) is in
@@ -18,42 +18,60 @@
 namespace lfb {
 namespace {
 
-// One CTA: cond_1 of the lower-triangular L (ld) from L and X = L^-1, smallest diagonal entry, finiteness.
-// out[0] = ||L||_1 ||X||_1, out[1] = min diag, out[2] = 1 if every entry read was finite.
+// One CTA: an upper bound of cond_2(L) from L (lower triangular, ld) and X = L^-1,
+//   cond_2 <= sqrt(||L||_1 ||L||_inf ||X||_1 ||X||_inf)      (||M||_2^2 <= ||M||_1 ||M||_inf),
+// the smallest diagonal entry and finiteness.  Warp per column, lanes down the rows (coalesced); row sums through
+// shared-memory atomics.  out[0] = the bound, out[1] = min diag, out[2] = 1 if every entry read was finite.
 template <typename T>
-__global__ void __launch_bounds__(512) cholqr_guard_kernel(const T *__restrict__ Lm, const T *__restrict__ X, int64_t ld, int n, double *out) {
-    __shared__ double s_l[512], s_x[512], s_d[512];
-    __shared__ int s_ok[512];
-    const int tid = threadIdx.x;
+__global__ void __launch_bounds__(1024) cholqr_guard_kernel(const T *__restrict__ Lm, const T *__restrict__ X, int64_t ld, int n, double *out) {
+    __shared__ double rowL[1024], rowX[1024];
+    __shared__ double colL[32], colX[32], dmin[32];
+    __shared__ int okf[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += 1024) rowL[i] = rowX[i] = 0.0;
+    __syncthreads();
     double ml = 0.0, mx = 0.0, md = 1e300;
     int ok = 1;
-    for (int c = tid; c < n; c += 512) {
+    for (int c = warp; c < n; c += 32) {
         double sl = 0.0, sx = 0.0;
-        for (int r = c; r < n; ++r) {
-            const double l = (double)Lm[r + (int64_t)c * ld], x = (double)X[r + (int64_t)c * ld];
-            sl += fabs(l);
-            sx += fabs(x);
+        for (int r = c + lane; r < n; r += 32) {
+            const double l = fabs((double)Lm[r + (int64_t)c * ld]), x = fabs((double)X[r + (int64_t)c * ld]);
+            sl += l;
+            sx += x;
+            atomicAdd(&rowL[r], l);
+            atomicAdd(&rowX[r], x);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sl += __shfl_xor_sync(0xffffffffu, sl, o);
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
         }
         if (!isfinite(sl) || !isfinite(sx)) ok = 0;
         ml = fmax(ml, sl);
         mx = fmax(mx, sx);
         md = fmin(md, (double)Lm[c + (int64_t)c * ld]);
     }
-    s_l[tid] = ml; s_x[tid] = mx; s_d[tid] = md; s_ok[tid] = ok;
+    if (lane == 0) { colL[warp] = ml; colX[warp] = mx; dmin[warp] = md; okf[warp] = ok; }
     __syncthreads();
-    for (int s = 256; s > 0; s >>= 1) {
-        if (tid < s) {
-            s_l[tid] = fmax(s_l[tid], s_l[tid + s]);
-            s_x[tid] = fmax(s_x[tid], s_x[tid + s]);
-            s_d[tid] = fmin(s_d[tid], s_d[tid + s]);
-            s_ok[tid] &= s_ok[tid + s];
+    if (warp == 0) {
+        double rl = 0.0, rx = 0.0;
+        for (int i = lane; i < n; i += 32) { rl = fmax(rl, rowL[i]); rx = fmax(rx, rowX[i]); }
+        double cl = colL[lane], cx = colX[lane], dm = dmin[lane];
+        int k = okf[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            rl = fmax(rl, __shfl_xor_sync(0xffffffffu, rl, o));
+            rx = fmax(rx, __shfl_xor_sync(0xffffffffu, rx, o));
+            cl = fmax(cl, __shfl_xor_sync(0xffffffffu, cl, o));
+            cx = fmax(cx, __shfl_xor_sync(0xffffffffu, cx, o));
+            dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+            k &= __shfl_xor_sync(0xffffffffu, k, o);
         }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        out[0] = s_l[0] * s_x[0];
-        out[1] = s_d[0];
-        out[2] = (double)s_ok[0];
+        if (lane == 0) {
+            out[0] = sqrt(cl * rl * cx * rx);
+            out[1] = dm;
+            out[2] = (double)k;
+        }
     }
 }
 
@@ -82,7 +100,7 @@ bool cholqr_factor(lfb_handle &h, const T *A, int64_t rows, int64_t n, int64_t l
     cholesky_lower<T>(h, G.get(), n, ldg, /*clean=*/0, info.get());                            // G = L L^T (lower)
     fill<T>(h, X.get(), n, n, ldg, T(0), T(1));
     trsm_left<T>(h, /*lower=*/1, /*trans=*/0, n, n, G.get(), ldg, (const T *)nullptr, X.get(), ldg);   // X = L^-1
-    cholqr_guard_kernel<T><<<1, 512, 0, h.stream>>>(G.get(), X.get(), ldg, (int)n, guard.get());
+    cholqr_guard_kernel<T><<<1, 1024, 0, h.stream>>>(G.get(), X.get(), ldg, (int)n, guard.get());
     LFB_LAUNCH_CHECK(h);
     double hg[3] = {0, 0, 0};
     int64_t hinfo = 0;
