@@ -173,6 +173,22 @@ int lfb_apply_constraints_f32(lfb_handle *h, float *v, int64_t n, int64_t k, int
                               const float *cholesky_yy, int64_t m, int64_t l_rs, int64_t l_cs,
                               const float *y, int64_t y_rows, int64_t y_cols, int64_t y_rs, int64_t y_cs);
 
+/* lobpcg/algorithm.rs:16-44 generalized_eig / sorted_eig: the small dense eigenproblems of every LOBPCG iteration, as ONE call.
+ * a: k x k view; b: k x k view or NULL (then the plain problem).  order: 0 = the pair as `eigh_into` / `generalized_eig` return
+ * it (vals: k entries, vecs: k x k); 1 = Largest, 2 = Smallest: `sort_eig(order)` (eigh.rs:275-325), columns multiplied by the
+ * signum of their first entry (sign BIT, :40-41), truncated to `size` (vals: size entries, vecs: k x size).  Both eigen-
+ * decompositions, the k x k products between them, the sort's gather and the sign fix run on the device in one upload /
+ * download.  LFB_INVALID_ARGUMENT if an eigenvalue is NaN (the reference's sort panics). */
+int lfb_sorted_eig_f64(lfb_handle *h, const double *a, int64_t k, int64_t a_rs, int64_t a_cs, const double *b, int64_t b_rs, int64_t b_cs,
+                       int64_t size, int order, double *vals, double *vecs, int64_t v_rs, int64_t v_cs);
+int lfb_sorted_eig_f32(lfb_handle *h, const float *a, int64_t k, int64_t a_rs, int64_t a_cs, const float *b, int64_t b_rs, int64_t b_cs,
+                       int64_t size, int order, float *vals, float *vecs, int64_t v_rs, int64_t v_cs);
+/* The same on device-resident column-major operands (d_a, d_b consumed; d_b may be NULL); vals_host is HOST memory, d_vecs is
+ * k x size (k x k for order 0) on the device: with lfb_orthonormalize_dev_f64, lfb_apply_constraints_dev_f64 and lfb_gemm_dev_f64
+ * every n x k block of a LOBPCG iteration (algorithm.rs:193-417) stays in HBM -- tests/test_gpu_lobpcg_resident.py runs the loop. */
+int lfb_sorted_eig_dev_f64(lfb_handle *h, double *d_a, int64_t lda, double *d_b, int64_t ldb, int64_t k, int64_t size, int order,
+                           double *vals_host, double *d_vecs, int64_t ldv);
+
 /* ---- eigh.rs:202-268 EighInto / Eigh / EigValshInto / EigValsh (symmetric_eig, eigh.rs:10-129) ---------
  * a: n x n view (only read; the reference consumes `self`, nothing of it is observable afterwards).
  * vals: n contiguous entries, in the reference's own (unsorted) order -- EigSort stays host-side.

@@ -583,27 +583,40 @@ def sort_eig_desc(res):
     return sort_eig(res, LARGEST)
 
 
-# ---- lobpcg/algorithm.rs:16-44: the small dense eigenproblems of LOBPCG (host compositions over eigh) ----
+# ---- lobpcg/algorithm.rs:16-44: the small dense eigenproblems of LOBPCG, ONE library call each (lfb_sorted_eig) ----
+def _sorted_eig_call(a: np.ndarray, b, size: int, order_code: int, eng=None):
+    e = eng or engine()
+    k = _check_square(a)
+    if b is not None:
+        b = np.asarray(b, dtype=a.dtype)
+        if b.shape != a.shape:
+            raise ValueError(f"b has shape {b.shape}, expected {a.shape}")
+    nout = k if order_code == 0 else min(size, k)
+    vals = np.zeros(nout, dtype=a.dtype)
+    vecs = np.zeros((k, nout), dtype=a.dtype)
+    if k == 0:
+        return vals, vecs
+    it = a.itemsize
+    bp = (_vecp(b), b.strides[0] // it, b.strides[1] // it) if b is not None else (None, 0, 0)
+    vb, vq = (vals if nout else np.zeros(1, dtype=a.dtype)), (vecs if nout else np.zeros((k, 1), dtype=a.dtype))
+    st = e.call("lfb_sorted_eig" + _sfx(a), _vecp(a), k, a.strides[0] // it, a.strides[1] // it, *bp, size, order_code,
+                _vecp(vb), _vecp(vq), vq.strides[0] // it, vq.strides[1] // it)
+    if st == _ffi.INVALID_ARGUMENT:
+        raise ValueError("NaN values in array")          # cmp_floats panics (eigh.rs:326-328)
+    e._check(st)
+    return vals, vecs
+
+
 def generalized_eig(a: np.ndarray, b: np.ndarray, eng=None):
-    """lobpcg/algorithm.rs:16-25: pencil (A, B) through two `eigh_into` calls; the k x k products in between are
-    ndarray GEMMs in the reference and NumPy GEMMs here (k = a few block sizes)."""
-    vals_b, vecs_b = eigh_into(b, eng)
-    floor = a.dtype.type(np.float32(1e-10))                          # `A::from(1e-10f32)` (:18)
-    recip = 1.0 / np.sqrt(np.maximum(vals_b, floor))
-    vecs_b_tilde = vecs_b * recip                                    # Array2 * Array1: column j scaled by recip[j] (:19)
-    a_tilde = vecs_b_tilde.T @ (a @ vecs_b_tilde)                    # :20
-    vals_a, vecs_a = eigh_into(np.ascontiguousarray(a_tilde), eng)   # :21
-    return vals_a, vecs_b_tilde @ vecs_a                             # :22-24
+    """lobpcg/algorithm.rs:16-25: pencil (A, B) -> (vals_a, vecs_b~ vecs_a), unsorted; both eigendecompositions and the
+    k x k products between them run on the device in one call.  `a` and `b` are consumed, as in the reference."""
+    return _sorted_eig_call(a, b, a.shape[0], 0, eng)
 
 
 def sorted_eig(a: np.ndarray, b, size: int, order=LARGEST, eng=None):
     """lobpcg/algorithm.rs:28-44: full (generalized) eigenproblem, sorted by `order`, signs made deterministic by the
     first row (Rust's signum: the sign BIT), truncated to `size`.  `a` and `b` are consumed, as in the reference."""
-    res = generalized_eig(a, b, eng) if b is not None else eigh_into(a, eng)
-    vals, vecs = sort_eig(res, order)
-    s = np.where(np.signbit(vecs[0, :]), -1.0, 1.0).astype(vecs.dtype) if vecs.size else np.ones(0, dtype=vecs.dtype)
-    vecs = vecs * s
-    return vals[:size], vecs[:, :size]
+    return _sorted_eig_call(a, b, size, 1 if order == LARGEST else 2, eng)
 
 
 # ---- svd: src/svd.rs ---------------------------------------------------------------------------------

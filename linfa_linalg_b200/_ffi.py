@@ -54,6 +54,7 @@ _TYPED = {
     "lfb_svd": [_vp] + _VIEW + [_vp, _vp, _i64, _i64, _vp, _i64, _i64],
     "lfb_orthonormalize": [_vp] + _VIEW + [_vp, _i64, _i64, C.POINTER(_i64)],
     "lfb_apply_constraints": [_vp] + _VIEW + [_vp, _i64, _i64, _i64] + _VIEW,
+    "lfb_sorted_eig": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _int, _vp, _vp, _i64, _i64],
     "lfb_qr_batched": [_vp, _vp, _i64, _i64, _i64, _vp],
     "lfb_cholesky_batched": [_vp, _vp, _i64, _i64, _int, C.POINTER(_i64), C.POINTER(_i64)],
     "lfb_qr_dev": [_vp, _vp, _i64, _i64, _i64, _vp],
@@ -78,6 +79,7 @@ SIGNATURES.update({
     "lfb_hh_reconstruct_top_dev_f64": [_vp, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp],
     "lfb_hh_reconstruct_rows_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64],
     "lfb_orthonormalize_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp],
+    "lfb_sorted_eig_dev_f64": [_vp, _vp, _i64, _vp, _i64, _i64, _i64, _int, _vp, _vp, _i64],
     "lfb_apply_constraints_dev_f64": [_vp, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _vp, _i64],
     "lfb_gemm_dev_f64": [_vp, _int, _int, _i64, _i64, _i64, _dbl, _vp, _i64, _vp, _i64, _dbl, _vp, _i64],
     "lfb_gemm_dev_f32": [_vp, _int, _int, _i64, _i64, _i64, _flt, _vp, _i64, _vp, _i64, _flt, _vp, _i64],

@@ -423,6 +423,25 @@ int apply_constraints_host(lfb_handle *h, T *v, int64_t n, int64_t k, int64_t rs
     LFB_API_END(h)
 }
 
+// lobpcg/algorithm.rs:16-44 on host views: one upload, both eigendecompositions and the products between them on the device.
+template <typename T>
+int sorted_eig_host(lfb_handle *h, const T *a, int64_t k, int64_t a_rs, int64_t a_cs, const T *b, int64_t b_rs, int64_t b_cs, int64_t size,
+                    int order, T *vals, T *vecs, int64_t v_rs, int64_t v_cs) {
+    if (k < 0 || size < 0 || order < 0 || order > 2) return fail(h, LFB_INVALID_ARGUMENT, "bad arguments");
+    if (k == 0) return LFB_OK;
+    if (!vals || !vecs) return fail(h, LFB_INVALID_ARGUMENT, "null output");
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(k, 2);
+    const int64_t nout = order == 0 ? k : std::min(size, k);
+    DevBuf<T> dA(*h, (size_t)ld * k), dB(*h, b ? (size_t)ld * k : 1), dV(*h, (size_t)ld * std::max<int64_t>(nout, 1));
+    upload<T>(*h, a, k, k, a_rs, a_cs, dA, ld);
+    if (b) upload<T>(*h, b, k, k, b_rs, b_cs, dB, ld);
+    if (!sorted_eig_dev<T>(*h, dA, ld, b ? dB.get() : nullptr, ld, k, size, order, vals, dV, ld))
+        return fail(h, LFB_INVALID_ARGUMENT, "NaN values in array");
+    if (nout > 0) download<T>(*h, dV, ld, vecs, k, nout, v_rs, v_cs);
+    LFB_API_END(h)
+}
+
 template <typename T>
 int invc_host(lfb_handle *h, const T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, T *inv, int64_t i_rs, int64_t i_cs,
               int64_t *fail_index) {
@@ -747,6 +766,21 @@ LFB_SOLVE_ENTRIES(f32, float)
 LFB_LOBPCG_ENTRIES(f64, double)
 LFB_LOBPCG_ENTRIES(f32, float)
 #undef LFB_LOBPCG_ENTRIES
+int lfb_sorted_eig_f64(lfb_handle *h, const double *a, int64_t k, int64_t ars, int64_t acs, const double *b, int64_t brs, int64_t bcs, int64_t size,
+                       int order, double *vals, double *vecs, int64_t vrs, int64_t vcs) {
+    return sorted_eig_host<double>(h, a, k, ars, acs, b, brs, bcs, size, order, vals, vecs, vrs, vcs);
+}
+int lfb_sorted_eig_f32(lfb_handle *h, const float *a, int64_t k, int64_t ars, int64_t acs, const float *b, int64_t brs, int64_t bcs, int64_t size,
+                       int order, float *vals, float *vecs, int64_t vrs, int64_t vcs) {
+    return sorted_eig_host<float>(h, a, k, ars, acs, b, brs, bcs, size, order, vals, vecs, vrs, vcs);
+}
+int lfb_sorted_eig_dev_f64(lfb_handle *h, double *d_a, int64_t lda, double *d_b, int64_t ldb, int64_t k, int64_t size, int order,
+                           double *vals_host, double *d_vecs, int64_t ldv) {
+    if (k < 0 || size < 0 || order < 0 || order > 2 || (k > 0 && (!vals_host || !d_vecs || !d_a))) return fail(h, LFB_INVALID_ARGUMENT, "bad arguments");
+    LFB_API_BEGIN(h)
+    if (!sorted_eig_dev<double>(*h, d_a, lda, d_b, ldb, k, size, order, vals_host, d_vecs, ldv)) return fail(h, LFB_INVALID_ARGUMENT, "NaN values in array");
+    LFB_API_END(h)
+}
 int lfb_orthonormalize_dev_f64(lfb_handle *h, double *d_v, int64_t rows, int64_t cols, int64_t ld, double *d_l, int64_t ldl,
                                int64_t *d_info) {
     if (rows < 0 || cols < 0 || !d_info) return fail(h, LFB_INVALID_ARGUMENT, "bad arguments");

@@ -251,6 +251,9 @@ template <typename T> void trsm_right(lfb_handle &h, int64_t rows, int64_t n, co
 template <typename T> void orthonormalize(lfb_handle &h, T *V, int64_t rows, int64_t cols, int64_t ld, T *Lm, int64_t ldl, int64_t *d_info);
 template <typename T> void apply_constraints(lfb_handle &h, T *V, int64_t n, int64_t k, int64_t ldv, const T *Lyy, int64_t m, int64_t ldl,
                                              const T *Y, int64_t ldy);
+// lobpcg/algorithm.rs:16-44 on device-resident k x k operands (lobpcg_blocks.cu); false if an eigenvalue is NaN.
+template <typename T> bool sorted_eig_dev(lfb_handle &h, T *dA, int64_t lda, T *dB, int64_t ldb, int64_t k, int64_t size, int order, T *vals_host,
+                                          T *dVecs, int64_t ldv);
 // Householder reconstruction (tsqr_hr.cu): top n x n block of an explicit Q -> reference compact form; U' for the rows below.
 template <typename T> void hh_reconstruct_top(lfb_handle &h, T *Qtop, int64_t n, int64_t ld, const T *R, int64_t ldr, T *U, int64_t ldu, T *diag);
 // Tall-skinny thin QR in the reference's compact form (identical contract to qr_factor) via TSQR + reconstruction.

@@ -81,6 +81,33 @@ class OracleEngine:
     def close(self):
         pass
 
+    # -- lobpcg/algorithm.rs:16-44 -----------------------------------------------------------------------------
+    def _sorted_eig(self, sfx, a, k, a_rs, a_cs, b, b_rs, b_cs, size, order, vals, vecs, v_rs, v_cs):
+        if k == 0:
+            return OK
+        am = np.array(_mat(a, k, k, a_rs, a_cs, sfx))
+        if _addr(b):
+            bm = np.array(_mat(b, k, k, b_rs, b_cs, sfx))
+            vb, qb = O.symmetric_eig(bm, vectors=True)                                   # :17
+            floor = am.dtype.type(np.float32(1e-10))
+            qb = qb * (1.0 / np.sqrt(np.maximum(vb, floor))).astype(am.dtype)            # :18-19
+            at = np.ascontiguousarray(qb.T @ (am @ qb))                                  # :20
+            va, qa = O.symmetric_eig(at, vectors=True)                                   # :21
+            q = qb @ qa                                                                  # :22
+        else:
+            va, q = O.symmetric_eig(am, vectors=True)
+        nout = k
+        if order != 0:
+            if np.isnan(va).any():
+                return INVALID_ARGUMENT
+            idx = np.argsort(-va if order == 1 else va, kind="stable")
+            nout = min(size, k)
+            va, q = va[idx][:nout], q[:, idx][:, :nout]
+            q = q * np.where(np.signbit(q[0, :]), -1.0, 1.0).astype(q.dtype)
+        _vec(vals, nout, sfx)[:] = va
+        _mat(vecs, k, nout, v_rs, v_cs, sfx)[...] = q
+        return OK
+
     # -- qr.rs ----------------------------------------------------------------------------------------------
     def _qr(self, sfx, p, rows, cols, rs, cs, diag):
         if rows < cols:
