@@ -195,6 +195,6 @@ def test_sorted_eig_dev_and_host_agree_with_numpy():
     assert np.max(np.abs(qa.cpu().numpy().T - vecs)) <= 1e-10
     for dt in (np.float32,):
         v32, q32 = L.sorted_eig(a.astype(dt), None, 5, L.SMALLEST)
-        assert np.max(np.abs(v32 - np.linalg.eigvalsh(a)[:5])) <= 1e-4 * np.abs(ref).max()
+        assert np.max(np.abs(v32 - np.linalg.eigvalsh(a)[:5])) <= 64 * k * 1.2e-7 * np.linalg.norm(a, 2)
     D.e.set_stream(None)
     D.e.close()
