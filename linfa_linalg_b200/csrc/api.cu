@@ -94,6 +94,27 @@ int qt_mul_host(lfb_handle *h, const T *qr, int64_t rows, int64_t cols, int64_t 
     LFB_API_END(h)
 }
 
+// Strided 2-D block of PAGEABLE caller memory (height rows of `width` elements, `pitch` elements apart) <-> a compact pinned
+// buffer (pitch = width), copied by the handle's host threads in row groups of ~1 MiB.
+template <typename T>
+void host_gather(lfb_handle &h, const T *src, int64_t pitch, int64_t width, int64_t height, T *dst) {
+    const int64_t per = std::max<int64_t>(1, (int64_t)(1 << 20) / std::max<int64_t>(1, width * (int64_t)sizeof(T)));
+    const int jobs = (int)cdiv(height, per);
+    h.pool().run(jobs, [&](int j) {
+        const int64_t r0 = j * per, r1 = std::min(height, r0 + per);
+        for (int64_t r = r0; r < r1; ++r) memcpy(dst + r * width, src + r * pitch, sizeof(T) * width);
+    });
+}
+template <typename T>
+void host_scatter(lfb_handle &h, const T *src, int64_t width, int64_t height, T *dst, int64_t pitch) {
+    const int64_t per = std::max<int64_t>(1, (int64_t)(1 << 20) / std::max<int64_t>(1, width * (int64_t)sizeof(T)));
+    const int jobs = (int)cdiv(height, per);
+    h.pool().run(jobs, [&](int j) {
+        const int64_t r0 = j * per, r1 = std::min(height, r0 + per);
+        for (int64_t r = r0; r < r1; ++r) memcpy(dst + r * pitch, src + r * width, sizeof(T) * width);
+    });
+}
+
 template <typename T>
 int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t cs, int clean, int64_t *fail_index) {
     if (rows != cols) return fail(h, LFB_NOT_SQUARE, "Matrix is not square");                 // lib.rs:64-71
@@ -115,8 +136,43 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
     // diagonal block, which is only defined (= the caller's own data) if that block was uploaded as part of a band.
     const int64_t NBc = std::max<int64_t>(64, round_up(h->opt.chol_nb, 64));
     const int64_t BAND = round_up(std::max<int64_t>(1024, NBc), NBc);
+    // Pageable caller memory (what an ndarray owns): cudaMemcpy from it is staged by the driver at ~6-10 GB/s and blocks the
+    // calling thread.  Instead the handle's host threads gather every band into the handle's pinned buffer while the DMA of
+    // the previous band runs, and on the way back scatter each finished block column while the factorisation continues.
+    bool pinned_host = false;
+    {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, a) == cudaSuccess) pinned_host = pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged;
+        else cudaGetLastError();
+    }
+    const bool staged = tri && !pinned_host && h->opt.host_staging;
+    T *stagebuf = nullptr;
+    if (staged) {
+        size_t tri_elems = 0;
+        for (int64_t r0 = 0; r0 < n; r0 += BAND) tri_elems += (size_t)(std::min(n, r0 + BAND) - r0) * (size_t)std::max(std::min(n, r0 + BAND), n - r0);
+        stagebuf = (T *)h->pinned_buf(sizeof(T) * tri_elems);
+    }
+    std::unique_ptr<DevBuf<T>> rowtmp;
     if (!tri) {
         upload<T>(*h, a, n, n, rs, cs, dA, ld);
+    } else if (staged) {
+        T *sp = stagebuf;
+        if (lay != L_COL) rowtmp.reset(new DevBuf<T>(*h, (size_t)hld * n));
+        for (int64_t b0 = 0; b0 < n; b0 += BAND) {
+            const int64_t b1 = std::min(n, b0 + BAND);
+            if (lay == L_COL) {      // columns b0..b1, rows b0..n-1 of each: width n - b0, height b1 - b0, pitch hld
+                host_gather<T>(*h, a + b0 + b0 * hld, hld, n - b0, b1 - b0, sp);
+                LFB_CUDA(cudaMemcpy2DAsync(dA.get() + b0 + b0 * ld, ld * sizeof(T), sp, (n - b0) * sizeof(T), (n - b0) * sizeof(T), b1 - b0,
+                                           cudaMemcpyHostToDevice, h->stream));
+                sp += (size_t)(n - b0) * (b1 - b0);
+            } else {                 // rows b0..b1, columns 0..b1-1 of each: width b1, height b1 - b0
+                host_gather<T>(*h, a + b0 * hld, hld, b1, b1 - b0, sp);
+                LFB_CUDA(cudaMemcpy2DAsync(rowtmp->get() + b0 * hld, hld * sizeof(T), sp, b1 * sizeof(T), b1 * sizeof(T), b1 - b0,
+                                           cudaMemcpyHostToDevice, h->stream));
+                sp += (size_t)b1 * (b1 - b0);
+            }
+        }
+        if (lay != L_COL) transpose<T>(*h, rowtmp->get(), n, n, hld, dA, ld);
     } else if (lay == L_COL) {   // column j holds rows j..n-1: bands of columns
         for (int64_t c0 = 0; c0 < n; c0 += BAND) {
             const int64_t c1 = std::min(n, c0 + BAND);
@@ -137,14 +193,11 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
     // hides behind the trailing updates instead of following the factorisation.
     // Only for page-locked host memory: a D2H copy into pageable memory is staged synchronously and would stall
     // the thread that is still enqueueing the factorisation.
-    bool pinned_host = false;
-    {
-        cudaPointerAttributes pa;
-        if (cudaPointerGetAttributes(&pa, a) == cudaSuccess) pinned_host = pa.type == cudaMemoryTypeHost;
-        else cudaGetLastError();
-    }
-    const bool overlap = tri && !clean && h->opt.chol_overlap_d2h && pinned_host;
+    const bool overlap = tri && !clean && h->opt.chol_overlap_d2h && (pinned_host || staged);
     std::vector<cudaEvent_t> pev;
+    struct Piece { cudaEvent_t done; int64_t k0, nb; T *st; };   // staged: block columns waiting for their host scatter
+    std::vector<Piece> pieces;
+    size_t stage_off = 0;
     std::unique_ptr<DevBuf<T>> stage;
     if (overlap) {
         if (!h->copy_stream) LFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -152,13 +205,39 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
         lfb_handle *hh = h;
         T *dAp = dA.get();
         T *stg = stage ? stage->get() : nullptr;
-        h->chol_panel_hook = [hh, dAp, stg, a, n, ld, hld, lay, &pev](int64_t k0, int64_t nb) {
+        h->chol_panel_hook = [hh, dAp, stg, a, n, ld, hld, lay, &pev, staged, stagebuf, &pieces, &stage_off](int64_t k0, int64_t nb) {
             cudaEvent_t e;
             LFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             pev.push_back(e);
             LFB_CUDA(cudaEventRecord(e, hh->stream));
             LFB_CUDA(cudaStreamWaitEvent(hh->copy_stream, e, 0));
             const int64_t below = n - k0;
+            if (staged) {            // pageable caller memory: device -> pinned staging now, host threads scatter it later
+                T *st = stagebuf + stage_off;
+                stage_off += (size_t)below * nb;
+                if (lay == L_COL) {
+                    LFB_CUDA(cudaMemcpy2DAsync(st, below * sizeof(T), dAp + k0 + k0 * ld, ld * sizeof(T), below * sizeof(T), nb,
+                                               cudaMemcpyDeviceToHost, hh->copy_stream));
+                } else {
+                    T *t = stg + (size_t)k0 * n;
+                    cudaStream_t keep = hh->stream;
+                    hh->stream = hh->copy_stream;
+                    try {
+                        transpose<T>(*hh, dAp + k0 + k0 * ld, below, nb, ld, t, nb);
+                    } catch (...) {
+                        hh->stream = keep;
+                        throw;
+                    }
+                    hh->stream = keep;
+                    LFB_CUDA(cudaMemcpyAsync(st, t, sizeof(T) * below * nb, cudaMemcpyDeviceToHost, hh->copy_stream));
+                }
+                cudaEvent_t d;
+                LFB_CUDA(cudaEventCreateWithFlags(&d, cudaEventDisableTiming));
+                pev.push_back(d);
+                LFB_CUDA(cudaEventRecord(d, hh->copy_stream));
+                pieces.push_back({d, k0, nb, st});
+                return;
+            }
             if (lay == L_COL) {      // host column-major: the block column is a 2-D copy as it is
                 LFB_CUDA(cudaMemcpy2DAsync(a + k0 + k0 * hld, hld * sizeof(T), dAp + k0 + k0 * ld, ld * sizeof(T), below * sizeof(T), nb,
                                            cudaMemcpyDeviceToHost, hh->copy_stream));
@@ -191,9 +270,41 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
     h->chol_panel_hook = nullptr;
     LFB_CUDA(cudaMemcpyAsync(&info, dInfo.get(), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     if (overlap) {
+        // staged: scatter every block column into the caller's storage as soon as its D2H has landed -- the factorisation
+        // is fully enqueued by now and keeps running while the host threads copy
+        for (auto &pc : pieces) {
+            LFB_CUDA(cudaEventSynchronize(pc.done));
+            const int64_t below = n - pc.k0;
+            if (lay == L_COL) host_scatter<T>(*h, pc.st, below, pc.nb, a + pc.k0 + pc.k0 * hld, hld);   // nb columns of `below` rows
+            else host_scatter<T>(*h, pc.st, pc.nb, below, a + pc.k0 * hld + pc.k0, hld);               // `below` rows of nb entries
+        }
         LFB_CUDA(cudaStreamSynchronize(h->copy_stream));
         LFB_CUDA(cudaStreamSynchronize(h->stream));
         for (auto e : pev) cudaEventDestroy(e);
+    } else if (staged && !clean) {
+        // no overlap requested: same staging, after the factorisation
+        T *sp = stagebuf;
+        std::unique_ptr<DevBuf<T>> tmp;
+        if (lay != L_COL) {
+            tmp.reset(new DevBuf<T>(*h, (size_t)hld * n));
+            transpose<T>(*h, dA, n, n, ld, tmp->get(), hld);
+        }
+        for (int64_t b0 = 0; b0 < n; b0 += BAND) {
+            const int64_t b1 = std::min(n, b0 + BAND);
+            if (lay == L_COL) {
+                LFB_CUDA(cudaMemcpy2DAsync(sp, (n - b0) * sizeof(T), dA.get() + b0 + b0 * ld, ld * sizeof(T), (n - b0) * sizeof(T), b1 - b0,
+                                           cudaMemcpyDeviceToHost, h->stream));
+                LFB_CUDA(cudaStreamSynchronize(h->stream));
+                host_scatter<T>(*h, sp, n - b0, b1 - b0, a + b0 + b0 * hld, hld);
+                sp += (size_t)(n - b0) * (b1 - b0);
+            } else {
+                LFB_CUDA(cudaMemcpy2DAsync(sp, b1 * sizeof(T), tmp->get() + b0 * hld, hld * sizeof(T), b1 * sizeof(T), b1 - b0,
+                                           cudaMemcpyDeviceToHost, h->stream));
+                LFB_CUDA(cudaStreamSynchronize(h->stream));
+                host_scatter<T>(*h, sp, b1, b1 - b0, a + b0 * hld, hld);
+                sp += (size_t)b1 * (b1 - b0);
+            }
+        }
     } else if (!tri || clean) {
         download<T>(*h, dA, ld, a, n, n, rs, cs);
     } else if (lay == L_COL) {
@@ -624,6 +735,7 @@ int lfb_destroy(lfb_handle *h) {
     for (auto &e : h->prof_ev) if (e) cudaEventDestroy(e);
     if (h->panel_dbg) cudaFree(h->panel_dbg);
     if (h->pinned) cudaFreeHost(h->pinned);
+    delete h->host_pool;
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
@@ -680,12 +792,12 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     struct Opt { const char *name; int64_t *field; int64_t lo, hi; };
     const int64_t BIG = int64_t(1) << 40;
     const Opt table[] = {
-        {"qr_nb", &o.qr_nb, 32, 1024}, {"qr_nb_f32", &o.qr_nb_f32, 32, 1024}, {"qr_sub", &o.qr_sub, 1, 32}, {"chol_base", &o.chol_base, 1, 64},
+        {"qr_nb", &o.qr_nb, 32, 1024}, {"qr_nb_f32", &o.qr_nb_f32, 32, 1024}, {"qr_vt", &o.qr_vt, 0, 1}, {"qr_sub", &o.qr_sub, 1, 32}, {"chol_base", &o.chol_base, 1, 64},
         {"chol_nb", &o.chol_nb, 64, 8192}, {"chol_tn", &o.chol_tn, 0, 1}, {"chol_potf2_rl", &o.chol_potf2_rl, 0, 1}, {"gemm_tma", &o.gemm_tma, 0, 1}, {"gemm_splitk", &o.gemm_splitk, 0, 1}, {"gemm_deterministic", &o.gemm_deterministic, 0, 1}, {"tsqr_cholqr_cond", &o.tsqr_cholqr_cond, 0, 1 << 20},
         {"gemm_v2", &o.gemm_v2, 0, 1}, {"sgemm_tc", &o.sgemm_tc, 0, 2}, {"gemm_split_waves", &o.gemm_split_waves, 1, 64}, {"panel_cluster", &o.panel_cluster, 0, 2},
         {"panel_cluster_max", &o.panel_cluster_max, 1, 16}, {"lookahead", &o.lookahead, 0, 1}, {"tsqr_chunk", &o.tsqr_chunk, 64, BIG},
         {"batched_quad", &o.batched_quad, 0, 4}, {"tsqr_streams", &o.tsqr_streams, 1, 64}, {"tsqr_graph", &o.tsqr_graph, 0, 1},
-        {"qr_tsqr_auto", &o.qr_tsqr_auto, 0, 1}, {"trd_fused", &o.trd_fused, 0, 1}, {"chol_overlap_d2h", &o.chol_overlap_d2h, 0, 1},
+        {"qr_tsqr_auto", &o.qr_tsqr_auto, 0, 1}, {"trd_fused", &o.trd_fused, 0, 1}, {"chol_overlap_d2h", &o.chol_overlap_d2h, 0, 1}, {"host_staging", &o.host_staging, 0, 1},
         {"rot_staged", &o.rot_staged, 0, 1}, {"eigh_stable_2x2", &o.eigh_stable_2x2, 0, 1}, {"rot_serial", &o.rot_serial, 0, 1},
         {"fast_hypot", &o.fast_hypot, 0, 1}, {"bd_blocked", &o.bd_blocked, 0, 1}, {"trd_profile", &o.trd_profile, 0, 1},
         {"trd_symv_async", &o.trd_symv_async, 0, 1},

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -11,6 +12,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/linfa_b200.h"
@@ -42,6 +44,7 @@ struct CudaError : std::runtime_error {
 struct Options {
     int64_t qr_nb = 128;     // outer panel width of blocked compact-WY QR
     int64_t qr_nb_f32 = 256; // same for f32 when the trailing updates run on the tcgen05 kernel (n >= 2048)
+    int64_t qr_vt = 0;       // f64 QR: rank-nb update through a transposed copy of V (TN form); measured: no gain (263.8 vs 263.5 ms), off
     int64_t qr_sub = 32;     // inner BLAS-2 sub-panel width (<= 32)
     int64_t chol_base = 64;  // recursion base of Cholesky / TRSM (<= 64)
     int64_t chol_nb = 512;   // right-looking panel width of Cholesky (K of the trailing SYRK)
@@ -68,11 +71,65 @@ struct Options {
     int64_t eigh_stable_2x2 = 1;    // eigh.rs:111 basis without cancellation (0 = the reference's formula verbatim)
     int64_t fast_hypot = 1;         // host recurrence: sqrt(x^2 + y^2) instead of hypot when far from underflow
     int64_t chol_overlap_d2h = 1;   // host Cholesky (dirty, n >= 2048): finished block columns go back to the host during the factorisation
+    int64_t host_staging = 1;       // host Cholesky on PAGEABLE memory (n >= 2048): gather / scatter through the pinned buffer with host threads
     int64_t tsqr_streams = 8;       // chunks in flight (each panel kernel occupies one 16-SM cluster)
     int64_t qr_tsqr_auto = 0;       // 1: lfb_qr_* takes the TSQR + Householder-reconstruction route for tall-skinny inputs (rows >= 2 chunks, cols <= 512)
     int64_t tsqr_cholqr_cond = 16;  // tall-skinny leaf: Cholesky-QR (Gram GEMM + n x n Cholesky) when its cond_2 bound <= this; 0 = always Householder
     int64_t tsqr_graph = 0;         // 1: replay the local TSQR stage of a (buffer, shape) seen before as one CUDA graph
                                     // (measured: 145 vs 147 ms -- the stage is GPU bound, not launch bound -- so off by default)
+};
+
+// A few persistent host threads for the staging copies between pageable caller memory and the handle's pinned buffer
+// (one core's memcpy is ~8 GB/s, PCIe 5 x16 ~50 GB/s).  run(n, f) executes f(0..n-1) across the pool and returns when all
+// are done; used by one call at a time, like the handle.
+struct HostPool {
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv_start, cv_done;
+    std::function<void(int)> job;
+    uint64_t generation = 0;
+    int next = 0, total = 0, pending = 0;
+    bool stop = false;
+    explicit HostPool(int n) {
+        for (int i = 0; i < n; ++i) threads.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_start.notify_all();
+        for (auto &t : threads) t.join();
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_start.wait(lk, [&] { return stop || (generation != seen && next < total); });
+            if (stop) return;
+            while (next < total) {
+                const int i = next++;
+                lk.unlock();
+                job(i);
+                lk.lock();
+                if (--pending == 0) cv_done.notify_all();
+            }
+            seen = generation;
+        }
+    }
+    void run(int n, const std::function<void(int)> &f) {
+        if (n <= 0) return;
+        if (threads.empty() || n == 1) {
+            for (int i = 0; i < n; ++i) f(i);
+            return;
+        }
+        std::unique_lock<std::mutex> lk(mu);
+        job = f;
+        next = 0; total = n; pending = n;
+        ++generation;
+        cv_start.notify_all();
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
 };
 
 }  // namespace lfb
@@ -97,6 +154,15 @@ struct lfb_handle {
     struct Block { void *p; size_t bytes; bool used; };
     std::vector<Block> blocks;
     void *pinned = nullptr; size_t pinned_bytes = 0;
+    lfb::HostPool *host_pool = nullptr;          // created on first use (pageable staging copies)
+    lfb::HostPool &pool() {
+        if (!host_pool) {
+            unsigned hc = std::thread::hardware_concurrency();
+            int n = (int)std::min<unsigned>(8, std::max<unsigned>(2, hc / 2));
+            host_pool = new lfb::HostPool(n);
+        }
+        return *host_pool;
+    }
 
     // ---- CUDA graphs of launch-bound multi-stream stages (TSQR local stage), keyed by buffer and shape ----
     struct GraphEntry {

@@ -633,7 +633,8 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
     const int SUB = (int)std::max<int64_t>(1, std::min<int64_t>(h.opt.qr_sub, W));
     const int64_t ldv = round_up(m, 4);     // 16-byte columns for TMA in both precisions
     // f32 with the tensor-core GEMM: a transposed copy of every finished panel's V (nb x rows, K-major) for C -= V W
-    const bool use_vt = sizeof(T) == 4 && h.opt.sgemm_tc != 0 && m >= 256 && n > NB;
+    // (f64, option qr_vt: the same copy turns C -= V W into the TMA kernel's K-major/K-major variant, 2 box loads per stage instead of 9)
+    const bool use_vt = ((sizeof(T) == 4 && h.opt.sgemm_tc != 0) || (sizeof(T) == 8 && h.opt.qr_vt != 0)) && m >= 256 && n > NB;
     DevBuf<T> Vt0(h, use_vt ? (size_t)NB * ldv : 1), Vt1(h, use_vt ? (size_t)NB * ldv : 1);
     T *Vtbuf[2] = {use_vt ? Vt0.get() : nullptr, use_vt ? Vt1.get() : nullptr};
     // two generations of the panel workspaces (V, T): with look-ahead panel k+1 is factored while the
