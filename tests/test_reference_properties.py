@@ -13,7 +13,10 @@ for ANY backward-stable method is skipped, as proptest's own 1000 draws practica
 import numpy as np
 import pytest
 
-CASES = 40
+# proptest runs 1000 cases per property (tests/qr.rs:38 ...).  The oracle back end (CPU, microseconds per case) runs all 1000;
+# the device back end pays a PCIe round trip per call, so it runs the first 200 of the SAME sequence of draws.
+CASES = {"oracle": 1000, "b200": 200}
+_current_cases = [40]
 FLOAT_RANGE = (-100.0, 100.0)          # tests/common.rs:9
 DIM_RANGE = (1, 10)                    # tests/common.rs:10
 
@@ -21,6 +24,7 @@ DIM_RANGE = (1, 10)                    # tests/common.rs:10
 @pytest.fixture(scope="module", params=["oracle", pytest.param("b200", marks=pytest.mark.gpu)])
 def eng(request):
     import linfa_linalg_b200 as L
+    _current_cases[0] = CASES[request.param]
     if request.param == "oracle":
         from oracle_engine import OracleEngine
         return OracleEngine()
@@ -58,7 +62,7 @@ def dims(rng):
 
 
 def cases(seed):
-    for i in range(CASES):
+    for i in range(_current_cases[0]):
         yield np.random.default_rng(1000 * seed + i)
 
 
