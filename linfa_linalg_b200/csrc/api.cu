@@ -709,6 +709,7 @@ int lfb_create(lfb_handle **out, int device) {
         int lo = 0, hi = 0;
         LFB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         LFB_CUDA(cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, hi));
+        LFB_CUDA(cudaStreamCreateWithPriority(&h->aux2_stream, cudaStreamNonBlocking, hi));
         for (auto &e : h->ev) LFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         cudaDeviceProp prop;
         LFB_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -739,6 +740,7 @@ int lfb_destroy(lfb_handle *h) {
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->aux2_stream) cudaStreamDestroy(h->aux2_stream);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     delete h;
     return LFB_OK;
@@ -793,7 +795,7 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
     const int64_t BIG = int64_t(1) << 40;
     const Opt table[] = {
         {"qr_nb", &o.qr_nb, 32, 1024}, {"qr_nb_f32", &o.qr_nb_f32, 32, 1024}, {"qr_vt", &o.qr_vt, 0, 1}, {"qr_sub", &o.qr_sub, 1, 32}, {"chol_base", &o.chol_base, 1, 64},
-        {"chol_nb", &o.chol_nb, 64, 8192}, {"chol_tn", &o.chol_tn, 0, 1}, {"chol_potf2_rl", &o.chol_potf2_rl, 0, 1}, {"gemm_tma", &o.gemm_tma, 0, 1}, {"gemm_splitk", &o.gemm_splitk, 0, 1}, {"gemm_deterministic", &o.gemm_deterministic, 0, 1}, {"tsqr_cholqr_cond", &o.tsqr_cholqr_cond, 0, 1 << 20},
+        {"chol_nb", &o.chol_nb, 64, 8192}, {"chol_tn", &o.chol_tn, 0, 1}, {"chol_split_panel", &o.chol_split_panel, 0, 1}, {"chol_trace", &o.chol_trace, 0, 1}, {"chol_potf2_rl", &o.chol_potf2_rl, 0, 1}, {"gemm_tma", &o.gemm_tma, 0, 1}, {"gemm_splitk", &o.gemm_splitk, 0, 1}, {"gemm_deterministic", &o.gemm_deterministic, 0, 1}, {"tsqr_cholqr_cond", &o.tsqr_cholqr_cond, 0, 1 << 20},
         {"gemm_v2", &o.gemm_v2, 0, 1}, {"sgemm_tc", &o.sgemm_tc, 0, 2}, {"gemm_split_waves", &o.gemm_split_waves, 1, 64}, {"panel_cluster", &o.panel_cluster, 0, 2},
         {"panel_cluster_max", &o.panel_cluster_max, 1, 16}, {"lookahead", &o.lookahead, 0, 1}, {"tsqr_chunk", &o.tsqr_chunk, 64, BIG},
         {"batched_quad", &o.batched_quad, 0, 4}, {"tsqr_streams", &o.tsqr_streams, 1, 64}, {"tsqr_graph", &o.tsqr_graph, 0, 1},

@@ -49,6 +49,8 @@ struct Options {
     int64_t chol_base = 64;  // recursion base of Cholesky / TRSM (<= 64)
     int64_t chol_nb = 512;   // right-looking panel width of Cholesky (K of the trailing SYRK)
     int64_t chol_tn = 1;     // f64: trailing SYRK in TN form on a transposed copy of the panel (K-major TMA tiles on both sides)
+    int64_t chol_split_panel = 1; // look-ahead panel on TWO side streams: diagonal-block chain | rows below it (profiles/r2_chol_analysis.md)
+    int64_t chol_trace = 0;    // debug: event time stamps of every stage of the look-ahead pipeline on stderr
     int64_t chol_potf2_rl = 1; // diagonal 64 x 64 blocks: right-looking register-blocked kernel (0 = first-generation left-looking)
     int64_t gemm_tma = 1;    // use the TMA-fed DGEMM when operands are 16-byte aligned
     int64_t gemm_splitk = 1; // allow split-K for skinny-output GEMMs
@@ -140,6 +142,7 @@ struct lfb_handle {
     cudaStream_t stream = nullptr;      // stream in use
     cudaStream_t own_stream = nullptr;  // created by lfb_create
     cudaStream_t aux_stream = nullptr;  // high-priority side stream for look-ahead panel factorisation
+    cudaStream_t aux2_stream = nullptr; // second high-priority side stream (Cholesky: the below-diagonal half of a panel)
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     void *panel_dbg = nullptr;          // device buffer for the panel kernel's phase counters (debug)
     bool is_sub = false;                // a worker handle owned by another handle (TSQR chunk pool)

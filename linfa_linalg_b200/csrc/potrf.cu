@@ -12,6 +12,7 @@
 // block is NOT a substitution (a 2000-instruction dependent chain per row) but a multiplication by
 // the explicitly inverted 64x64 block (recursive doubling, 6 levels), which is throughput-bound.
 // Only the lower triangle is read or written (the `dirty` contract, cholesky.rs:17-19).
+#include <array>
 #include <memory>
 
 #include "common.cuh"
@@ -348,6 +349,70 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
                 gemm<T>(h, 0, 1, below, rem, jb, T(-1), Bp, ld, Bp, ld, T(1), A + (j0 + jb) + (j0 + jb) * ld, ld, /*lower_only=*/1);
         }
     };
+    // The same panel on TWO streams (look-ahead mode, option chol_split_panel).  The event trace of the single-stream panel
+    // (profiles/r2_chol_analysis.md) shows the factorisation GEMM bound for the first third and bound by the side-stream
+    // panel afterwards: 0.8-1.3 ms per panel, of which the 64-pivot diagonal kernels are 0.32 -- the rest is the full-height
+    // TRSM / K = 64 GEMM of every block sitting between two diagonal kernels.  Here the chain that the next diagonal block
+    // really depends on -- potf2(j), the TRSM and update INSIDE the nb x nb diagonal block (<= 4 and <= 16 CTAs) -- runs on
+    // the handle's stream, and the rows below the diagonal block follow on a second stream: TRSM(j) after potf2(j),
+    // update(j) after the diagonal block's TRSM(j) (its B operand).  Same kernels, same arithmetic per entry.
+    DevBuf<T> LinvAll(h, (size_t)CB * CB * (NB / CB));
+    std::vector<cudaEvent_t> evP, evT;
+    cudaEvent_t evJoin = nullptr;
+    const bool split_ok = h.opt.chol_split_panel && h.aux2_stream != nullptr;
+    if (split_ok) {
+        evP.resize(NB / CB); evT.resize(NB / CB);
+        for (auto &e : evP) LFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : evT) LFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        LFB_CUDA(cudaEventCreateWithFlags(&evJoin, cudaEventDisableTiming));
+    }
+    struct EvGuard {
+        std::vector<cudaEvent_t> &a, &b; cudaEvent_t &j;
+        ~EvGuard() { for (auto e : a) cudaEventDestroy(e); for (auto e : b) cudaEventDestroy(e); if (j) cudaEventDestroy(j); }
+    } ev_guard{evP, evT, evJoin};
+    auto factor_panel_split = [&](int64_t k0, int64_t nb) {
+        const int64_t pend = k0 + nb, tall = n - pend;          // rows below the diagonal block
+        cudaStream_t s1 = h.stream, s2 = h.aux2_stream;
+        LFB_CUDA(cudaEventRecord(evJoin, s1));
+        LFB_CUDA(cudaStreamWaitEvent(s2, evJoin, 0));           // the second stream starts where the first one is
+        int jb_i = 0;
+        for (int64_t j0 = k0; j0 < pend; j0 += CB, ++jb_i) {
+            const int jb = (int)std::min<int64_t>(CB, pend - j0);
+            T *Ajj = A + j0 + j0 * ld;
+            T *Lj = LinvAll.get() + (size_t)jb_i * CB * CB;
+            if (h.opt.chol_potf2_rl) potf2_rl_inv_kernel<T><<<1, 256, smem_p, s1>>>(Ajj, ld, jb, j0, d_info, Lj);
+            else potf2_inv_kernel<T><<<1, 256, smem_p, s1>>>(Ajj, ld, jb, j0, d_info, Lj);
+            LFB_LAUNCH_CHECK(h);
+            LFB_CUDA(cudaEventRecord(evP[jb_i], s1));
+            const int64_t inner = pend - (j0 + jb);             // rows of the diagonal block below this 64-block
+            T *Bp = Ajj + jb;                                   // rows j0+jb.., columns j0..j0+jb
+            if (inner > 0) {
+                trsm_mult_kernel<T><<<(unsigned)cdiv(inner, 128), 256, smem_t, s1>>>(Bp, ld, inner, jb, Lj, d_info);
+                LFB_LAUNCH_CHECK(h);
+                LFB_CUDA(cudaEventRecord(evT[jb_i], s1));
+                gemm<T>(h, 0, 1, inner, inner, jb, T(-1), Bp, ld, Bp, ld, T(1), A + (j0 + jb) + (j0 + jb) * ld, ld, /*lower_only=*/1);
+            }
+            if (tall > 0) {
+                T *Bt = A + pend + j0 * ld;                     // rows pend.., columns j0..j0+jb
+                LFB_CUDA(cudaStreamWaitEvent(s2, evP[jb_i], 0));
+                trsm_mult_kernel<T><<<(unsigned)cdiv(tall, 128), 256, smem_t, s2>>>(Bt, ld, tall, jb, Lj, d_info);
+                LFB_LAUNCH_CHECK(h);
+                if (inner > 0) {                                // A[pend.., j0+jb..pend) -= Bt * Bp^T
+                    LFB_CUDA(cudaStreamWaitEvent(s2, evT[jb_i], 0));
+                    h.stream = s2;
+                    try {
+                        gemm<T>(h, 0, 1, tall, inner, jb, T(-1), Bt, ld, Bp, ld, T(1), A + pend + (j0 + jb) * ld, ld, 0);
+                    } catch (...) {
+                        h.stream = s1;
+                        throw;
+                    }
+                    h.stream = s1;
+                }
+            }
+        }
+        LFB_CUDA(cudaEventRecord(evJoin, s2));
+        LFB_CUDA(cudaStreamWaitEvent(s1, evJoin, 0));           // the panel is complete on the first stream again
+    };
     // Look-ahead: the trailing SYRK of panel k is split into the block column of panel k+1 (done
     // first) and the rest; panel k+1 is factored on a high-priority side stream while the rest of
     // the SYRK runs, so the latency-bound diagonal kernels leave the critical path.
@@ -370,9 +435,28 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
         if (tn) gemm<T>(h, 1, 0, rows_, cols_, nb, T(-1), Pt + r_off * ldpt, ldpt, Pt + r_off * ldpt, ldpt, T(1), Cp, ld, /*lower_only=*/1);
         else gemm<T>(h, 0, 1, rows_, cols_, nb, T(-1), P + r_off, ld, P + r_off, ld, T(1), Cp, ld, /*lower_only=*/1);
     };
+    // Debug option chol_trace: CUDA-event time stamps of every stage on both streams (there is no nsys in the image), one
+    // line per panel on stderr after the call: when the block-column SYRK, the side-stream panel and the rest of the SYRK
+    // started and ended relative to the start of the factorisation.
+    struct Mark { cudaEvent_t e; int panel; int what; };
+    std::vector<Mark> marks;
+    const bool trace = h.opt.chol_trace != 0;
+    cudaEvent_t t_base = nullptr;
+    auto mark = [&](cudaStream_t st, int panel, int what) {
+        if (!trace) return;
+        cudaEvent_t e;
+        LFB_CUDA(cudaEventCreate(&e));
+        LFB_CUDA(cudaEventRecord(e, st));
+        marks.push_back({e, panel, what});
+    };
+    if (trace) {
+        LFB_CUDA(cudaEventCreate(&t_base));
+        LFB_CUDA(cudaEventRecord(t_base, h.stream));
+    }
     factor_panel(0, std::min<int64_t>(NB, n));
     if (h.chol_panel_hook) h.chol_panel_hook(0, std::min<int64_t>(NB, n));
     if (tn && n > NB) transpose<T>(h, A + NB, n - NB, NB, ld, PtBuf[0]->get(), ldpt);
+    mark(h.stream, -1, 0);
     int cur = 0;
     for (int64_t k0 = 0; k0 < n; k0 += NB, cur ^= 1) {
         const int64_t nb = std::min<int64_t>(NB, n - k0);
@@ -384,13 +468,19 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
         const T *Pt = tn ? PtBuf[cur]->get() : nullptr;
         T *PtNext = tn ? PtBuf[cur ^ 1]->get() : nullptr;
         const int64_t rows2 = rows - nbn;
+        const int pi = (int)(k0 / NB);
         if (la) {
+            mark(sm, pi, 1);
             syrk(P, Pt, 0, rows, nbn, nb, A + pend + pend * ld);
+            mark(sm, pi, 2);
             LFB_CUDA(cudaEventRecord(h.ev[0], sm));
             LFB_CUDA(cudaStreamWaitEvent(sp, h.ev[0], 0));
             h.stream = sp;
             try {
-                factor_panel(pend, nbn);
+                mark(sp, pi, 3);
+                if (split_ok) factor_panel_split(pend, nbn);
+                else factor_panel(pend, nbn);
+                mark(sp, pi, 4);
                 if (h.chol_panel_hook) h.chol_panel_hook(pend, nbn);     // h.stream is the side stream here
                 if (tn && rows2 > 0) transpose<T>(h, A + (pend + nbn) + pend * ld, rows2, nbn, ld, PtNext, ldpt);
             } catch (...) {
@@ -400,6 +490,7 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
             LFB_CUDA(cudaEventRecord(h.ev[1], sp));
             h.stream = sm;
             if (rows2 > 0) syrk(P, Pt, nbn, rows2, rows2, nb, A + (pend + nbn) + (pend + nbn) * ld);
+            mark(sm, pi, 5);
             LFB_CUDA(cudaStreamWaitEvent(sm, h.ev[1], 0));
         } else {
             syrk(P, Pt, 0, rows, rows, nb, A + pend + pend * ld);
@@ -407,6 +498,23 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
             if (h.chol_panel_hook) h.chol_panel_hook(pend, nbn);
             if (tn && rows2 > 0) transpose<T>(h, A + (pend + nbn) + pend * ld, rows2, nbn, ld, PtNext, ldpt);
         }
+    }
+    if (trace) {
+        LFB_CUDA(cudaStreamSynchronize(sm));
+        LFB_CUDA(cudaStreamSynchronize(sp));
+        std::map<int, std::array<float, 6>> rowsT;
+        for (auto &mk : marks) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, t_base, mk.e);
+            rowsT[mk.panel][mk.what] = t;
+            cudaEventDestroy(mk.e);
+        }
+        cudaEventDestroy(t_base);
+        fprintf(stderr, "chol_trace n=%lld nb=%lld (ms from start): panel | syrk_col start end | side panel start end | syrk_rest end\n",
+                (long long)n, (long long)NB);
+        for (auto &kv : rowsT)
+            fprintf(stderr, "  %3d | %8.3f %8.3f | %8.3f %8.3f | %8.3f\n", kv.first, kv.second[1], kv.second[2], kv.second[3], kv.second[4],
+                    kv.second[5]);
     }
     if (clean) triangular_zero<T>(h, A, n, ld, /*keep_lower=*/1);
 }
