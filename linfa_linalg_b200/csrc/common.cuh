@@ -49,6 +49,8 @@ struct Options {
     int64_t chol_base = 64;  // recursion base of Cholesky / TRSM (<= 64)
     int64_t chol_nb = 512;   // right-looking panel width of Cholesky (K of the trailing SYRK)
     int64_t chol_tn = 1;     // f64: trailing SYRK in TN form on a transposed copy of the panel (K-major TMA tiles on both sides)
+    int64_t chol_nb_tail = 256;    // panel width once fewer than chol_tail_rows rows remain
+    int64_t chol_tail_rows = 8192;
     int64_t chol_split_panel = 1; // look-ahead panel on TWO side streams: diagonal-block chain | rows below it (profiles/r2_chol_analysis.md)
     int64_t chol_trace = 0;    // debug: event time stamps of every stage of the look-ahead pipeline on stderr
     int64_t chol_potf2_rl = 1; // diagonal 64 x 64 blocks: right-looking register-blocked kernel (0 = first-generation left-looking)

@@ -429,7 +429,7 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
     const int64_t ldpt = NB;
     std::unique_ptr<DevBuf<T>> PtBuf[2];
     if (tn)
-        for (auto &b : PtBuf) b.reset(new DevBuf<T>(h, (size_t)ldpt * (n > NB ? n - NB : 1)));
+        for (auto &b : PtBuf) b.reset(new DevBuf<T>(h, (size_t)ldpt * n));
     // C (rows x cols, lower part) -= P[0:rows, :] * P[0:cols, :]^T with P = panel rows r_off.. (and the matching slice of Pt)
     auto syrk = [&](const T *P, const T *Pt, int64_t r_off, int64_t rows_, int64_t cols_, int64_t nb, T *Cp) {
         if (tn) gemm<T>(h, 1, 0, rows_, cols_, nb, T(-1), Pt + r_off * ldpt, ldpt, Pt + r_off * ldpt, ldpt, T(1), Cp, ld, /*lower_only=*/1);
@@ -453,22 +453,30 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
         LFB_CUDA(cudaEventCreate(&t_base));
         LFB_CUDA(cudaEventRecord(t_base, h.stream));
     }
-    factor_panel(0, std::min<int64_t>(NB, n));
-    if (h.chol_panel_hook) h.chol_panel_hook(0, std::min<int64_t>(NB, n));
-    if (tn && n > NB) transpose<T>(h, A + NB, n - NB, NB, ld, PtBuf[0]->get(), ldpt);
+    // Panel width by position: NB while many rows remain, chol_nb_tail once fewer than chol_tail_rows are left -- there the
+    // step is bound by the panel chain, whose granularity (not its length) is what a narrower panel improves, while the
+    // SYRKs that lose efficiency at the smaller K are short anyway (n = 8192: 12.2 ms at nb 256 against 13.0 at 512).
+    const int64_t NBT = std::min<int64_t>(NB, std::max<int64_t>(CB, round_up(h.opt.chol_nb_tail, CB)));
+    auto width_at = [&](int64_t k0) { return std::min<int64_t>((n - k0 > h.opt.chol_tail_rows) ? NB : NBT, n - k0); };
+    const int64_t nb0 = width_at(0);
+    factor_panel(0, nb0);
+    if (h.chol_panel_hook) h.chol_panel_hook(0, nb0);
+    if (tn && n > nb0) transpose<T>(h, A + nb0, n - nb0, nb0, ld, PtBuf[0]->get(), ldpt);
     mark(h.stream, -1, 0);
     int cur = 0;
-    for (int64_t k0 = 0; k0 < n; k0 += NB, cur ^= 1) {
-        const int64_t nb = std::min<int64_t>(NB, n - k0);
+    int pi = -1;
+    for (int64_t k0 = 0, nb_step = nb0; k0 < n; k0 += nb_step, cur ^= 1) {
+        const int64_t nb = width_at(k0);
+        nb_step = nb;
+        ++pi;
         const int64_t pend = k0 + nb;
         const int64_t rows = n - pend;
         if (rows <= 0) break;
-        const int64_t nbn = std::min<int64_t>(NB, rows);
+        const int64_t nbn = width_at(pend);
         T *P = A + pend + k0 * ld;
         const T *Pt = tn ? PtBuf[cur]->get() : nullptr;
         T *PtNext = tn ? PtBuf[cur ^ 1]->get() : nullptr;
         const int64_t rows2 = rows - nbn;
-        const int pi = (int)(k0 / NB);
         if (la) {
             mark(sm, pi, 1);
             syrk(P, Pt, 0, rows, nbn, nb, A + pend + pend * ld);
