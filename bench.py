@@ -294,7 +294,7 @@ def main():
     achieved_tf = g_fl.value / (g_ms.value * 1e-3) / 1e12 if g_ms.value > 0 else 0.0
     # DRAM traffic of the same launches from the committed ncu capture (bytes per launch, like `achieved`)
     traffic, traffic_note = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_chol16384_gemm_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_chol16384_gemm_traffic.json")
     if n == 16384 and os.path.exists(tp):
         tj = json.load(open(tp))
         traffic = tj["traffic_bytes_per_launch"]
