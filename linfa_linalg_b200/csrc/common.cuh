@@ -79,6 +79,7 @@ struct Options {
     int64_t tsqr_streams = 8;       // chunks in flight (each panel kernel occupies one 16-SM cluster)
     int64_t qr_tsqr_auto = 0;       // 1: lfb_qr_* takes the TSQR + Householder-reconstruction route for tall-skinny inputs (rows >= 2 chunks, cols <= 512)
     int64_t tsqr_cholqr_cond = 16;  // tall-skinny leaf: Cholesky-QR (Gram GEMM + n x n Cholesky) when its cond_2 bound <= this; 0 = always Householder
+    int64_t hr_lu_blocked = 1;      // Householder reconstruction: shared-memory panel LU of the top block (0 = one pivot at a time in global memory)
     int64_t tsqr_graph = 0;         // 1: replay the local TSQR stage of a (buffer, shape) seen before as one CUDA graph
                                     // (measured: 145 vs 147 ms -- the stage is GPU bound, not launch bound -- so off by default)
 };

@@ -57,6 +57,82 @@ __global__ void __launch_bounds__(1024) hr_lu_kernel(T *Q, int64_t ld, int n, T 
     }
 }
 
+// Blocked version of the same LU (n <= 512), one CTA: 32-column panels live in shared memory while they are factored
+// (three CTA barriers per pivot on shared data instead of three round trips to L2 per pivot), the block row U12 = L11^-1 A12
+// is solved from shared memory, and the trailing update A22 -= L21 U12 streams the rest of the matrix through the SM once
+// per PANEL instead of once per pivot: 89 MB -> ~3 MB of L2 traffic at n = 256.  1.75 ms -> ~0.2 ms
+// (profiles/r2_multi_gpu.md); the arithmetic per entry is the same right-looking elimination, s_k = -sgn(q_kk) as before.
+constexpr int HR_PB = 32;
+template <typename T>
+__global__ void __launch_bounds__(1024) hr_lu_blocked_kernel(T *Q, int64_t ld, int n, T *s) {
+    extern __shared__ __align__(16) unsigned char hr_smem[];
+    T *P = reinterpret_cast<T *>(hr_smem);            // panel: [n rows][HR_PB + 1]
+    T *U = P + (size_t)n * (HR_PB + 1);               // block row: [HR_PB][n + 1]
+    __shared__ T s_piv;
+    const int tid = threadIdx.x;
+    for (int k0 = 0; k0 < n; k0 += HR_PB) {
+        const int kb = min(HR_PB, n - k0), m = n - k0;           // panel is m x kb
+        for (int e = tid; e < m * kb; e += 1024) {
+            const int r = e % m, c = e / m;
+            P[r * (HR_PB + 1) + c] = Q[(k0 + r) + (int64_t)(k0 + c) * ld];
+        }
+        __syncthreads();
+        for (int j = 0; j < kb; ++j) {
+            if (tid == 0) {
+                const T q = P[j * (HR_PB + 1) + j];
+                const T sk = q < T(0) ? T(1) : T(-1);            // s_k = -sgn(q_kk), sgn(0) = +1
+                const T p = q - sk;                              // |p| = 1 + |q_kk|
+                P[j * (HR_PB + 1) + j] = p;
+                s[k0 + j] = sk;
+                s_piv = p;
+            }
+            __syncthreads();
+            const T p = s_piv;
+            for (int r = j + 1 + tid; r < m; r += 1024) P[r * (HR_PB + 1) + j] /= p;
+            __syncthreads();
+            const int w = kb - j - 1, hgt = m - j - 1;
+            for (int e = tid; e < w * hgt; e += 1024) {
+                const int r = j + 1 + e % hgt, c = j + 1 + e / hgt;
+                P[r * (HR_PB + 1) + c] -= P[r * (HR_PB + 1) + j] * P[j * (HR_PB + 1) + c];
+            }
+            __syncthreads();
+        }
+        for (int e = tid; e < m * kb; e += 1024) {               // the finished panel goes back
+            const int r = e % m, c = e / m;
+            Q[(k0 + r) + (int64_t)(k0 + c) * ld] = P[r * (HR_PB + 1) + c];
+        }
+        const int nc = n - k0 - kb;                              // columns right of the panel
+        if (nc > 0) {
+            for (int e = tid; e < kb * nc; e += 1024) {          // A12 -> shared
+                const int j = e % kb, c = e / kb;
+                U[j * (n + 1) + c] = Q[(k0 + j) + (int64_t)(k0 + kb + c) * ld];
+            }
+            __syncthreads();
+            for (int c = tid; c < nc; c += 1024)                 // U12 = L11^-1 A12 (unit lower), one column per thread
+                for (int j = 1; j < kb; ++j) {
+                    T acc = U[j * (n + 1) + c];
+                    for (int i = 0; i < j; ++i) acc -= P[j * (HR_PB + 1) + i] * U[i * (n + 1) + c];
+                    U[j * (n + 1) + c] = acc;
+                }
+            __syncthreads();
+            for (int e = tid; e < kb * nc; e += 1024) {
+                const int j = e % kb, c = e / kb;
+                Q[(k0 + j) + (int64_t)(k0 + kb + c) * ld] = U[j * (n + 1) + c];
+            }
+            const int mr = m - kb;                               // rows below the panel's diagonal block
+            for (int e = tid; e < mr * nc; e += 1024) {          // A22 -= L21 U12
+                const int r = e % mr, c = e / mr;
+                const T *l = P + (size_t)(kb + r) * (HR_PB + 1);
+                T acc = T(0);
+#pragma unroll 8
+                for (int i = 0; i < kb; ++i) acc += l[i] * U[i * (n + 1) + c];
+                Q[(k0 + kb + r) + (int64_t)(k0 + kb + c) * ld] -= acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // c_k and diag_ref[k] from the LU pivots, the signs and diag(R).
 template <typename T>
 __global__ void hr_scale_kernel(const T *Q, int64_t ld, int n, const T *R, int64_t ldr, const T *s, T *c, T *diag) {
@@ -102,7 +178,16 @@ template <typename T>
 void hh_reconstruct_top(lfb_handle &h, T *Qtop, int64_t n, int64_t ld, const T *R, int64_t ldr, T *U, int64_t ldu, T *diag) {
     if (n <= 0) return;
     DevBuf<T> s(h, n), c(h, n);
-    hr_lu_kernel<T><<<1, 1024, 0, h.stream>>>(Qtop, ld, (int)n, s);
+    const size_t smem_lu = sizeof(T) * ((size_t)n * (HR_PB + 1) + (size_t)HR_PB * (n + 1));
+    if (h.opt.hr_lu_blocked && n <= 512 && smem_lu + 1024 <= h.smem_optin) {
+        static DeviceOnce cfg;   // function attributes are per device
+        cfg.run(h.device, [&] {
+            LFB_CUDA(cudaFuncSetAttribute(hr_lu_blocked_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem_optin - 1024));   // minus the static s_piv
+        });
+        hr_lu_blocked_kernel<T><<<1, 1024, smem_lu, h.stream>>>(Qtop, ld, (int)n, s);
+    } else {
+        hr_lu_kernel<T><<<1, 1024, 0, h.stream>>>(Qtop, ld, (int)n, s);
+    }
     LFB_LAUNCH_CHECK(h);
     hr_scale_kernel<T><<<(unsigned)cdiv(n, 256), 256, 0, h.stream>>>(Qtop, ld, (int)n, R, ldr, s, c, diag);
     LFB_LAUNCH_CHECK(h);
