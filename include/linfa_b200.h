@@ -141,6 +141,15 @@ int lfb_qr_solve_f64(lfb_handle *h, const double *qr, int64_t rows, int64_t cols
 int lfb_qr_solve_f32(lfb_handle *h, const float *qr, int64_t rows, int64_t cols, int64_t rs, int64_t cs, const float *diag,
                      const float *b, int64_t b_rows, int64_t bcols, int64_t b_rs, int64_t b_cs,
                      float *x, int64_t x_rs, int64_t x_cs);
+/* qr.rs:156-181 QRDecomp::solve_tr_into on an existing compact factor + diag: x (rows x bcols) = Q (R^-T b), b is cols x bcols.
+ * The triangular solve (R^T m = b with |diag| as the diagonal, :172-177), generate_q (:180) and the product Q m run on the
+ * device in one round trip.  LFB_WRONG_ROWS if b does not have `cols` rows (:160-165), LFB_NON_INVERTIBLE (:166-168). */
+int lfb_qr_solve_tr_f64(lfb_handle *h, const double *qr, int64_t rows, int64_t cols, int64_t rs, int64_t cs, const double *diag,
+                        const double *b, int64_t b_rows, int64_t bcols, int64_t b_rs, int64_t b_cs,
+                        double *x, int64_t x_rs, int64_t x_cs);
+int lfb_qr_solve_tr_f32(lfb_handle *h, const float *qr, int64_t rows, int64_t cols, int64_t rs, int64_t cs, const float *diag,
+                        const float *b, int64_t b_rows, int64_t bcols, int64_t b_rs, int64_t b_cs,
+                        float *x, int64_t x_rs, int64_t x_cs);
 /* cholesky.rs:118-163 SolveCInplace / SolveC: b (n x bcols) is overwritten with the solution of A x = b;
  * with write_factor != 0, a receives its Cholesky factor in the lower triangle (solvec_inplace, :136-144).
  * LFB_NOT_POSITIVE_DEFINITE reports the failing pivot in *fail_index. */

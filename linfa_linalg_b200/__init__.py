@@ -222,8 +222,10 @@ class QRDecomp:
             raise WrongRows(n, b.shape[0])
         if not self.is_invertible():
             raise NonInvertible()
-        _solve_tri(self._e, self.qr[:n, :n].T, b, LOWER, np.abs(self.diag))
-        return self.generate_q() @ b  # :180 (Q.dot(b) is ndarray GEMM in the reference too)
+        x = np.zeros((self.qr.shape[0], b.shape[1]), dtype=self.qr.dtype)
+        st = self._e.call("lfb_qr_solve_tr" + _sfx(self.qr), *_view(self.qr), _vecp(self.diag), *_view(b), *_view(x)[:1], *_view(x)[3:])
+        self._e._check(st)          # R^T m = b, generate_q and Q m on the device in one round trip (:172-180)
+        return x
 
     def solve(self, b):  # qr.rs:184-186
         return self.solve_into(_owned(b).astype(self.qr.dtype, copy=False))

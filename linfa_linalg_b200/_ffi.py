@@ -49,6 +49,7 @@ _TYPED = {
     "lfb_eigh": [_vp] + _VIEW + [_vp, _vp, _i64, _i64],
     "lfb_least_squares": [_vp] + _VIEW + _VIEW + [_vp, _i64, _i64],
     "lfb_qr_solve": [_vp] + _VIEW + [_vp] + _VIEW + [_vp, _i64, _i64],
+    "lfb_qr_solve_tr": [_vp] + _VIEW + [_vp] + _VIEW + [_vp, _i64, _i64],
     "lfb_solvec": [_vp] + _VIEW + [_int] + _VIEW + [C.POINTER(_i64)],
     "lfb_invc": [_vp] + _VIEW + [_vp, _i64, _i64, C.POINTER(_i64)],
     "lfb_svd": [_vp] + _VIEW + [_vp, _vp, _i64, _i64, _vp, _i64, _i64],

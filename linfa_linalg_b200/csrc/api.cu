@@ -455,6 +455,32 @@ int qr_solve_host(lfb_handle *h, const T *qr, int64_t rows, int64_t cols, int64_
     LFB_API_END(h)
 }
 
+// QRDecomp::solve_tr_into (qr.rs:156-181): x (rows x bcols) = Q m with R^T m = b.
+template <typename T>
+int qr_solve_tr_host(lfb_handle *h, const T *qr, int64_t rows, int64_t cols, int64_t rs, int64_t cs, const T *diag, const T *b,
+                     int64_t b_rows, int64_t bcols, int64_t b_rs, int64_t b_cs, T *x, int64_t x_rs, int64_t x_cs) {
+    if (rows < cols) return fail(h, LFB_NOT_THIN, "Expected matrix rows >= cols");
+    if (b_rows != cols) return fail(h, LFB_WRONG_ROWS, "Matrix has the wrong number of rows");      // :160-165
+    for (int64_t i = 0; i < cols; ++i)
+        if (diag[i] == T(0)) return fail(h, LFB_NON_INVERTIBLE, "Matrix is not invertible");         // :166-168
+    if (rows == 0 || cols == 0 || bcols == 0) return LFB_OK;
+    LFB_API_BEGIN(h)
+    const int64_t ld = round_up(rows, 4), ldb = round_up(cols, 2);
+    DevBuf<T> dM(*h, (size_t)ld * cols), dQ(*h, (size_t)ld * cols), dB(*h, (size_t)ldb * bcols), dX(*h, (size_t)ld * bcols);
+    DevBuf<T> dD(*h, cols), dAbs(*h, cols);
+    std::vector<T> ad((size_t)cols);
+    for (int64_t i = 0; i < cols; ++i) ad[i] = std::fabs(diag[i]);
+    upload<T>(*h, qr, rows, cols, rs, cs, dM, ld);
+    upload<T>(*h, b, cols, bcols, b_rs, b_cs, dB, ldb);
+    upload_vec<T>(*h, diag, cols, dD);
+    upload_vec<T>(*h, ad.data(), cols, dAbs);
+    trsm_left<T>(*h, 0, 1, cols, bcols, dM, ld, dAbs, dB, ldb);                                      // :172-177  R^T m = b
+    assemble_q<T>(*h, dM, rows, cols, ld, 0, dD, dQ, ld);                                            // :180 generate_q
+    gemm<T>(*h, 0, 0, rows, bcols, cols, T(1), dQ, ld, dB, ldb, T(0), dX, ld);                       // :180 Q m
+    download<T>(*h, dX, ld, x, rows, bcols, x_rs, x_cs);
+    LFB_API_END(h)
+}
+
 // cholesky.rs:136-144 SolveCInplace::solvec_inplace (b in place; a receives its Cholesky factor in the lower
 // triangle when write_factor != 0, as `cholesky_inplace_dirty` leaves it) and, with b == nullptr, cholesky.rs:178-182
 // InverseCInplace::invc_inplace (the identity right-hand side is generated on the device; result in x).
@@ -855,6 +881,10 @@ int lfb_eigh_f32(lfb_handle *h, const float *a, int64_t r, int64_t c, int64_t rs
     int lfb_qr_solve_##SFX(lfb_handle *h, const T *qr, int64_t r, int64_t c, int64_t rs, int64_t cs, const T *diag, const T *b, \
                            int64_t br, int64_t bc, int64_t brs, int64_t bcs, T *x, int64_t xrs, int64_t xcs) {             \
         return qr_solve_host<T>(h, qr, r, c, rs, cs, diag, b, br, bc, brs, bcs, x, xrs, xcs);                              \
+    }                                                                                                                      \
+    int lfb_qr_solve_tr_##SFX(lfb_handle *h, const T *qr, int64_t r, int64_t c, int64_t rs, int64_t cs, const T *diag, const T *b, \
+                              int64_t br, int64_t bc, int64_t brs, int64_t bcs, T *x, int64_t xrs, int64_t xcs) {          \
+        return qr_solve_tr_host<T>(h, qr, r, c, rs, cs, diag, b, br, bc, brs, bcs, x, xrs, xcs);                           \
     }                                                                                                                      \
     int lfb_solvec_##SFX(lfb_handle *h, T *a, int64_t r, int64_t c, int64_t rs, int64_t cs, int write_factor, T *b, int64_t br, \
                          int64_t bc, int64_t brs, int64_t bcs, int64_t *fail_index) {                                      \

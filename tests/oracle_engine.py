@@ -81,6 +81,23 @@ class OracleEngine:
     def close(self):
         pass
 
+    def _qr_solve_tr(self, sfx, p, rows, cols, rs, cs, diag, b, b_rows, bcols, b_rs, b_cs, x, x_rs, x_cs):
+        """qr.rs:156-181 solve_tr_into: R^T m = b with |diag| as the diagonal, then Q m."""
+        if rows < cols:
+            return NOT_THIN
+        if b_rows != cols:
+            return WRONG_ROWS
+        d = _vec(diag, cols, sfx)
+        if np.any(d == 0):
+            return NON_INVERTIBLE
+        if rows == 0 or cols == 0 or bcols == 0:
+            return OK
+        qrm = _mat(p, rows, cols, rs, cs, sfx)
+        w = np.array(_mat(b, cols, bcols, b_rs, b_cs, sfx))
+        O.solve_triangular(qrm[:cols, :cols].T, w, O.LOWER, ext_diag=np.abs(d))
+        _mat(x, rows, bcols, x_rs, x_cs, sfx)[...] = O.generate_q(qrm, d) @ w
+        return OK
+
     # -- lobpcg/algorithm.rs:16-44 -----------------------------------------------------------------------------
     def _sorted_eig(self, sfx, a, k, a_rs, a_cs, b, b_rs, b_cs, size, order, vals, vecs, v_rs, v_cs):
         if k == 0:

@@ -328,6 +328,26 @@ def test_svd_f32(L, eng):  # tests/svd.rs:66-72
     assert np.max(np.abs(vt - np.eye(2))) <= 1e-7
 
 
+def test_qr_solve_tr(L, eng):  # src/qr.rs:156-191 solve_tr_into / solve_tr: the minimum-norm solution of A^T x = b
+    for rng in cases(14):
+        cols = dims(rng)
+        rows = int(rng.integers(cols, 11))
+        vals, lay = matrix(rng, rows, cols)
+        k = dims(rng)
+        b = rng.uniform(*FLOAT_RANGE, (cols, k))
+        if np.linalg.cond(vals) > 1e6:
+            continue
+        dec = L.qr(with_layout(vals, *lay), eng)
+        x = dec.solve_tr(b)
+        assert x.shape == (rows, k)
+        scale = max(1.0, np.max(np.abs(x)))
+        assert np.max(np.abs(vals.T @ x - b)) <= 1e-7 * scale * np.linalg.cond(vals)
+        q = dec.generate_q()
+        assert np.max(np.abs(x - q @ (q.T @ x))) <= 1e-7 * scale          # x lies in range(Q): the minimum-norm solution
+        with pytest.raises(L.WrongRows):                                    # :160-165
+            dec.solve_tr(np.zeros((cols + 1, 1)))
+
+
 # ---- src/lobpcg/algorithm.rs: the dense helpers of LOBPCG ---------------------------------------------------------------------
 def test_lobpcg_sorted_eigen(L, eng):  # src/lobpcg/algorithm.rs:457-472
     m = np.random.default_rng(21).uniform(0, 1, (10, 10)) * 10.0
