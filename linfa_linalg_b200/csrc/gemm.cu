@@ -9,6 +9,8 @@
 //
 // This is the reference's XXX at src/reflection.rs:23 ("Can use matrix multiplication algorithm
 // instead of iterative algorithm") made concrete: every trailing update funnels here.
+#include <memory>
+
 #include "common.cuh"
 
 namespace lfb {
@@ -27,6 +29,7 @@ struct GemmP {
     int ksplit;      // K range per blockIdx.z (multiple of BK)
     int atomic;      // accumulate alpha*acc with atomicAdd (C pre-scaled by beta)
     int vecA, vecB, vecC;
+    int64_t zstride; // deterministic split-K: split z writes its partial tile to C + z * zstride (a workspace slice)
 };
 
 __device__ __forceinline__ double2 ldg2(const double *p, bool v0, bool v1, bool vec) {
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(256) dgemm_kernel(GemmP p) {
         __syncthreads();
     }
 
-    double *__restrict__ C = static_cast<double *>(p.C);
+    double *__restrict__ C = static_cast<double *>(p.C) + (int64_t)blockIdx.z * p.zstride;
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(512, 1) dgemm_v2_kernel(GemmP p) {
     }
     cp_async_wait<0>();
 
-    double *__restrict__ C = static_cast<double *>(p.C);
+    double *__restrict__ C = static_cast<double *>(p.C) + (int64_t)blockIdx.z * p.zstride;
     const double alpha = p.alpha, beta = p.beta;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -361,6 +364,7 @@ struct SgemmP {
     float *C;
     float alpha, beta;
     int lower_only, ksplit, atomic;
+    int64_t zstride;   // as GemmP::zstride
 };
 
 __global__ void __launch_bounds__(256) sgemm_kernel(SgemmP p) {
@@ -410,7 +414,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(SgemmP p) {
             int m = m0 + tx * 4 + i;
             if (m >= p.M) continue;
             if (p.lower_only && m < n) continue;
-            float *c = p.C + m + (int64_t)n * p.ldc;
+            float *c = p.C + (int64_t)blockIdx.z * p.zstride + m + (int64_t)n * p.ldc;
             float v = p.alpha * acc[j][i];
             if (p.atomic) atomicAdd(c, v);
             else *c = v + (p.beta != 0.f ? p.beta * *c : 0.f);
@@ -446,6 +450,22 @@ void launch_dgemm(lfb_handle &h, const GemmP &p, dim3 grid) {
         dgemm_kernel<AM, BMo><<<grid, 256, smem, h.stream>>>(p);
     }
     LFB_LAUNCH_CHECK(h);
+}
+
+// C = beta C + sum_z W_z in the fixed order z = 0, 1, ...: second stage of the deterministic split-K of the fallback kernels
+template <typename T>
+__global__ void splitk_reduce_any_kernel(const T *__restrict__ W, int64_t ldw, int64_t zstride, int splits, T *__restrict__ C, int64_t M,
+                                         int64_t N, int64_t ldc, T beta, int lower_only) {
+    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    for (int64_t n = blockIdx.y; n < N; n += gridDim.y) {
+        if (lower_only && m < n) continue;
+        const T *w = W + m + n * ldw;
+        T acc = T(0);
+        for (int z = 0; z < splits; ++z) acc += w[(int64_t)z * zstride];
+        T *c = C + m + n * ldc;
+        *c = beta == T(0) ? acc : beta * *c + acc;
+    }
 }
 
 inline int choose_splits(lfb_handle &h, int64_t tiles, int64_t K, int bk) {
@@ -506,17 +526,32 @@ static void dgemm_impl(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int6
     int splits = choose_splits(h, tm * tn, K, BK);
     p.ksplit = (int)round_up(cdiv(K, splits), BK);
     splits = (int)cdiv(K, p.ksplit);
-    p.atomic = splits > 1;
-    if (p.atomic && beta != 1.0) {
-        dim3 g((unsigned)cdiv(M, 256), (unsigned)(N < 65535 ? N : 65535));
-        scale_kernel<double><<<g, 256, 0, h.stream>>>(C, M, N, ldc, beta, lower_only);
-        LFB_LAUNCH_CHECK(h);
+    p.zstride = 0;
+    std::unique_ptr<DevBuf<double>> work;
+    const int64_t ldw = round_up(M, 2);
+    const bool det = splits > 1 && h.opt.gemm_deterministic;     // slices + ordered reduce instead of atomicAdd (bit-reproducible)
+    if (det) {
+        work.reset(new DevBuf<double>(h, (size_t)ldw * N * splits));
+        p.C = work->get(); p.ldc = ldw; p.zstride = ldw * N;
+        p.beta = 0.0; p.atomic = 0; p.vecC = 1;
+    } else {
+        p.atomic = splits > 1;
+        if (p.atomic && beta != 1.0) {
+            dim3 g((unsigned)cdiv(M, 256), (unsigned)(N < 65535 ? N : 65535));
+            scale_kernel<double><<<g, 256, 0, h.stream>>>(C, M, N, ldc, beta, lower_only);
+            LFB_LAUNCH_CHECK(h);
+        }
     }
     dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)splits);
     if (ta == 0 && tb == 0) launch_dgemm<0, 0>(h, p, grid);
     else if (ta == 1 && tb == 0) launch_dgemm<1, 0>(h, p, grid);
     else if (ta == 0 && tb == 1) launch_dgemm<0, 1>(h, p, grid);
     else launch_dgemm<1, 1>(h, p, grid);
+    if (det) {
+        dim3 g((unsigned)cdiv(M, 128), (unsigned)(N < 65535 ? N : 65535));
+        splitk_reduce_any_kernel<double><<<g, 128, 0, h.stream>>>(work->get(), ldw, p.zstride, splits, C, M, N, ldc, beta, lower_only);
+        LFB_LAUNCH_CHECK(h);
+    }
 }
 
 // Defined in gemm_tf32.cu (tcgen05 / TMEM, 3xTF32): returns true if it handled the call.
@@ -555,15 +590,30 @@ void gemm<float>(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int64_t K,
     int splits = choose_splits(h, tm * tn, K, 16);
     p.ksplit = (int)round_up(cdiv(K, splits), 16);
     splits = (int)cdiv(K, p.ksplit);
-    p.atomic = splits > 1;
-    if (p.atomic && beta != 1.f) {
-        dim3 g((unsigned)cdiv(M, 256), (unsigned)(N < 65535 ? N : 65535));
-        scale_kernel<float><<<g, 256, 0, h.stream>>>(C, M, N, ldc, beta, lower_only);
-        LFB_LAUNCH_CHECK(h);
+    p.zstride = 0;
+    std::unique_ptr<DevBuf<float>> work;
+    const int64_t ldw = round_up(M, 4);
+    const bool det = splits > 1 && h.opt.gemm_deterministic;
+    if (det) {
+        work.reset(new DevBuf<float>(h, (size_t)ldw * N * splits));
+        p.C = work->get(); p.ldc = ldw; p.zstride = ldw * N;
+        p.beta = 0.f; p.atomic = 0;
+    } else {
+        p.atomic = splits > 1;
+        if (p.atomic && beta != 1.f) {
+            dim3 g((unsigned)cdiv(M, 256), (unsigned)(N < 65535 ? N : 65535));
+            scale_kernel<float><<<g, 256, 0, h.stream>>>(C, M, N, ldc, beta, lower_only);
+            LFB_LAUNCH_CHECK(h);
+        }
     }
     dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)splits);
     sgemm_kernel<<<grid, 256, 0, h.stream>>>(p);
     LFB_LAUNCH_CHECK(h);
+    if (det) {
+        dim3 g((unsigned)cdiv(M, 128), (unsigned)(N < 65535 ? N : 65535));
+        splitk_reduce_any_kernel<float><<<g, 128, 0, h.stream>>>(work->get(), ldw, p.zstride, splits, C, M, N, ldc, beta, lower_only);
+        LFB_LAUNCH_CHECK(h);
+    }
 }
 
 }  // namespace lfb

@@ -123,3 +123,33 @@ def test_qr_f32_1536x1280_on_tensor_cores(L, mode):
     q64 = q.astype(np.float64)
     assert np.linalg.norm(q64.T @ q64 - np.eye(n)) <= 16 * m * EPS32
     assert np.linalg.norm(q64 @ r - a0) <= 16 * m * EPS32 * np.linalg.norm(a0.astype(np.float64))
+
+
+@pytest.mark.parametrize("dt,ta,m,n,k", [("f64", 1, 128, 256, 200000), ("f64", 1, 37, 19, 100001), ("f64", 0, 64, 40, 50000),
+                                         ("f32", 1, 128, 128, 65536), ("f32", 1, 33, 70, 100001)])
+def test_split_k_is_bit_reproducible(L, dt, ta, m, n, k):
+    """Skinny outputs with a long K are split over CTAs; the partial tiles are summed by a reduce kernel in a fixed order
+    (`gemm_deterministic`, default), so repeated calls give bit-identical results -- like the reference's sequential loops --
+    on all four GEMM kernels (f64 TMA, f64 fallback, f32 tcgen05, f32 FFMA fallback)."""
+    import torch
+    tdt = torch.float64 if dt == "f64" else torch.float32
+    e = L.Engine(0)
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    A = torch.rand((m, k) if ta else (k, m), dtype=tdt, device="cuda", generator=g) - 0.5       # column-major storage of op's operand
+    B = torch.rand((n, k), dtype=tdt, device="cuda", generator=g) - 0.5                         # column-major k x n
+    outs = []
+    for _ in range(3):
+        Cm = torch.zeros((n, m), dtype=tdt, device="cuda")
+        torch.cuda.synchronize()
+        e.set_stream(torch.cuda.current_stream().cuda_stream)
+        st = e.call("lfb_gemm_dev_" + dt, ta, 0, m, n, k, 1.0, C.c_void_p(A.data_ptr()), A.stride(0), C.c_void_p(B.data_ptr()), B.stride(0),
+                    0.0, C.c_void_p(Cm.data_ptr()), m)
+        e._check(st)
+        torch.cuda.synchronize()
+        e.set_stream(None)
+        outs.append(Cm.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = (A.double() if ta else A.double().t()) @ B.double().t()
+    tol = (1e-11 if dt == "f64" else 2e-6) * k
+    assert float((outs[0].t().double() - ref).abs().max()) <= tol
+    e.close()
