@@ -38,6 +38,7 @@ struct TmaP {
     double *C;
     double alpha, beta;
     int lower_only, ksplit, atomic, vecC;
+    int tri;            // lower_only on a square tile grid: blockIdx.x enumerates the LIVE tiles (i >= j) row by row -- no dead CTAs
     int partial;        // deterministic split-K: split z writes alpha * (its partial product) to C + z * zstride (ld = ldc), no atomics
     int64_t zstride;
 };
@@ -103,7 +104,15 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint64_t *empty = full + STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    int ti = blockIdx.x, tj = blockIdx.y;
+    if (p.tri) {                                                   // t = i (i + 1) / 2 + j,  j <= i
+        const int t = blockIdx.x;
+        ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while (ti * (ti + 1) / 2 > t) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        tj = t - ti * (ti + 1) / 2;
+    }
+    const int m0 = ti * BM, n0 = tj * BN;
     if (p.lower_only && m0 + BM <= n0) return;
     const int kbeg = blockIdx.z * p.ksplit;
     const int kend = min(p.K, kbeg + p.ksplit);
@@ -394,6 +403,11 @@ bool dgemm_tma_try(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int64_t 
         }
     }
     dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)splits);
+    p.tri = 0;
+    if (lower_only && tm == tn && tm > 1 && tm < 40000) {          // the SYRK of the Cholesky: only the tm (tm + 1) / 2 live tiles are launched
+        p.tri = 1;
+        grid = dim3((unsigned)(tm * (tm + 1) / 2), 1, (unsigned)splits);
+    }
     if (AK && BKm) launch<1, 1>(h, ma, mb, p, grid);
     else if (AK && !BKm) launch<1, 0>(h, ma, mb, p, grid);
     else if (!AK && BKm) launch<0, 1>(h, ma, mb, p, grid);
