@@ -28,10 +28,14 @@ flops = n ** 3 / 3 if kind == "chol" else 4.0 / 3.0 * n ** 3
 for spec in sys.argv[4:]:
     eng = L.Engine(0)
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    prof = False
     if spec != "-":
         for kv in spec.split(","):
             k, v = kv.split("=")
-            eng.set_option(k, int(v))
+            if k == "prof":                 # serial run under the GEMM profiler (look-ahead off): GEMM share of the factorisation
+                prof = int(v) != 0
+            else:
+                eng.set_option(k, int(v))
 
     def step():
         W.copy_(S)
@@ -49,6 +53,22 @@ for spec in sys.argv[4:]:
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     res = {"kind": kind + ("_f32" if f32 else "_f64"), "n": n, "opts": spec, "ms": round(best, 3), "tflops": round(flops / best / 1e9, 2)}
+    if prof:
+        gms, gfl, gc = C.c_double(), C.c_double(), C.c_int64()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        W.copy_(S)
+        eng.lib.lfb_profile_begin(eng.h)
+        e0.record()
+        if kind == "chol":
+            getattr(eng.lib, "lfb_cholesky_dev" + sfx)(eng.h, p(W), n, n, 0, p(aux))
+        else:
+            getattr(eng.lib, "lfb_qr_dev" + sfx)(eng.h, p(W), n, n, n, p(aux))
+        e1.record()
+        torch.cuda.synchronize()
+        eng.lib.lfb_profile_end(eng.h, C.byref(gms), C.byref(gfl), C.byref(gc))
+        res.update({"prof_total_ms": round(e0.elapsed_time(e1), 3), "prof_gemm_ms": round(gms.value, 3), "prof_gemm_calls": gc.value,
+                    "prof_gemm_tflops": round(gfl.value / max(gms.value, 1e-9) / 1e9, 2), "prof_gemm_flop_share": round(gfl.value / flops, 4)})
     if kind == "chol":
         Lf = torch.triu(W[:2048, :2048]).t().double()
         Sd = S[:2048, :2048].double()
