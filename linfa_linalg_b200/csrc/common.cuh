@@ -45,6 +45,8 @@ struct Options {
     int64_t qr_nb = 128;     // outer panel width of blocked compact-WY QR
     int64_t qr_nb_f32 = 256; // same for f32 when the trailing updates run on the tcgen05 kernel (n >= 2048)
     int64_t qr_vt = 0;       // f64 QR: rank-nb update through a transposed copy of V (TN form); measured: no gain (263.8 vs 263.5 ms), off
+    int64_t qr_panel_cholqr = 1; // f64 blocked QR: panel = guarded Cholesky-QR + Householder reconstruction (tsqr_hr.cu) when its condition bound passes; else the cluster panel kernels
+    int64_t qr_trace = 0;    // debug: event time stamps of every stage of the look-ahead pipeline on stderr
     int64_t qr_sub = 32;     // inner BLAS-2 sub-panel width (<= 32)
     int64_t chol_base = 64;  // recursion base of Cholesky / TRSM (<= 64)
     int64_t chol_nb = 512;   // right-looking panel width of Cholesky (K of the trailing SYRK)
@@ -55,6 +57,9 @@ struct Options {
     int64_t chol_trace = 0;    // debug: event time stamps of every stage of the look-ahead pipeline on stderr
     int64_t chol_potf2_rl = 1; // diagonal 64 x 64 blocks: right-looking register-blocked kernel (0 = first-generation left-looking)
     int64_t gemm_tma = 1;    // use the TMA-fed DGEMM when operands are 16-byte aligned
+    int64_t gemm_tma2 = 1;   // f64 TMA GEMM with 128 x 64 tiles and two CTAs per SM (one's epilogue under the other's main loop): K <= gemm_tma2_maxk with at
+                             // least one wave of tiles, and split-K products with one row of tiles (W = V^T C); 2 = every split-K product; 0 = off
+    int64_t gemm_tma2_maxk = 1024;
     int64_t gemm_splitk = 1; // allow split-K for skinny-output GEMMs
     int64_t gemm_deterministic = 1; // split-K partial tiles summed in a fixed order by a reduce kernel (0 = atomicAdd epilogue)
     int64_t gemm_split_waves = 6; // target waves of (tile, split-K) work items for skinny outputs
@@ -157,7 +162,12 @@ struct lfb_handle {
     lfb::Options opt;
 
     // ---- caching device allocator (the engine reuses workspaces across calls) ----
-    struct Block { void *p; size_t bytes; bool used; };
+    // A freed block remembers the stream that was current when it was released: work still queued there may be reading it, so
+    // only a request made on the SAME stream (ordered behind that work) may take it.  The look-ahead drivers run two or three
+    // streams of one handle concurrently and both sides allocate split-K workspaces; without the tag a side-stream GEMM could be
+    // handed the workspace a main-stream GEMM is still reducing.  switch_stream() synchronises and clears the tags.
+    struct Block { void *p; size_t bytes; bool used; cudaStream_t st; bool tagged; };
+    void untag_blocks() { for (auto &b : blocks) b.tagged = false; }
     std::vector<Block> blocks;
     void *pinned = nullptr; size_t pinned_bytes = 0;
     lfb::HostPool *host_pool = nullptr;          // created on first use (pageable staging copies)
@@ -207,7 +217,7 @@ struct lfb_handle {
         bytes = (bytes + 255) & ~size_t(255);
         int best = -1;
         for (int i = 0; i < (int)blocks.size(); ++i)
-            if (!blocks[i].used && blocks[i].bytes >= bytes && blocks[i].bytes <= 2 * bytes + (1 << 20))
+            if (!blocks[i].used && (!blocks[i].tagged || blocks[i].st == stream) && blocks[i].bytes >= bytes && blocks[i].bytes <= 2 * bytes + (1 << 20))
                 if (best < 0 || blocks[i].bytes < blocks[best].bytes) best = i;
         if (best >= 0) { blocks[best].used = true; return blocks[best].p; }
         void *p = nullptr;
@@ -222,11 +232,11 @@ struct lfb_handle {
                 throw lfb::CudaError(LFB_ERR_ALLOC, "device allocation of " + std::to_string(bytes) + " bytes failed");
             }
         }
-        blocks.push_back({p, bytes, true});
+        blocks.push_back({p, bytes, true, nullptr, false});
         return p;
     }
     void dfree(void *p) {
-        for (auto &b : blocks) if (b.p == p) { b.used = false; return; }
+        for (auto &b : blocks) if (b.p == p) { b.used = false; b.st = stream; b.tagged = true; return; }
     }
     void trim() {
         drop_graphs();   // captured graphs hold pointers into the pool
@@ -327,7 +337,7 @@ template <typename T> void apply_constraints(lfb_handle &h, T *V, int64_t n, int
 template <typename T> bool sorted_eig_dev(lfb_handle &h, T *dA, int64_t lda, T *dB, int64_t ldb, int64_t k, int64_t size, int order, T *vals_host,
                                           T *dVecs, int64_t ldv);
 // Householder reconstruction (tsqr_hr.cu): top n x n block of an explicit Q -> reference compact form; U' for the rows below.
-template <typename T> void hh_reconstruct_top(lfb_handle &h, T *Qtop, int64_t n, int64_t ld, const T *R, int64_t ldr, T *U, int64_t ldu, T *diag);
+template <typename T> void hh_reconstruct_top(lfb_handle &h, T *Qtop, int64_t n, int64_t ld, const T *R, int64_t ldr, T *U, int64_t ldu, T *diag, int internal = 0);
 // Tall-skinny thin QR in the reference's compact form (identical contract to qr_factor) via TSQR + reconstruction.
 template <typename T> void qr_tsqr(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *diag);
 // Cholesky-QR leaf (cholqr.cu): R (n x n upper, diag >= 0) and optionally R^-1 of a tall block WITHOUT touching A; returns

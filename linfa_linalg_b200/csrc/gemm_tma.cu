@@ -38,6 +38,7 @@ struct TmaP {
     double *C;
     double alpha, beta;
     int lower_only, ksplit, atomic, vecC;
+    int ptn;            // dgemm_tma2_kernel with tri: number of 64-column tile columns
     int tri;            // lower_only on a square tile grid: blockIdx.x enumerates the LIVE tiles (i >= j) row by row -- no dead CTAs
     int partial;        // deterministic split-K: split z writes alpha * (its partial product) to C + z * zstride (ld = ldc), no atomics
     int64_t zstride;
@@ -282,6 +283,191 @@ dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
 }
 
+// ---- two CTAs per SM -------------------------------------------------------------------------------------------------
+// With K = nb = 128 (QR trailing update) a 128 x 128 tile's main loop is 8 k-steps, and all sixteen consumer warps of the ONE
+// resident CTA leave it together: the FP64 tensor pipe idles for the whole epilogue (C read-modify-write), 24 us per tile against
+// 17 us of DMMA time.  A persistent tile loop does not change that (profiles/r2_dgemm_tn.md).  Here the tile is 128 x 64 with eight
+// warps (same 32 x 32 warp tile, same fragment code), a 4-stage 24 KB ring and <= 128 registers, so TWO CTAs share an SM and one's
+// epilogue overlaps the other's main loop.  No producer warp (a ninth warp would round the register allocation up to twelve):
+// thread 0 refills the slot the CTA finished one iteration earlier.
+constexpr int BN2 = 64, NC2 = 8, ST2 = 4;
+constexpr int TILE_B2 = BN2 * BK * 8;             // 8 KB
+constexpr int STAGE2 = TILE_BYTES + TILE_B2;      // 24 KB
+
+template <int AK, int BKm>
+__global__ void __launch_bounds__(NC2 * 32, 2)
+dgemm_tma2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TmaP p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + ST2 * STAGE2);
+    uint64_t *empty = full + ST2;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int ti = blockIdx.x, tj = blockIdx.y;
+    if (p.tri) {   // lower_only: row i of 128-row tiles has min(2 (i + 1), ptn) live 64-column tiles; blockIdx.x enumerates them row by row
+        const int t = blockIdx.x;
+        const int full_rows = p.ptn / 2;                      // rows i < full_rows hold 2 (i + 1) tiles: t < full_rows (full_rows + 1)
+        if (t < full_rows * (full_rows + 1)) {
+            ti = (int)((sqrtf(4.f * (float)t + 1.f) - 1.f) * 0.5f);
+            while (ti * (ti + 1) > t) --ti;
+            while ((ti + 1) * (ti + 2) <= t) ++ti;
+            tj = t - ti * (ti + 1);
+        } else {
+            const int r = t - full_rows * (full_rows + 1);
+            ti = full_rows + r / p.ptn;
+            tj = r % p.ptn;
+        }
+    }
+    const int m0 = ti * BM, n0 = tj * BN2;
+    if (p.lower_only && m0 + BM <= n0) return;
+    const int kbeg = blockIdx.z * p.ksplit;
+    const int kend = min(p.K, kbeg + p.ksplit);
+    if (kbeg >= kend) return;
+    const int KT = (kend - kbeg + BK - 1) / BK;
+
+    auto load_stage = [&](int kt) {
+        const int slot = kt % ST2;
+        mbar_wait(&empty[slot], ((kt / ST2) & 1) ^ 1);      // the previous use of the slot has been consumed by all eight warps
+        mbar_expect_tx(&full[slot], STAGE2);
+        unsigned char *sa = smem + slot * STAGE2, *sb = sa + TILE_BYTES;
+        const int k0 = kbeg + kt * BK;
+        if (AK) {
+            tma_load_2d(sa, &mapA, k0, m0, &full[slot]);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) tma_load_2d(sa + b * 2048, &mapA, m0 + 16 * b, k0, &full[slot]);
+        }
+        if (BKm) {
+            tma_load_2d(sb, &mapB, k0, n0, &full[slot]);
+        } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) tma_load_2d(sb + b * 2048, &mapB, n0 + 16 * b, k0, &full[slot]);
+        }
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < ST2; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NC2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int kt = 0; kt < ST2 - 1 && kt < KT; ++kt) load_stage(kt);
+    }
+    __syncthreads();
+
+    const int gid = lane >> 2, tig = lane & 3;
+    const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;
+    uint32_t abase[4], apre[4], bbase[4], bpre[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        {
+            const int r = wm0 + frag_row<AK>(f, gid);
+            if (AK) {
+                abase[f] = r * 128 + (tig & 1) * 8;
+                apre[f] = (uint32_t)(((r & 7) ^ (tig >> 1)) << 4);
+            } else {
+                abase[f] = (r >> 4) * 2048 + tig * 128 + (r & 1) * 8;
+                apre[f] = (uint32_t)(((((r & 15) >> 1) ^ tig)) << 4);
+            }
+        }
+        {
+            const int r = wn0 + frag_row<BKm>(f, gid);
+            if (BKm) {
+                bbase[f] = r * 128 + (tig & 1) * 8;
+                bpre[f] = (uint32_t)(((r & 7) ^ (tig >> 1)) << 4);
+            } else {
+                bbase[f] = (r >> 4) * 2048 + tig * 128 + (r & 1) * 8;
+                bpre[f] = (uint32_t)(((((r & 15) >> 1) ^ tig)) << 4);
+            }
+        }
+    }
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i][0] = acc[j][i][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int slot = kt % ST2;
+        mbar_wait(&full[slot], (kt / ST2) & 1);
+        const unsigned char *sa = smem + slot * STAGE2, *sb = sa + TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < BK / 4; ++ks) {
+            double fa[4], fb[4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const uint32_t oa = AK ? abase[f] + (apre[f] ^ (uint32_t)(ks << 5))
+                                       : abase[f] + ks * 512 + (apre[f] ^ (uint32_t)((ks & 1) << 6));
+                fa[f] = *reinterpret_cast<const double *>(sa + oa);
+                const uint32_t ob = BKm ? bbase[f] + (bpre[f] ^ (uint32_t)(ks << 5))
+                                        : bbase[f] + ks * 512 + (bpre[f] ^ (uint32_t)((ks & 1) << 6));
+                fb[f] = *reinterpret_cast<const double *>(sb + ob);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dmma884(acc[j][i][0], acc[j][i][1], fb[j], fa[i]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+        if (tid == 0 && kt + ST2 - 1 < KT) load_stage(kt + ST2 - 1);   // slot of iteration kt - 1
+        __syncwarp();
+    }
+
+    // epilogue through the (now idle) ring, as in dgemm_tma_kernel
+    constexpr int LDT = BM + 2;
+    double *tile = reinterpret_cast<double *>(smem);   // [BN2][LDT]
+    __syncthreads();
+    const double alpha = p.alpha, beta = p.partial ? 0.0 : p.beta;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int nl = wn0 + frag_row<BKm>(j, gid);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) tile[nl * LDT + wm0 + frag_row<AK>(i, 2 * tig + e)] = alpha * acc[j][i][e];
+    }
+    __syncthreads();
+    double *__restrict__ C = p.C + (p.partial ? (int64_t)blockIdx.z * p.zstride : 0);
+    constexpr int PER = 8;
+#pragma unroll 1
+    for (int round = 0; round < (BM / 2) * BN2 / (NC2 * 32 * PER); ++round) {
+        double2 old[PER];
+        bool ok[PER];
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            const int idx = tid + (round * PER + it) * NC2 * 32;
+            const int nl = idx / (BM / 2), ml = (idx % (BM / 2)) * 2;
+            const int m = m0 + ml, n = n0 + nl;
+            ok[it] = m < p.M && n < p.N && (!p.lower_only || m + 1 >= n);
+            old[it] = make_double2(0.0, 0.0);
+            if (ok[it] && beta != 0.0) {
+                if (m + 1 < p.M) old[it] = *reinterpret_cast<const double2 *>(C + m + (int64_t)n * p.ldc);
+                else old[it].x = C[m + (int64_t)n * p.ldc];
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+            if (!ok[it]) continue;
+            const int idx = tid + (round * PER + it) * NC2 * 32;
+            const int nl = idx / (BM / 2), ml = (idx % (BM / 2)) * 2;
+            const int m = m0 + ml, n = n0 + nl;
+            const double2 t = *reinterpret_cast<const double2 *>(tile + nl * LDT + ml);
+            double2 o = make_double2(t.x + beta * old[it].x, t.y + beta * old[it].y);
+            double *c = C + m + (int64_t)n * p.ldc;
+            const bool w0 = !p.lower_only || m >= n, w1 = m + 1 < p.M;
+            if (w0 && w1) *reinterpret_cast<double2 *>(c) = o;
+            else {
+                if (w0) c[0] = o.x;
+                if (w1) c[1] = o.y;
+            }
+        }
+    }
+}
+
+
 typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -349,6 +535,17 @@ void launch(lfb_handle &h, const CUtensorMap &ma, const CUtensorMap &mb, const T
     LFB_LAUNCH_CHECK(h);
 }
 
+template <int AK, int BKm>
+void launch2(lfb_handle &h, const CUtensorMap &ma, const CUtensorMap &mb, const TmaP &p, dim3 grid) {
+    constexpr size_t smem = ST2 * STAGE2 + 2 * ST2 * sizeof(uint64_t) + 1024;
+    static DeviceOnce cfg;
+    cfg.run(h.device, [&] {
+        LFB_CUDA(cudaFuncSetAttribute(dgemm_tma2_kernel<AK, BKm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    });
+    dgemm_tma2_kernel<AK, BKm><<<grid, NC2 * 32, smem, h.stream>>>(ma, mb, p);
+    LFB_LAUNCH_CHECK(h);
+}
+
 }  // namespace
 
 bool dgemm_tma_try(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int64_t K, double alpha, const double *A,
@@ -400,6 +597,38 @@ bool dgemm_tma_try(lfb_handle &h, int ta, int tb, int64_t M, int64_t N, int64_t 
             dim3 g((unsigned)cdiv(M, 256), (unsigned)(N < 65535 ? N : 65535));
             scale_kernel_d<double><<<g, 256, 0, h.stream>>>(C, M, N, ldc, beta, lower_only);
             LFB_LAUNCH_CHECK(h);
+        }
+    }
+    // short main loops, full waves, no split-K, C addressable by 16-byte pairs: 128 x 64 tiles, two CTAs per SM
+    const bool tma2 = h.opt.gemm_tma2 && p.vecC && !p.atomic &&
+                      ((splits == 1 && K <= h.opt.gemm_tma2_maxk && tm * tn >= h.sm_count) || (p.partial && (h.opt.gemm_tma2 >= 2 || tm == 1)));
+    if (tma2) {
+        alignas(64) CUtensorMap mb2;
+        if (BKm ? make_map(&mb2, B, K, N, ldb, BK, BN2) : true) {
+            const CUtensorMap &mbu = BKm ? mb2 : mb;
+            const int64_t tn2 = cdiv(N, BN2);
+            dim3 grid2((unsigned)tm, (unsigned)tn2, (unsigned)splits);
+            p.tri = 0;
+            if (lower_only && tm > 1 && tm < 20000) {
+                // live tiles row by row: rows i < tn2 / 2 hold 2 (i + 1), the rest all tn2 (kernel: the inverse map)
+                const int64_t fr = std::min<int64_t>(tn2 / 2, tm);
+                const int64_t live = fr * (fr + 1) + (tm - fr) * tn2;
+                if (live < (1LL << 31)) {
+                    p.tri = 1;
+                    p.ptn = (int)tn2;
+                    grid2 = dim3((unsigned)live, 1, (unsigned)splits);
+                }
+            }
+            if (AK && BKm) launch2<1, 1>(h, ma, mbu, p, grid2);
+            else if (AK && !BKm) launch2<1, 0>(h, ma, mbu, p, grid2);
+            else if (!AK && BKm) launch2<0, 1>(h, ma, mbu, p, grid2);
+            else launch2<0, 0>(h, ma, mbu, p, grid2);
+            if (p.partial) {
+                dim3 g((unsigned)cdiv(M, 128), (unsigned)(N < 65535 ? N : 65535));
+                splitk_reduce_kernel<<<g, 128, 0, h.stream>>>(work->get(), ldw, p.zstride, splits, C, M, N, ldc, beta, lower_only);
+                LFB_LAUNCH_CHECK(h);
+            }
+            return true;
         }
     }
     dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)splits);

@@ -15,6 +15,10 @@
 // I - V T V^T with T = (striu(V^T V) + I/2)^-1 (tau = 2 for unit-norm v), and GEMM trailing updates.
 #include <cooperative_groups.h>
 
+#include <array>
+#include <map>
+#include <vector>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -649,7 +653,39 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
 
     // Factors panel [k0, k0+nb) on the handle's current stream; stages V (rows from k0) and, if the
     // panel has a trailing matrix, builds its compact-WY T.
+    // The panel as a guarded Cholesky-QR + Householder reconstruction (cholqr.cu, tsqr_hr.cu): Gram GEMM, nb x nb Cholesky,
+    // Q_top = A_top R^-1, LU of (Q_top - S) -> the reflectors of the top block, beta and U', rows below = A_2 (R^-1 U'^-1) -- the
+    // SAME reflectors, pivots and R a Householder sweep over the panel produces (the reconstruction is exact, not "up to signs"),
+    // in ~30 short launches that are GEMMs where the height matters, against 0.5 ms (128 rows) - 2.9 ms (16384 rows) for the
+    // cluster kernels: with those the QR of 16384^2 is bound by the panel chain from panel 60 of 128 on (qr_trace,
+    // profiles/r2_qr_panel.md).  Taken only when the guard accepts the panel (cond bound <= tsqr_cholqr_cond, Cholesky succeeded);
+    // rank-deficient, graded or ill-conditioned panels go to the cluster kernels, A untouched by the attempt.
+    auto panel_cholqr = [&](int64_t k0, int nb, T *V) -> bool {
+        const int64_t prow = m - k0;
+        T *P = A + k0 + k0 * ld;
+        const int64_t ldu = round_up(nb, 2);
+        DevBuf<T> R(h, (size_t)ldu * nb), Rinv(h, (size_t)ldu * nb), U(h, (size_t)ldu * nb), Qt(h, (size_t)ldu * nb);
+        if (!cholqr_factor<T>(h, P, prow, nb, ld, R.get(), ldu, Rinv.get(), ldu)) return false;
+        gemm<T>(h, 0, 0, nb, nb, nb, T(1), P, ld, Rinv.get(), ldu, T(0), Qt.get(), ldu);                 // Q_top
+        hh_reconstruct_top<T>(h, Qt.get(), nb, ldu, R.get(), ldu, U.get(), ldu, beta + k0, /*internal=*/1);
+        trsm_right_upper<T>(h, nb, nb, U.get(), ldu, Rinv.get(), ldu);                                   // Rinv <- R^-1 U'^-1
+        if (prow > nb) {
+            gemm<T>(h, 0, 0, prow - nb, nb, nb, T(1), P + nb, ld, Rinv.get(), ldu, T(0), V + nb, ldv);   // staged V, rows below the top block
+            copy2d<T>(h, V + nb, ldv, P + nb, ld, prow - nb, nb);
+        }
+        copy2d<T>(h, Qt.get(), ldu, P, ld, nb, nb);
+        copy_v<T>(h, A, ld, k0, k0, nb, nb, (const T *)nullptr, V, ldv);                                 // top of the staged V: zero above the diagonal
+        return true;
+    };
+
     auto factor_panel = [&](int64_t k0, int nb, T *V, T *Tm, T *Vt) {
+        if (sizeof(T) == 8 && h.opt.qr_panel_cholqr && nb >= 64 && (m - k0) >= 2 * (int64_t)nb && panel_cholqr(k0, nb, V)) {
+            if (n - (k0 + nb) > 0) {
+                build_t<T>(h, V, ldv, m - k0, nb, G, Tm, NB);
+                if (Vt) transpose<T>(h, V, m - k0, nb, ldv, Vt, NB);
+            }
+            return;
+        }
         bool v_staged = true;   // the cluster kernels stage V as they go
         for (int s0 = 0; s0 < nb;) {
             const int64_t c0 = k0 + s0;
@@ -693,9 +729,27 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
 
     cudaStream_t sm = h.stream, sp = h.aux_stream;
     const bool la = h.opt.lookahead && sp != nullptr && !h.prof_on && n >= 4 * NB;
+    // Debug option qr_trace (like chol_trace): event time stamps of the look-ahead pipeline, one line per panel on stderr.
+    struct Mark { cudaEvent_t e; int panel; int what; };
+    std::vector<Mark> marks;
+    const bool trace = h.opt.qr_trace != 0 && la;
+    cudaEvent_t t_base = nullptr;
+    auto mark = [&](cudaStream_t st, int panel, int what) {
+        if (!trace) return;
+        cudaEvent_t e;
+        LFB_CUDA(cudaEventCreate(&e));
+        LFB_CUDA(cudaEventRecord(e, st));
+        marks.push_back({e, panel, what});
+    };
+    if (trace) {
+        LFB_CUDA(cudaEventCreate(&t_base));
+        LFB_CUDA(cudaEventRecord(t_base, h.stream));
+    }
     factor_panel(0, (int)std::min<int64_t>(NB, n), Vbuf[0], Tbuf[0], Vtbuf[0]);
     int cur = 0;
+    int pi = -1;
     for (int64_t k0 = 0; k0 < n; k0 += NB, cur ^= 1) {
+        ++pi;
         const int nb = (int)std::min<int64_t>(NB, n - k0);
         const int64_t trail = n - (k0 + nb);
         if (trail <= 0) break;
@@ -705,25 +759,48 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
         if (la) {
             // trailing update of the NEXT panel's columns first, then factor that panel on the side
             // stream while the rest of the trailing matrix is updated here
+            mark(sm, pi, 0);
             apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C, ld, nbn, W1, W2, Vtbuf[cur], NB);
+            mark(sm, pi, 1);
             LFB_CUDA(cudaEventRecord(h.ev[2], sm));
             LFB_CUDA(cudaStreamWaitEvent(sp, h.ev[2], 0));
+            // the rest of the update is queued BEFORE the panel: the Cholesky-QR panel ends its guard with a host
+            // synchronisation of the side stream, and the main stream must already hold its work by then
+            if (trail > nbn)
+                apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C + (int64_t)nbn * ld, ld, trail - nbn, W1, W2, Vtbuf[cur], NB);
+            mark(sm, pi, 4);
             h.stream = sp;
             try {
+                mark(sp, pi, 2);
                 factor_panel(k0 + nb, nbn, Vbuf[cur ^ 1], Tbuf[cur ^ 1], Vtbuf[cur ^ 1]);
+                mark(sp, pi, 3);
             } catch (...) {
                 h.stream = sm;
                 throw;
             }
             LFB_CUDA(cudaEventRecord(h.ev[3], sp));
             h.stream = sm;
-            if (trail > nbn)
-                apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C + (int64_t)nbn * ld, ld, trail - nbn, W1, W2, Vtbuf[cur], NB);
             LFB_CUDA(cudaStreamWaitEvent(sm, h.ev[3], 0));
         } else {
             apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C, ld, trail, W1, W2, Vtbuf[cur], NB);
             factor_panel(k0 + nb, nbn, Vbuf[cur ^ 1], Tbuf[cur ^ 1], Vtbuf[cur ^ 1]);
         }
+    }
+    if (trace) {
+        LFB_CUDA(cudaStreamSynchronize(sm));
+        LFB_CUDA(cudaStreamSynchronize(sp));
+        std::map<int, std::array<float, 5>> rowsT;
+        for (auto &mk : marks) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, t_base, mk.e);
+            rowsT[mk.panel][mk.what] = t;
+            cudaEventDestroy(mk.e);
+        }
+        cudaEventDestroy(t_base);
+        fprintf(stderr, "qr_trace m=%lld n=%lld nb=%d (ms from start): panel | next-panel columns start end | side panel start end | rest of update end\n",
+                (long long)m, (long long)n, NB);
+        for (auto &kv : rowsT)
+            fprintf(stderr, "  %3d | %8.3f %8.3f | %8.3f %8.3f | %8.3f\n", kv.first, kv.second[0], kv.second[1], kv.second[2], kv.second[3], kv.second[4]);
     }
 }
 

@@ -134,11 +134,13 @@ __global__ void __launch_bounds__(1024) hr_lu_blocked_kernel(T *Q, int64_t ld, i
 }
 
 // c_k and diag_ref[k] from the LU pivots, the signs and diag(R).
+// internal = 1: the blocked QR's own convention instead (householder.cu: unit-norm reflectors without the running sign,
+// beta_k = s_k R_kk, R rows as the reflections leave them = s_k R[k, :]); the driver's final sign pass turns that into the above.
 template <typename T>
-__global__ void hr_scale_kernel(const T *Q, int64_t ld, int n, const T *R, int64_t ldr, const T *s, T *c, T *diag) {
+__global__ void hr_scale_kernel(const T *Q, int64_t ld, int n, const T *R, int64_t ldr, const T *s, T *c, T *diag, int internal) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const T sp = k > 0 ? s[k - 1] : T(1);
+    const T sp = (k > 0 && !internal) ? s[k - 1] : T(1);
     T u = Q[k + (int64_t)k * ld];
     u = u < T(0) ? -u : u;
     c[k] = -sp * s[k] * sqrt(u / T(2));
@@ -151,14 +153,15 @@ __global__ void hr_scale_kernel(const T *Q, int64_t ld, int n, const T *R, int64
 // U' = diag(1/c) U out of the upper triangle, then the top block's final contents: c_k on the diagonal (head of
 // v_ref,k), c_k y_ik below, R[k, j>k] above.  Every thread reads only its own entry of Q.
 template <typename T>
-__global__ void hr_finish_kernel(T *Q, int64_t ld, int n, const T *R, int64_t ldr, const T *c, T *U, int64_t ldu) {
+__global__ void hr_finish_kernel(T *Q, int64_t ld, int n, const T *R, int64_t ldr, const T *c, T *U, int64_t ldu, const T *s_int) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     for (int j = blockIdx.y; j < n; j += gridDim.y) {
         const T q = Q[i + (int64_t)j * ld];
         if (i < j) {
             U[i + (int64_t)j * ldu] = q / c[i];
-            Q[i + (int64_t)j * ld] = R[i + (int64_t)j * ldr];
+            const T r = R[i + (int64_t)j * ldr];
+            Q[i + (int64_t)j * ld] = (s_int && s_int[i] < T(0)) ? -r : r;
         } else if (i == j) {
             U[i + (int64_t)j * ldu] = q / c[i];
             Q[i + (int64_t)j * ld] = c[i];
@@ -175,7 +178,7 @@ __global__ void hr_finish_kernel(T *Q, int64_t ld, int n, const T *R, int64_t ld
 // compact factor; R (n x n upper, diag >= 0) its triangular factor; U (n x n) receives U' for the rows below
 // (Y2' = Q2 U'^-1); diag[n] the signed pivots.
 template <typename T>
-void hh_reconstruct_top(lfb_handle &h, T *Qtop, int64_t n, int64_t ld, const T *R, int64_t ldr, T *U, int64_t ldu, T *diag) {
+void hh_reconstruct_top(lfb_handle &h, T *Qtop, int64_t n, int64_t ld, const T *R, int64_t ldr, T *U, int64_t ldu, T *diag, int internal) {
     if (n <= 0) return;
     DevBuf<T> s(h, n), c(h, n);
     const size_t smem_lu = sizeof(T) * ((size_t)n * (HR_PB + 1) + (size_t)HR_PB * (n + 1));
@@ -189,10 +192,10 @@ void hh_reconstruct_top(lfb_handle &h, T *Qtop, int64_t n, int64_t ld, const T *
         hr_lu_kernel<T><<<1, 1024, 0, h.stream>>>(Qtop, ld, (int)n, s);
     }
     LFB_LAUNCH_CHECK(h);
-    hr_scale_kernel<T><<<(unsigned)cdiv(n, 256), 256, 0, h.stream>>>(Qtop, ld, (int)n, R, ldr, s, c, diag);
+    hr_scale_kernel<T><<<(unsigned)cdiv(n, 256), 256, 0, h.stream>>>(Qtop, ld, (int)n, R, ldr, s, c, diag, internal);
     LFB_LAUNCH_CHECK(h);
     dim3 grid((unsigned)cdiv(n, 256), ycap(n));
-    hr_finish_kernel<T><<<grid, 256, 0, h.stream>>>(Qtop, ld, (int)n, R, ldr, c, U, ldu);
+    hr_finish_kernel<T><<<grid, 256, 0, h.stream>>>(Qtop, ld, (int)n, R, ldr, c, U, ldu, internal ? s.get() : (const T *)nullptr);
     LFB_LAUNCH_CHECK(h);
 }
 
@@ -229,7 +232,7 @@ void qr_tsqr(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *dia
 }
 
 #define INST(T)                                                                                                        \
-    template void hh_reconstruct_top<T>(lfb_handle &, T *, int64_t, int64_t, const T *, int64_t, T *, int64_t, T *);   \
+    template void hh_reconstruct_top<T>(lfb_handle &, T *, int64_t, int64_t, const T *, int64_t, T *, int64_t, T *, int); \
     template void qr_tsqr<T>(lfb_handle &, T *, int64_t, int64_t, int64_t, T *);
 INST(float)
 INST(double)
