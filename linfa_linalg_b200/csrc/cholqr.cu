@@ -97,12 +97,20 @@ bool cholqr_factor(lfb_handle &h, const T *A, int64_t rows, int64_t n, int64_t l
     DevBuf<int64_t> info(h, 1);
     DevBuf<double> guard(h, 4);
     gemm<T>(h, 1, 0, n, n, rows, T(1), A, ld, A, ld, T(0), G.get(), ldg, /*lower_only=*/1);      // G = A^T A
+    double hg[3] = {0, 0, 0};
+    if (n == 128 && h.opt.cholqr_fused && Rinv) {
+        // one single-CTA launch for the n x n stage (panel_hr.cu): Cholesky, inverse, guard numbers, R and R^-1 -- the scratch
+        // outputs are written before the verdict is known, the caller's matrix is not touched
+        cholqr128<T>(h, G.get(), ldg, R, ldr, Rinv, ldri, guard.get());
+        LFB_CUDA(cudaMemcpyAsync(hg, guard.get(), sizeof hg, cudaMemcpyDeviceToHost, h.stream));
+        LFB_CUDA(cudaStreamSynchronize(h.stream));
+        return hg[2] == 1.0 && hg[1] > 0.0 && std::isfinite(hg[0]) && hg[0] <= (double)h.opt.tsqr_cholqr_cond;
+    }
     cholesky_lower<T>(h, G.get(), n, ldg, /*clean=*/0, info.get());                            // G = L L^T (lower)
     fill<T>(h, X.get(), n, n, ldg, T(0), T(1));
     trsm_left<T>(h, /*lower=*/1, /*trans=*/0, n, n, G.get(), ldg, (const T *)nullptr, X.get(), ldg);   // X = L^-1
     cholqr_guard_kernel<T><<<1, 1024, 0, h.stream>>>(G.get(), X.get(), ldg, (int)n, guard.get());
     LFB_LAUNCH_CHECK(h);
-    double hg[3] = {0, 0, 0};
     int64_t hinfo = 0;
     LFB_CUDA(cudaMemcpyAsync(hg, guard.get(), sizeof hg, cudaMemcpyDeviceToHost, h.stream));
     LFB_CUDA(cudaMemcpyAsync(&hinfo, info.get(), sizeof hinfo, cudaMemcpyDeviceToHost, h.stream));

@@ -46,6 +46,7 @@ struct Options {
     int64_t qr_nb_f32 = 256; // same for f32 when the trailing updates run on the tcgen05 kernel (n >= 2048)
     int64_t qr_vt = 0;       // f64 QR: rank-nb update through a transposed copy of V (TN form); measured: no gain (263.8 vs 263.5 ms), off
     int64_t qr_panel_cholqr = 1; // f64 blocked QR: panel = guarded Cholesky-QR + Householder reconstruction (tsqr_hr.cu) when its condition bound passes; else the cluster panel kernels
+    int64_t cholqr_fused = 1;    // 128-column Cholesky-QR stages as single-CTA kernels (panel_hr.cu): Cholesky + inverse + guard, and reconstruction + M + T
     int64_t qr_trace = 0;    // debug: event time stamps of every stage of the look-ahead pipeline on stderr
     int64_t qr_sub = 32;     // inner BLAS-2 sub-panel width (<= 32)
     int64_t chol_base = 64;  // recursion base of Cholesky / TRSM (<= 64)
@@ -342,6 +343,9 @@ template <typename T> void hh_reconstruct_top(lfb_handle &h, T *Qtop, int64_t n,
 template <typename T> void qr_tsqr(lfb_handle &h, T *A, int64_t rows, int64_t cols, int64_t ld, T *diag);
 // Cholesky-QR leaf (cholqr.cu): R (n x n upper, diag >= 0) and optionally R^-1 of a tall block WITHOUT touching A; returns
 // false (nothing written) when the Gram matrix is not safely positive definite -- the caller then takes the Householder route.
+template <typename T> void cholqr128(lfb_handle &h, const T *G, int64_t ldg, T *R, int64_t ldr, T *Rinv, int64_t ldri, double *guard);
+template <typename T> void hr_panel128(lfb_handle &h, T *Atop, int64_t ld, const T *R, int64_t ldr, const T *Rinv, int64_t ldri, T *beta, T *M, int64_t ldm,
+                                       T *Tm, int64_t ldt, T *Vtop, int64_t ldv);
 template <typename T> bool cholqr_factor(lfb_handle &h, const T *A, int64_t rows, int64_t n, int64_t ld, T *R, int64_t ldr, T *Rinv, int64_t ldri);
 template <typename T> void triangular_zero(lfb_handle &h, T *A, int64_t n, int64_t ld, int keep_lower);
 double microbench_fp64(lfb_handle &h, int kind);

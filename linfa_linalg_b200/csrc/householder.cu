@@ -660,12 +660,22 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
     // cluster kernels: with those the QR of 16384^2 is bound by the panel chain from panel 60 of 128 on (qr_trace,
     // profiles/r2_qr_panel.md).  Taken only when the guard accepts the panel (cond bound <= tsqr_cholqr_cond, Cholesky succeeded);
     // rank-deficient, graded or ill-conditioned panels go to the cluster kernels, A untouched by the attempt.
-    auto panel_cholqr = [&](int64_t k0, int nb, T *V) -> bool {
+    auto panel_cholqr = [&](int64_t k0, int nb, T *V, T *Tm, bool *t_built) -> bool {
         const int64_t prow = m - k0;
         T *P = A + k0 + k0 * ld;
         const int64_t ldu = round_up(nb, 2);
         DevBuf<T> R(h, (size_t)ldu * nb), Rinv(h, (size_t)ldu * nb), U(h, (size_t)ldu * nb), Qt(h, (size_t)ldu * nb);
         if (!cholqr_factor<T>(h, P, prow, nb, ld, R.get(), ldu, Rinv.get(), ldu)) return false;
+        if (nb == 128 && h.opt.cholqr_fused) {
+            // U receives M = R^-1 U^-1 C; the top block, beta, the staged top of V and T come out of the same launch
+            hr_panel128<T>(h, P, ld, R.get(), ldu, Rinv.get(), ldu, beta + k0, U.get(), ldu, Tm, NB, V, ldv);
+            if (prow > nb) {
+                gemm<T>(h, 0, 0, prow - nb, nb, nb, T(1), P + nb, ld, U.get(), ldu, T(0), V + nb, ldv);
+                copy2d<T>(h, V + nb, ldv, P + nb, ld, prow - nb, nb);
+            }
+            *t_built = true;
+            return true;
+        }
         gemm<T>(h, 0, 0, nb, nb, nb, T(1), P, ld, Rinv.get(), ldu, T(0), Qt.get(), ldu);                 // Q_top
         hh_reconstruct_top<T>(h, Qt.get(), nb, ldu, R.get(), ldu, U.get(), ldu, beta + k0, /*internal=*/1);
         trsm_right_upper<T>(h, nb, nb, U.get(), ldu, Rinv.get(), ldu);                                   // Rinv <- R^-1 U'^-1
@@ -679,9 +689,10 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
     };
 
     auto factor_panel = [&](int64_t k0, int nb, T *V, T *Tm, T *Vt) {
-        if (sizeof(T) == 8 && h.opt.qr_panel_cholqr && nb >= 64 && (m - k0) >= 2 * (int64_t)nb && panel_cholqr(k0, nb, V)) {
+        bool t_built = false;
+        if (sizeof(T) == 8 && h.opt.qr_panel_cholqr && nb >= 64 && (m - k0) >= 2 * (int64_t)nb && panel_cholqr(k0, nb, V, Tm, &t_built)) {
             if (n - (k0 + nb) > 0) {
-                build_t<T>(h, V, ldv, m - k0, nb, G, Tm, NB);
+                if (!t_built) build_t<T>(h, V, ldv, m - k0, nb, G, Tm, NB);
                 if (Vt) transpose<T>(h, V, m - k0, nb, ldv, Vt, NB);
             }
             return;

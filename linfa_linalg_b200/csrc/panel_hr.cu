@@ -1,0 +1,470 @@
+// The 128-column panel of the blocked QR as two single-CTA kernels (qr.rs:29-45 through householder.cu: qr_factor_std).
+//
+// qr_trace on QR 16384^2 (profiles/r2_qr_panel.md): from panel 60 of 128 on, the step is bound by the panel chain on the
+// look-ahead stream, and that chain is ~25 dependent launches of ~24 us each (0.6 ms alone, 0.5 - 2.3 ms next to the trailing
+// GEMM, which every launch has to squeeze past).  The two n x n stages between the Gram GEMM and the tall GEMM are latency,
+// not work (128^3 flops each), so each becomes ONE launch with the block resident in shared memory:
+//
+//   cholqr128_kernel     G = A^T A  ->  R = chol(G)^T, R^-1, and the guard numbers of cholqr.cu (condition bound, smallest
+//                        pivot, finiteness);
+//   hr_panel128_kernel   Q_top = A_top R^-1, LU of (Q_top - S) (tsqr_hr.cu: the Householder reconstruction), then everything the
+//                        driver needs from it: the top block of the factor in the driver's internal convention, beta, the
+//                        matrix M = R^-1 U^-1 C that turns the rows below into reflector rows (V_2 = A_2 M, one tall GEMM), and
+//                        the compact-WY factor  T = -C^-1 U S Y_1^-T C^-1  (Ballard et al.'s T for Y, rescaled to the unit-norm
+//                        reflectors V = Y C) -- which replaces the second Gram GEMM + triangular inversion of build_t.
+//
+// Every O(n^3) stage is a "register sweep": thread (tr, tc) of the 32 x 32 thread grid owns the 4 x 4 elements (tr + 32 x, tc + 32 y)
+// of the working matrix in registers (cyclic, so the load stays balanced as a sweep advances); a step reads one published pivot
+// row / column from shared memory (8 loads per 16 FMAs, against one shared access per FMA for the in-place versions first
+// written: an SM issues one shared-memory instruction per cycle, which made those 3-4 x slower), updates its 16 elements, and the
+// owners of the next pivot row / column publish it -- one barrier per step.  The two dense products (Q_top = A_top R^-1 and T)
+// are 4 x 4 register-tiled.
+//
+// The formulas were checked against a plain Householder sweep in NumPy before this file was written (V, beta, R, T all to 1e-14
+// at 700 x 128); tests/test_gpu_parity*.py hold the result to the oracle.
+#include "common.cuh"
+
+namespace lfb {
+namespace {
+
+constexpr int PN = 128, PLD = PN + 1;
+__device__ __forceinline__ int pk(int i, int j) { return j * (j + 1) / 2 + i; }   // packed upper triangle, i <= j
+
+// a[x][s] / a[s][y] with a run-time s as selects: a dynamic index would send the register tile to local memory
+template <typename T> __device__ __forceinline__ T col_of(const T (&a)[4][4], int x, int s) {
+    return s == 0 ? a[x][0] : s == 1 ? a[x][1] : s == 2 ? a[x][2] : a[x][3];
+}
+template <typename T> __device__ __forceinline__ T row_of(const T (&a)[4][4], int s, int y) {
+    return s == 0 ? a[0][y] : s == 1 ? a[1][y] : s == 2 ? a[2][y] : a[3][y];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G, int64_t ldg, T *__restrict__ R, int64_t ldr,
+                                                         T *__restrict__ Rinv, int64_t ldri, double *__restrict__ guard) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *S = reinterpret_cast<T *>(smem_raw);      // [PN][PLD]: G, then lower = L and strict upper = (L^-1)^T
+    T *rk = S + PN * PLD;                        // L_kk
+    T *xd = rk + PN;                             // 1 / L_kk
+    T *buf = xd + PN;                            // [2][PN] published pivot column / row
+    double *red = reinterpret_cast<double *>(buf + 2 * PN);   // 4 x PN norms
+    __shared__ int s_fail;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tr = lane, tc = warp;
+    if (tid == 0) s_fail = 0;
+    for (int j = warp; j < PN; j += 32)
+        for (int i = j + lane; i < PN; i += 32) S[i * PLD + j] = G[i + (int64_t)j * ldg];
+    __syncthreads();
+    T a[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int i = tr + 32 * x, j = tc + 32 * y;
+            a[x][y] = i >= j ? S[i * PLD + j] : S[j * PLD + i];
+        }
+    if (tc == 0) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) buf[tr + 32 * x] = a[x][0];
+    }
+    __syncthreads();
+    // Cholesky, right-looking.  Column k keeps the unscaled Schur-complement entries a_ik (L_ik = a_ik / sqrt(a_kk)); the full
+    // square is updated (the matrix stays symmetric), so one published column serves rows and columns.
+
+    for (int k = 0; k < PN; ++k) {
+        const T *cb = buf + (k & 1) * PN;
+        T *cn = buf + ((k & 1) ^ 1) * PN;
+        const T d = cb[k];
+        if (!(d > T(0)) || !isfinite(d)) {       // uniform: every thread reads the same d
+            if (tid == 0) s_fail = 1;
+            break;
+        }
+        if (tid == 0) rk[k] = sqrt(d);
+        const T dinv = T(1) / d;
+        // 32-row / 32-column blocks that lie wholly at or before the pivot are dead for every thread: skipped with block-uniform
+        // tests (the FP64 pipe issues half a warp per clock, so a full 128 x 128 rank-1 update is 512 cycles of a step)
+        const int b0 = (k + 1) >> 5;             // first block with an index > k
+        T l[4], u[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) l[x] = (x >= b0 && tr + 32 * x > k) ? -cb[tr + 32 * x] * dinv : T(0);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) u[y] = (y >= b0 && tc + 32 * y > k) ? cb[tc + 32 * y] : T(0);
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            if (x >= b0) {
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+                    if (y >= b0) a[x][y] = fma(l[x], u[y], a[x][y]);
+            }
+        if (k + 1 < PN && tc == ((k + 1) & 31)) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) cn[tr + 32 * x] = col_of(a, x, (k + 1) >> 5);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (s_fail) {
+        if (tid == 0) { guard[0] = 1e300; guard[1] = 0.0; guard[2] = 0.0; }
+        return;
+    }
+    if (tid < PN) xd[tid] = T(1) / rk[tid];
+    __syncthreads();
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int i = tr + 32 * x, j = tc + 32 * y;
+            if (i > j) S[i * PLD + j] = a[x][y] * xd[j];
+            else if (i == j) S[i * PLD + j] = rk[j];
+        }
+    // X = L^-1 by a forward sweep on W = I: row k of X is W[k, :] / L_kk, then W[i, :] -= L_ik X[k, :] for i > k
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) a[x][y] = (tr + 32 * x == tc + 32 * y) ? T(1) : T(0);
+    if (tr == 0) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            a[0][y] *= xd[0];
+            buf[tc + 32 * y] = a[0][y];
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < PN; ++k) {
+        const T *rb = buf + (k & 1) * PN;
+        T *rn = buf + ((k & 1) ^ 1) * PN;
+        const int b0 = (k + 1) >> 5, b1 = k >> 5;   // live: row blocks >= b0 (i > k), column blocks <= b1 (X[k, j] = 0 for j > k)
+        T l[4], u[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) l[x] = (x >= b0 && tr + 32 * x > k) ? -S[(tr + 32 * x) * PLD + k] : T(0);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) u[y] = (y <= b1) ? rb[tc + 32 * y] : T(0);
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            if (x >= b0) {
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+                    if (y <= b1) a[x][y] = fma(l[x], u[y], a[x][y]);
+            }
+        if (k + 1 < PN && tr == ((k + 1) & 31)) {
+            const T sc = xd[k + 1];
+            const int xs = (k + 1) >> 5;
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const T v = row_of(a, xs, y) * sc;
+                rn[tc + 32 * y] = v;
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+                    if (x == xs) a[x][y] = v;
+            }
+        }
+        __syncthreads();
+    }
+    // X (lower) goes to the strict upper part of S transposed, for the guard sums and a coalesced write
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int i = tr + 32 * x, j = tc + 32 * y;
+            if (i > j) S[j * PLD + i] = a[x][y];
+        }
+    __syncthreads();
+    // guard: sqrt(||L||_1 ||L||_inf ||X||_1 ||X||_inf) >= cond_2(L)
+    if (tid < PN) {
+        const int t = tid;
+        double cl = 0.0, rl = 0.0, cx = fabs((double)xd[t]), rx = fabs((double)xd[t]);
+        for (int i = t; i < PN; ++i) cl += fabs((double)S[i * PLD + t]);
+        for (int j = 0; j <= t; ++j) rl += fabs((double)S[t * PLD + j]);
+        for (int i = t + 1; i < PN; ++i) cx += fabs((double)S[t * PLD + i]);      // X_it
+        for (int j = 0; j < t; ++j) rx += fabs((double)S[j * PLD + t]);           // X_tj
+        red[t] = cl; red[PN + t] = rl; red[2 * PN + t] = cx; red[3 * PN + t] = rx;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double m[4] = {0.0, 0.0, 0.0, 0.0}, dm = 1e300;
+        for (int t = lane; t < PN; t += 32) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m[q] = fmax(m[q], red[q * PN + t]);
+            dm = fmin(dm, (double)rk[t]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m[q] = fmax(m[q], __shfl_xor_sync(0xffffffffu, m[q], o));
+            dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+        }
+        if (lane == 0) {
+            const double b = sqrt(m[0] * m[1] * m[2] * m[3]);
+            guard[0] = b;
+            guard[1] = dm;
+            guard[2] = isfinite(b) ? 1.0 : 0.0;
+        }
+    }
+    for (int j = warp; j < PN; j += 32)
+        for (int i = lane; i < PN; i += 32) {
+            R[i + (int64_t)j * ldr] = i <= j ? S[j * PLD + i] : T(0);                            // L_ji
+            Rinv[i + (int64_t)j * ldri] = i < j ? S[i * PLD + j] : (i == j ? xd[j] : T(0));     // X_ji
+        }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop, int64_t ld, const T *__restrict__ R, int64_t ldr,
+                                                          const T *__restrict__ Rinv, int64_t ldri, T *__restrict__ beta,
+                                                          T *__restrict__ M, int64_t ldm, T *__restrict__ Tm, int64_t ldt,
+                                                          T *__restrict__ Vtop, int64_t ldv) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *Q = reinterpret_cast<T *>(smem_raw);      // [PN][PLD]: A_top, then Y_1 (strictly lower) and U
+    T *P = Q + PN * PLD;                         // packed upper: R^-1, later Z
+    T *sv = P + PN * (PN + 1) / 2;               // s_k
+    T *pv = sv + PN;                             // U_kk
+    T *pinv = pv + PN;                           // 1 / U_kk
+    T *cv = pinv + PN;                           // c'_k
+    T *colb = cv + PN;                           // [2][PN]
+    T *rowb = colb + 2 * PN;                     // [2][PN]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tr = lane, tc = warp;
+    for (int j = warp; j < PN; j += 32)
+        for (int i = lane; i < PN; i += 32) {
+            Q[i * PLD + j] = Atop[i + (int64_t)j * ld];
+            if (i <= j) P[pk(i, j)] = Rinv[i + (int64_t)j * ldri];
+        }
+    __syncthreads();
+    // Q_top = A_top R^-1, 4 x 4 register tile per thread; the result stays in registers as the input of the LU
+    T a[4][4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) a[x][y] = T(0);
+    for (int k = 0; k <= tc + 96; ++k) {         // R^-1 is upper triangular: column j needs k <= j
+        T l[4], u[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) l[x] = Q[(tr + 32 * x) * PLD + k];
+#pragma unroll
+        for (int y = 0; y < 4; ++y) u[y] = (k <= tc + 32 * y) ? P[pk(k, tc + 32 * y)] : T(0);
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
+    }
+    if (tc == 0) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) colb[tr + 32 * x] = a[x][0];
+    }
+    if (tr == 0) {
+#pragma unroll
+        for (int y = 0; y < 4; ++y) rowb[tc + 32 * y] = a[0][y];
+    }
+    __syncthreads();
+    // LU of (Q_top - S) without pivoting (|pivot| = 1 + |q_kk| >= 1); multipliers stay unscaled (a_ik) until the write-back
+    for (int k = 0; k < PN; ++k) {
+        const T *cb = colb + (k & 1) * PN, *rb = rowb + (k & 1) * PN;
+        T *cn = colb + ((k & 1) ^ 1) * PN, *rn = rowb + ((k & 1) ^ 1) * PN;
+        const T q = cb[k];
+        const T sk = q < T(0) ? T(1) : T(-1);    // s_k = -sgn(q_kk), sgn(0) = +1 (tsqr_hr.cu)
+        const T p = q - sk;
+        const T pin = T(1) / p;
+        if (tid == 0) { sv[k] = sk; pv[k] = p; pinv[k] = pin; }
+        const int b0 = (k + 1) >> 5;             // blocks wholly at or before the pivot are dead (block-uniform skip)
+        T l[4], u[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) l[x] = (x >= b0 && tr + 32 * x > k) ? -cb[tr + 32 * x] * pin : T(0);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) u[y] = (y >= b0 && tc + 32 * y > k) ? rb[tc + 32 * y] : T(0);
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            if (x >= b0) {
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+                    if (y >= b0) a[x][y] = fma(l[x], u[y], a[x][y]);
+            }
+        if (k + 1 < PN) {
+            if (tc == ((k + 1) & 31)) {
+#pragma unroll
+                for (int x = 0; x < 4; ++x) cn[tr + 32 * x] = col_of(a, x, (k + 1) >> 5);
+            }
+            if (tr == ((k + 1) & 31)) {
+#pragma unroll
+                for (int y = 0; y < 4; ++y) rn[tc + 32 * y] = row_of(a, (k + 1) >> 5, y);
+            }
+        }
+        __syncthreads();
+    }
+    // back to shared memory: Y_1 strictly below the diagonal (scaled now), U on and above it
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int i = tr + 32 * x, j = tc + 32 * y;
+            Q[i * PLD + j] = i > j ? a[x][y] * pinv[j] : (i == j ? pv[j] : a[x][y]);
+        }
+    if (tid < PN) {
+        const int k = tid;
+        cv[k] = -sv[k] * sqrt(fabs(pv[k]) / T(2));
+        beta[k] = sv[k] * fabs(R[k + (int64_t)k * ldr]);
+    }
+    // M = R^-1 U^-1 by a column sweep on W = R^-1: column j of M is W[:, j] / U_jj, then W[:, j'] -= M[:, j] U[j, j'] for j' > j
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int i = tr + 32 * x, j = tc + 32 * y;
+            a[x][y] = i <= j ? P[pk(i, j)] : T(0);
+        }
+    __syncthreads();                             // Q, pinv, cv complete; every thread has its part of R^-1
+    if (tc == 0) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+            a[x][0] *= pinv[0];
+            colb[tr + 32 * x] = a[x][0];
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < PN; ++j) {
+        const T *cb = colb + (j & 1) * PN;
+        T *cn = colb + ((j & 1) ^ 1) * PN;
+        const int b0 = (j + 1) >> 5, b1 = j >> 5;   // live: column blocks >= b0 (j' > j), row blocks <= b1 (M[i, j] = 0 for i > j)
+        T l[4], u[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) l[x] = (x <= b1) ? -cb[tr + 32 * x] : T(0);
+#pragma unroll
+        for (int y = 0; y < 4; ++y) u[y] = (y >= b0 && tc + 32 * y > j) ? Q[j * PLD + tc + 32 * y] : T(0);
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            if (x <= b1) {
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+                    if (y >= b0) a[x][y] = fma(l[x], u[y], a[x][y]);
+            }
+        if (j + 1 < PN && tc == ((j + 1) & 31)) {
+            const T sc = pinv[j + 1];
+            const int ys = (j + 1) >> 5;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const T v = col_of(a, x, ys) * sc;
+                cn[tr + 32 * x] = v;
+#pragma unroll
+                for (int y = 0; y < 4; ++y)
+                    if (y == ys) a[x][y] = v;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int i = tr + 32 * x, j = tc + 32 * y;
+            M[i + (int64_t)j * ldm] = i <= j ? a[x][y] * cv[j] : T(0);
+        }
+    if (Tm) {
+        // Z = Y_1^-T C^-1 (upper) by a row sweep from the bottom on W = C^-1: row k of Z is final when the sweep reaches it (unit
+        // diagonal), then W[i, :] -= Y_1[k, i] Z[k, :] for i < k
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) a[x][y] = (tr + 32 * x == tc + 32 * y) ? T(1) / cv[tc + 32 * y] : T(0);
+        if (tr == 31) {
+#pragma unroll
+            for (int y = 0; y < 4; ++y) rowb[PN + tc + 32 * y] = a[3][y];       // row 127 goes to buffer (127 & 1) = 1
+        }
+        __syncthreads();
+        for (int k = PN - 1; k >= 0; --k) {
+            const T *rb = rowb + (k & 1) * PN;
+            T *rn = rowb + ((k & 1) ^ 1) * PN;
+            const int b1 = (k - 1) >> 5, b0 = k >> 5;   // live: row blocks <= b1 (i < k; none when k = 0), column blocks >= b0 (Z[k, j] = 0 for j < k)
+            T l[4], u[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) l[x] = (k > 0 && x <= b1 && tr + 32 * x < k) ? -Q[k * PLD + tr + 32 * x] : T(0);
+#pragma unroll
+            for (int y = 0; y < 4; ++y) u[y] = (y >= b0) ? rb[tc + 32 * y] : T(0);
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+                if (k > 0 && x <= b1) {
+#pragma unroll
+                    for (int y = 0; y < 4; ++y)
+                        if (y >= b0) a[x][y] = fma(l[x], u[y], a[x][y]);
+                }
+            if (k > 0 && tr == ((k - 1) & 31)) {
+#pragma unroll
+                for (int y = 0; y < 4; ++y) rn[tc + 32 * y] = row_of(a, (k - 1) >> 5, y);
+            }
+            __syncthreads();
+        }
+        // T = -C^-1 (U S) Z: Z to the packed buffer, then a 4 x 4 register-tiled product of two upper triangles
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const int i = tr + 32 * x, j = tc + 32 * y;
+                if (i <= j) P[pk(i, j)] = a[x][y];
+                a[x][y] = T(0);
+            }
+        __syncthreads();
+        for (int k = tr; k <= tc + 96; ++k) {    // U_ik needs k >= i, z_kj needs k <= j
+            const T sk = sv[k];
+            T l[4], u[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) l[x] = (k >= tr + 32 * x) ? Q[(tr + 32 * x) * PLD + k] * sk : T(0);
+#pragma unroll
+            for (int y = 0; y < 4; ++y) u[y] = (k <= tc + 32 * y) ? P[pk(k, tc + 32 * y)] : T(0);
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const int i = tr + 32 * x, j = tc + 32 * y;
+                Tm[i + (int64_t)j * ldt] = i <= j ? -a[x][y] / cv[i] : T(0);
+            }
+    }
+    // the top block in the driver's convention: s_i R[i, j] above the diagonal, the reflector heads c'_j y_ij on and below it
+    for (int j = warp; j < PN; j += 32)
+        for (int i = lane; i < PN; i += 32) {
+            T v;
+            if (i < j) {
+                const T r = R[i + (int64_t)j * ldr];
+                v = sv[i] < T(0) ? -r : r;
+            } else {
+                v = (i == j) ? cv[j] : Q[i * PLD + j] * cv[j];
+            }
+            Atop[i + (int64_t)j * ld] = v;
+            Vtop[i + (int64_t)j * ldv] = i >= j ? v : T(0);
+        }
+}
+
+}  // namespace
+
+template <typename T>
+void cholqr128(lfb_handle &h, const T *G, int64_t ldg, T *R, int64_t ldr, T *Rinv, int64_t ldri, double *guard) {
+    const size_t smem = sizeof(T) * (size_t)(PN * PLD + 4 * PN) + sizeof(double) * 4 * PN;
+    static DeviceOnce cfg;
+    cfg.run(h.device, [&] {
+        LFB_CUDA(cudaFuncSetAttribute(cholqr128_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    });
+    cholqr128_kernel<T><<<1, 1024, smem, h.stream>>>(G, ldg, R, ldr, Rinv, ldri, guard);
+    LFB_LAUNCH_CHECK(h);
+}
+
+template <typename T>
+void hr_panel128(lfb_handle &h, T *Atop, int64_t ld, const T *R, int64_t ldr, const T *Rinv, int64_t ldri, T *beta, T *M, int64_t ldm,
+                 T *Tm, int64_t ldt, T *Vtop, int64_t ldv) {
+    const size_t smem = sizeof(T) * (size_t)(PN * PLD + PN * (PN + 1) / 2 + 8 * PN);
+    static DeviceOnce cfg;
+    cfg.run(h.device, [&] {
+        LFB_CUDA(cudaFuncSetAttribute(hr_panel128_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    });
+    hr_panel128_kernel<T><<<1, 1024, smem, h.stream>>>(Atop, ld, R, ldr, Rinv, ldri, beta, M, ldm, Tm, ldt, Vtop, ldv);
+    LFB_LAUNCH_CHECK(h);
+}
+
+#define INST(T)                                                                                                      \
+    template void cholqr128<T>(lfb_handle &, const T *, int64_t, T *, int64_t, T *, int64_t, double *);               \
+    template void hr_panel128<T>(lfb_handle &, T *, int64_t, const T *, int64_t, const T *, int64_t, T *, T *, int64_t, \
+                                 T *, int64_t, T *, int64_t);
+INST(float)
+INST(double)
+#undef INST
+
+}  // namespace lfb
