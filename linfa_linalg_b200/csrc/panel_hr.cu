@@ -22,12 +22,16 @@
 //
 // The formulas were checked against a plain Householder sweep in NumPy before this file was written (V, beta, R, T all to 1e-14
 // at 700 x 128); tests/test_gpu_parity*.py hold the result to the oracle.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lfb {
 namespace {
 
 constexpr int PN = 128, PLD = PN + 1;
+#define LFB_MARK(i) do { if (dbg && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
 __device__ __forceinline__ int pk(int i, int j) { return j * (j + 1) / 2 + i; }   // packed upper triangle, i <= j
 
 // a[x][s] / a[s][y] with a run-time s as selects: a dynamic index would send the register tile to local memory
@@ -40,7 +44,7 @@ template <typename T> __device__ __forceinline__ T row_of(const T (&a)[4][4], in
 
 template <typename T>
 __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G, int64_t ldg, T *__restrict__ R, int64_t ldr,
-                                                         T *__restrict__ Rinv, int64_t ldri, double *__restrict__ guard) {
+                                                         T *__restrict__ Rinv, int64_t ldri, double *__restrict__ guard, long long *dbg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *S = reinterpret_cast<T *>(smem_raw);      // [PN][PLD]: G, then lower = L and strict upper = (L^-1)^T
     T *rk = S + PN * PLD;                        // L_kk
@@ -51,6 +55,7 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tr = lane, tc = warp;
     if (tid == 0) s_fail = 0;
+    LFB_MARK(0);
     for (int j = warp; j < PN; j += 32)
         for (int i = j + lane; i < PN; i += 32) S[i * PLD + j] = G[i + (int64_t)j * ldg];
     __syncthreads();
@@ -67,6 +72,7 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
         for (int x = 0; x < 4; ++x) buf[tr + 32 * x] = a[x][0];
     }
     __syncthreads();
+    LFB_MARK(1);
     // Cholesky, right-looking.  Column k keeps the unscaled Schur-complement entries a_ik (L_ik = a_ik / sqrt(a_kk)); the full
     // square is updated (the matrix stays symmetric), so one published column serves rows and columns.
 
@@ -80,21 +86,15 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
         }
         if (tid == 0) rk[k] = sqrt(d);
         const T dinv = T(1) / d;
-        // 32-row / 32-column blocks that lie wholly at or before the pivot are dead for every thread: skipped with block-uniform
-        // tests (the FP64 pipe issues half a warp per clock, so a full 128 x 128 rank-1 update is 512 cycles of a step)
-        const int b0 = (k + 1) >> 5;             // first block with an index > k
         T l[4], u[4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x) l[x] = (x >= b0 && tr + 32 * x > k) ? -cb[tr + 32 * x] * dinv : T(0);
+        for (int x = 0; x < 4; ++x) l[x] = (tr + 32 * x > k) ? -cb[tr + 32 * x] * dinv : T(0);
 #pragma unroll
-        for (int y = 0; y < 4; ++y) u[y] = (y >= b0 && tc + 32 * y > k) ? cb[tc + 32 * y] : T(0);
+        for (int y = 0; y < 4; ++y) u[y] = (tc + 32 * y > k) ? cb[tc + 32 * y] : T(0);
 #pragma unroll
         for (int x = 0; x < 4; ++x)
-            if (x >= b0) {
 #pragma unroll
-                for (int y = 0; y < 4; ++y)
-                    if (y >= b0) a[x][y] = fma(l[x], u[y], a[x][y]);
-            }
+            for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
         if (k + 1 < PN && tc == ((k + 1) & 31)) {
 #pragma unroll
             for (int x = 0; x < 4; ++x) cn[tr + 32 * x] = col_of(a, x, (k + 1) >> 5);
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
         if (tid == 0) { guard[0] = 1e300; guard[1] = 0.0; guard[2] = 0.0; }
         return;
     }
+    LFB_MARK(2);
     if (tid < PN) xd[tid] = T(1) / rk[tid];
     __syncthreads();
 #pragma unroll
@@ -132,19 +133,15 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
     for (int k = 0; k < PN; ++k) {
         const T *rb = buf + (k & 1) * PN;
         T *rn = buf + ((k & 1) ^ 1) * PN;
-        const int b0 = (k + 1) >> 5, b1 = k >> 5;   // live: row blocks >= b0 (i > k), column blocks <= b1 (X[k, j] = 0 for j > k)
         T l[4], u[4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x) l[x] = (x >= b0 && tr + 32 * x > k) ? -S[(tr + 32 * x) * PLD + k] : T(0);
+        for (int x = 0; x < 4; ++x) l[x] = (tr + 32 * x > k) ? -S[(tr + 32 * x) * PLD + k] : T(0);
 #pragma unroll
-        for (int y = 0; y < 4; ++y) u[y] = (y <= b1) ? rb[tc + 32 * y] : T(0);
+        for (int y = 0; y < 4; ++y) u[y] = rb[tc + 32 * y];
 #pragma unroll
         for (int x = 0; x < 4; ++x)
-            if (x >= b0) {
 #pragma unroll
-                for (int y = 0; y < 4; ++y)
-                    if (y <= b1) a[x][y] = fma(l[x], u[y], a[x][y]);
-            }
+            for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
         if (k + 1 < PN && tr == ((k + 1) & 31)) {
             const T sc = xd[k + 1];
             const int xs = (k + 1) >> 5;
@@ -159,6 +156,7 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
         }
         __syncthreads();
     }
+    LFB_MARK(3);
     // X (lower) goes to the strict upper part of S transposed, for the guard sums and a coalesced write
 #pragma unroll
     for (int x = 0; x < 4; ++x)
@@ -168,6 +166,7 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
             if (i > j) S[j * PLD + i] = a[x][y];
         }
     __syncthreads();
+    LFB_MARK(4);
     // guard: sqrt(||L||_1 ||L||_inf ||X||_1 ||X||_inf) >= cond_2(L)
     if (tid < PN) {
         const int t = tid;
@@ -199,18 +198,20 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
             guard[2] = isfinite(b) ? 1.0 : 0.0;
         }
     }
+    LFB_MARK(5);
     for (int j = warp; j < PN; j += 32)
         for (int i = lane; i < PN; i += 32) {
             R[i + (int64_t)j * ldr] = i <= j ? S[j * PLD + i] : T(0);                            // L_ji
             Rinv[i + (int64_t)j * ldri] = i < j ? S[i * PLD + j] : (i == j ? xd[j] : T(0));     // X_ji
         }
+    LFB_MARK(6);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop, int64_t ld, const T *__restrict__ R, int64_t ldr,
                                                           const T *__restrict__ Rinv, int64_t ldri, T *__restrict__ beta,
                                                           T *__restrict__ M, int64_t ldm, T *__restrict__ Tm, int64_t ldt,
-                                                          T *__restrict__ Vtop, int64_t ldv) {
+                                                          T *__restrict__ Vtop, int64_t ldv, long long *dbg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *Q = reinterpret_cast<T *>(smem_raw);      // [PN][PLD]: A_top, then Y_1 (strictly lower) and U
     T *P = Q + PN * PLD;                         // packed upper: R^-1, later Z
@@ -222,12 +223,14 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
     T *rowb = colb + 2 * PN;                     // [2][PN]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tr = lane, tc = warp;
+    LFB_MARK(0);
     for (int j = warp; j < PN; j += 32)
         for (int i = lane; i < PN; i += 32) {
             Q[i * PLD + j] = Atop[i + (int64_t)j * ld];
             if (i <= j) P[pk(i, j)] = Rinv[i + (int64_t)j * ldri];
         }
     __syncthreads();
+    LFB_MARK(1);
     // Q_top = A_top R^-1, 4 x 4 register tile per thread; the result stays in registers as the input of the LU
     T a[4][4];
 #pragma unroll
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
         for (int y = 0; y < 4; ++y) rowb[tc + 32 * y] = a[0][y];
     }
     __syncthreads();
+    LFB_MARK(2);
     // LU of (Q_top - S) without pivoting (|pivot| = 1 + |q_kk| >= 1); multipliers stay unscaled (a_ik) until the write-back
     for (int k = 0; k < PN; ++k) {
         const T *cb = colb + (k & 1) * PN, *rb = rowb + (k & 1) * PN;
@@ -263,19 +267,15 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
         const T p = q - sk;
         const T pin = T(1) / p;
         if (tid == 0) { sv[k] = sk; pv[k] = p; pinv[k] = pin; }
-        const int b0 = (k + 1) >> 5;             // blocks wholly at or before the pivot are dead (block-uniform skip)
         T l[4], u[4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x) l[x] = (x >= b0 && tr + 32 * x > k) ? -cb[tr + 32 * x] * pin : T(0);
+        for (int x = 0; x < 4; ++x) l[x] = (tr + 32 * x > k) ? -cb[tr + 32 * x] * pin : T(0);
 #pragma unroll
-        for (int y = 0; y < 4; ++y) u[y] = (y >= b0 && tc + 32 * y > k) ? rb[tc + 32 * y] : T(0);
+        for (int y = 0; y < 4; ++y) u[y] = (tc + 32 * y > k) ? rb[tc + 32 * y] : T(0);
 #pragma unroll
         for (int x = 0; x < 4; ++x)
-            if (x >= b0) {
 #pragma unroll
-                for (int y = 0; y < 4; ++y)
-                    if (y >= b0) a[x][y] = fma(l[x], u[y], a[x][y]);
-            }
+            for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
         if (k + 1 < PN) {
             if (tc == ((k + 1) & 31)) {
 #pragma unroll
@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
         }
         __syncthreads();
     }
+    LFB_MARK(3);
     // back to shared memory: Y_1 strictly below the diagonal (scaled now), U on and above it
 #pragma unroll
     for (int x = 0; x < 4; ++x)
@@ -318,22 +319,19 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
         }
     }
     __syncthreads();
+    LFB_MARK(4);
     for (int j = 0; j < PN; ++j) {
         const T *cb = colb + (j & 1) * PN;
         T *cn = colb + ((j & 1) ^ 1) * PN;
-        const int b0 = (j + 1) >> 5, b1 = j >> 5;   // live: column blocks >= b0 (j' > j), row blocks <= b1 (M[i, j] = 0 for i > j)
         T l[4], u[4];
 #pragma unroll
-        for (int x = 0; x < 4; ++x) l[x] = (x <= b1) ? -cb[tr + 32 * x] : T(0);
+        for (int x = 0; x < 4; ++x) l[x] = -cb[tr + 32 * x];
 #pragma unroll
-        for (int y = 0; y < 4; ++y) u[y] = (y >= b0 && tc + 32 * y > j) ? Q[j * PLD + tc + 32 * y] : T(0);
+        for (int y = 0; y < 4; ++y) u[y] = (tc + 32 * y > j) ? Q[j * PLD + tc + 32 * y] : T(0);
 #pragma unroll
         for (int x = 0; x < 4; ++x)
-            if (x <= b1) {
 #pragma unroll
-                for (int y = 0; y < 4; ++y)
-                    if (y >= b0) a[x][y] = fma(l[x], u[y], a[x][y]);
-            }
+            for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
         if (j + 1 < PN && tc == ((j + 1) & 31)) {
             const T sc = pinv[j + 1];
             const int ys = (j + 1) >> 5;
@@ -355,6 +353,7 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
             const int i = tr + 32 * x, j = tc + 32 * y;
             M[i + (int64_t)j * ldm] = i <= j ? a[x][y] * cv[j] : T(0);
         }
+    LFB_MARK(5);
     if (Tm) {
         // Z = Y_1^-T C^-1 (upper) by a row sweep from the bottom on W = C^-1: row k of Z is final when the sweep reaches it (unit
         // diagonal), then W[i, :] -= Y_1[k, i] Z[k, :] for i < k
@@ -370,25 +369,22 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
         for (int k = PN - 1; k >= 0; --k) {
             const T *rb = rowb + (k & 1) * PN;
             T *rn = rowb + ((k & 1) ^ 1) * PN;
-            const int b1 = (k - 1) >> 5, b0 = k >> 5;   // live: row blocks <= b1 (i < k; none when k = 0), column blocks >= b0 (Z[k, j] = 0 for j < k)
             T l[4], u[4];
 #pragma unroll
-            for (int x = 0; x < 4; ++x) l[x] = (k > 0 && x <= b1 && tr + 32 * x < k) ? -Q[k * PLD + tr + 32 * x] : T(0);
+            for (int x = 0; x < 4; ++x) l[x] = (tr + 32 * x < k) ? -Q[k * PLD + tr + 32 * x] : T(0);
 #pragma unroll
-            for (int y = 0; y < 4; ++y) u[y] = (y >= b0) ? rb[tc + 32 * y] : T(0);
+            for (int y = 0; y < 4; ++y) u[y] = rb[tc + 32 * y];
 #pragma unroll
             for (int x = 0; x < 4; ++x)
-                if (k > 0 && x <= b1) {
 #pragma unroll
-                    for (int y = 0; y < 4; ++y)
-                        if (y >= b0) a[x][y] = fma(l[x], u[y], a[x][y]);
-                }
+                for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
             if (k > 0 && tr == ((k - 1) & 31)) {
 #pragma unroll
                 for (int y = 0; y < 4; ++y) rn[tc + 32 * y] = row_of(a, (k - 1) >> 5, y);
             }
             __syncthreads();
         }
+        LFB_MARK(6);
         // T = -C^-1 (U S) Z: Z to the packed buffer, then a 4 x 4 register-tiled product of two upper triangles
 #pragma unroll
         for (int x = 0; x < 4; ++x)
@@ -419,6 +415,7 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
                 Tm[i + (int64_t)j * ldt] = i <= j ? -a[x][y] / cv[i] : T(0);
             }
     }
+    LFB_MARK(7);
     // the top block in the driver's convention: s_i R[i, j] above the diagonal, the reflector heads c'_j y_ij on and below it
     for (int j = warp; j < PN; j += 32)
         for (int i = lane; i < PN; i += 32) {
@@ -432,6 +429,7 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
             Atop[i + (int64_t)j * ld] = v;
             Vtop[i + (int64_t)j * ldv] = i >= j ? v : T(0);
         }
+    LFB_MARK(8);
 }
 
 }  // namespace
@@ -443,8 +441,19 @@ void cholqr128(lfb_handle &h, const T *G, int64_t ldg, T *R, int64_t ldr, T *Rin
     cfg.run(h.device, [&] {
         LFB_CUDA(cudaFuncSetAttribute(cholqr128_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     });
-    cholqr128_kernel<T><<<1, 1024, smem, h.stream>>>(G, ldg, R, ldr, Rinv, ldri, guard);
+    static const bool dbg_on = getenv("LFB_PANEL_DBG") != nullptr;     // debug: per-phase clock64 deltas of thread 0 on stderr
+    long long *dbg = nullptr;
+    if (dbg_on) { LFB_CUDA(cudaMalloc(&dbg, 16 * sizeof(long long))); LFB_CUDA(cudaMemset(dbg, 0, 16 * sizeof(long long))); }
+    cholqr128_kernel<T><<<1, 1024, smem, h.stream>>>(G, ldg, R, ldr, Rinv, ldri, guard, dbg);
     LFB_LAUNCH_CHECK(h);
+    if (dbg_on) {
+        long long hd[16];
+        LFB_CUDA(cudaStreamSynchronize(h.stream));
+        LFB_CUDA(cudaMemcpy(hd, dbg, sizeof hd, cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        fprintf(stderr, "cholqr128 cycles: load %lld | cholesky %lld | X sweep %lld | X to smem %lld | guard %lld | emit %lld\n", hd[1] - hd[0],
+                hd[2] - hd[1], hd[3] - hd[2], hd[4] - hd[3], hd[5] - hd[4], hd[6] - hd[5]);
+    }
 }
 
 template <typename T>
@@ -455,8 +464,19 @@ void hr_panel128(lfb_handle &h, T *Atop, int64_t ld, const T *R, int64_t ldr, co
     cfg.run(h.device, [&] {
         LFB_CUDA(cudaFuncSetAttribute(hr_panel128_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     });
-    hr_panel128_kernel<T><<<1, 1024, smem, h.stream>>>(Atop, ld, R, ldr, Rinv, ldri, beta, M, ldm, Tm, ldt, Vtop, ldv);
+    static const bool dbg_on = getenv("LFB_PANEL_DBG") != nullptr;
+    long long *dbg = nullptr;
+    if (dbg_on) { LFB_CUDA(cudaMalloc(&dbg, 16 * sizeof(long long))); LFB_CUDA(cudaMemset(dbg, 0, 16 * sizeof(long long))); }
+    hr_panel128_kernel<T><<<1, 1024, smem, h.stream>>>(Atop, ld, R, ldr, Rinv, ldri, beta, M, ldm, Tm, ldt, Vtop, ldv, dbg);
     LFB_LAUNCH_CHECK(h);
+    if (dbg_on) {
+        long long hd[16];
+        LFB_CUDA(cudaStreamSynchronize(h.stream));
+        LFB_CUDA(cudaMemcpy(hd, dbg, sizeof hd, cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        fprintf(stderr, "hr_panel128 cycles: load %lld | Q R^-1 %lld | LU %lld | write-back + M init %lld | M sweep %lld | Z sweep %lld | T %lld | top block %lld\n",
+                hd[1] - hd[0], hd[2] - hd[1], hd[3] - hd[2], hd[4] - hd[3], hd[5] - hd[4], hd[6] - hd[5], hd[7] - hd[6], hd[8] - hd[7]);
+    }
 }
 
 #define INST(T)                                                                                                      \
