@@ -690,7 +690,8 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
 
     auto factor_panel = [&](int64_t k0, int nb, T *V, T *Tm, T *Vt) {
         bool t_built = false;
-        if (sizeof(T) == 8 && h.opt.qr_panel_cholqr && nb >= 64 && (m - k0) >= 2 * (int64_t)nb && panel_cholqr(k0, nb, V, Tm, &t_built)) {
+        if ((sizeof(T) == 8 ? h.opt.qr_panel_cholqr >= 1 : h.opt.qr_panel_cholqr >= 2) && nb >= 64 && (m - k0) >= 2 * (int64_t)nb &&
+            panel_cholqr(k0, nb, V, Tm, &t_built)) {
             if (n - (k0 + nb) > 0) {
                 if (!t_built) build_t<T>(h, V, ldv, m - k0, nb, G, Tm, NB);
                 if (Vt) transpose<T>(h, V, m - k0, nb, ldv, Vt, NB);

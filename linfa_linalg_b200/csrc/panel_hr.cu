@@ -13,12 +13,13 @@
 //                        the compact-WY factor  T = -C^-1 U S Y_1^-T C^-1  (Ballard et al.'s T for Y, rescaled to the unit-norm
 //                        reflectors V = Y C) -- which replaces the second Gram GEMM + triangular inversion of build_t.
 //
-// Every O(n^3) stage is a "register sweep": thread (tr, tc) of the 32 x 32 thread grid owns the 4 x 4 elements (tr + 32 x, tc + 32 y)
-// of the working matrix in registers (cyclic, so the load stays balanced as a sweep advances); a step reads one published pivot
-// row / column from shared memory (8 loads per 16 FMAs, against one shared access per FMA for the in-place versions first
-// written: an SM issues one shared-memory instruction per cycle, which made those 3-4 x slower), updates its 16 elements, and the
-// owners of the next pivot row / column publish it -- one barrier per step.  The two dense products (Q_top = A_top R^-1 and T)
-// are 4 x 4 register-tiled.
+// Every O(n^3) stage is a "register sweep": lane tr of warp tc (NW warps) owns the 4 x (128 / NW) elements (tr + 32 x, tc + NW y) of
+// the working matrix in registers; a step reads one published pivot row / column from shared memory, updates its elements (dead
+// ones are multiplied by zero: no divergence, no imbalance), and the owners of the next pivot row / column publish it -- one
+// barrier per step.  What bounds a step is the SM's ONE shared-memory instruction per cycle (LFB_PANEL_DBG=1 prints clock64 per
+// phase): in-place loops with a shared access per FMA were 3-4 x slower than the first register version, and with 32 warps and
+// 4 x 4 tiles every warp re-reads the whole pivot column (384 wavefronts, ~1200 cycles per step); NW = 8 warps with 4 x 16 tiles
+// halve that.  The two dense products (Q_top = A_top R^-1 and T) are register-tiled the same way.
 //
 // The formulas were checked against a plain Householder sweep in NumPy before this file was written (V, beta, R, T all to 1e-14
 // at 700 x 128); tests/test_gpu_parity*.py hold the result to the oracle.
@@ -31,20 +32,42 @@ namespace lfb {
 namespace {
 
 constexpr int PN = 128, PLD = PN + 1;
+constexpr int NW = 8;                      // warps per CTA
+constexpr int YN = PN / NW;                // columns per thread: tc + NW * y
+constexpr int NTH = NW * 32;
 #define LFB_MARK(i) do { if (dbg && threadIdx.x == 0) dbg[i] = clock64(); } while (0)
 __device__ __forceinline__ int pk(int i, int j) { return j * (j + 1) / 2 + i; }   // packed upper triangle, i <= j
 
-// a[x][s] / a[s][y] with a run-time s as selects: a dynamic index would send the register tile to local memory
-template <typename T> __device__ __forceinline__ T col_of(const T (&a)[4][4], int x, int s) {
-    return s == 0 ? a[x][0] : s == 1 ? a[x][1] : s == 2 ? a[x][2] : a[x][3];
+// Column s of the register tile with a run-time (warp-uniform) s.  A dynamic index would send the tile to local memory and a
+// select chain costs 4 (YN - 1) selects on the critical path of a step; the switch executes four moves.
+#define LFB_COL_CASES(OP) \
+    OP(0) OP(1) OP(2) OP(3) OP(4) OP(5) OP(6) OP(7) OP(8) OP(9) OP(10) OP(11) OP(12) OP(13) OP(14) OP(15)
+template <typename T> __device__ __forceinline__ void get_col(const T (&a)[4][YN], int s, T (&v)[4]) {
+    switch (s) {
+#define LFB_OP(n) case n: if (n < YN) { v[0] = a[0][n < YN ? n : 0]; v[1] = a[1][n < YN ? n : 0]; v[2] = a[2][n < YN ? n : 0]; v[3] = a[3][n < YN ? n : 0]; } break;
+        LFB_COL_CASES(LFB_OP)
+#undef LFB_OP
+        default: break;
+    }
 }
-template <typename T> __device__ __forceinline__ T row_of(const T (&a)[4][4], int s, int y) {
+template <typename T> __device__ __forceinline__ void set_col(T (&a)[4][YN], int s, const T (&v)[4]) {
+    switch (s) {
+#define LFB_OP(n) case n: if (n < YN) { a[0][n < YN ? n : 0] = v[0]; a[1][n < YN ? n : 0] = v[1]; a[2][n < YN ? n : 0] = v[2]; a[3][n < YN ? n : 0] = v[3]; } break;
+        LFB_COL_CASES(LFB_OP)
+#undef LFB_OP
+        default: break;
+    }
+}
+template <typename T> __device__ __forceinline__ T row_of(const T (&a)[4][YN], int s, int y) {
     return s == 0 ? a[0][y] : s == 1 ? a[1][y] : s == 2 ? a[2][y] : a[3][y];
 }
 
+#define FOR_X _Pragma("unroll") for (int x = 0; x < 4; ++x)
+#define FOR_Y _Pragma("unroll") for (int y = 0; y < YN; ++y)
+
 template <typename T>
-__global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G, int64_t ldg, T *__restrict__ R, int64_t ldr,
-                                                         T *__restrict__ Rinv, int64_t ldri, double *__restrict__ guard, long long *dbg) {
+__global__ void __launch_bounds__(NTH, 1) cholqr128_kernel(const T *__restrict__ G, int64_t ldg, T *__restrict__ R, int64_t ldr,
+                                                           T *__restrict__ Rinv, int64_t ldri, double *__restrict__ guard, long long *dbg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *S = reinterpret_cast<T *>(smem_raw);      // [PN][PLD]: G, then lower = L and strict upper = (L^-1)^T
     T *rk = S + PN * PLD;                        // L_kk
@@ -56,26 +79,21 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
     const int tr = lane, tc = warp;
     if (tid == 0) s_fail = 0;
     LFB_MARK(0);
-    for (int j = warp; j < PN; j += 32)
+    for (int j = warp; j < PN; j += NW)
         for (int i = j + lane; i < PN; i += 32) S[i * PLD + j] = G[i + (int64_t)j * ldg];
     __syncthreads();
-    T a[4][4];
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            const int i = tr + 32 * x, j = tc + 32 * y;
-            a[x][y] = i >= j ? S[i * PLD + j] : S[j * PLD + i];
-        }
+    T a[4][YN];
+    FOR_X FOR_Y {
+        const int i = tr + 32 * x, j = tc + NW * y;
+        a[x][y] = i >= j ? S[i * PLD + j] : S[j * PLD + i];
+    }
     if (tc == 0) {
-#pragma unroll
-        for (int x = 0; x < 4; ++x) buf[tr + 32 * x] = a[x][0];
+        FOR_X buf[tr + 32 * x] = a[x][0];
     }
     __syncthreads();
     LFB_MARK(1);
     // Cholesky, right-looking.  Column k keeps the unscaled Schur-complement entries a_ik (L_ik = a_ik / sqrt(a_kk)); the full
     // square is updated (the matrix stays symmetric), so one published column serves rows and columns.
-
     for (int k = 0; k < PN; ++k) {
         const T *cb = buf + (k & 1) * PN;
         T *cn = buf + ((k & 1) ^ 1) * PN;
@@ -86,18 +104,14 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
         }
         if (tid == 0) rk[k] = sqrt(d);
         const T dinv = T(1) / d;
-        T l[4], u[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) l[x] = (tr + 32 * x > k) ? -cb[tr + 32 * x] * dinv : T(0);
-#pragma unroll
-        for (int y = 0; y < 4; ++y) u[y] = (tc + 32 * y > k) ? cb[tc + 32 * y] : T(0);
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
-        if (k + 1 < PN && tc == ((k + 1) & 31)) {
-#pragma unroll
-            for (int x = 0; x < 4; ++x) cn[tr + 32 * x] = col_of(a, x, (k + 1) >> 5);
+        T l[4], u[YN];
+        FOR_X l[x] = (tr + 32 * x > k) ? -cb[tr + 32 * x] * dinv : T(0);
+        FOR_Y u[y] = (tc + NW * y > k) ? cb[tc + NW * y] : T(0);
+        FOR_X FOR_Y a[x][y] = fma(l[x], u[y], a[x][y]);
+        if (k + 1 < PN && tc == ((k + 1) & (NW - 1))) {
+            T v[4];
+            get_col(a, (k + 1) / NW, v);
+            FOR_X cn[tr + 32 * x] = v[x];
         }
         __syncthreads();
     }
@@ -109,62 +123,44 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
     LFB_MARK(2);
     if (tid < PN) xd[tid] = T(1) / rk[tid];
     __syncthreads();
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            const int i = tr + 32 * x, j = tc + 32 * y;
-            if (i > j) S[i * PLD + j] = a[x][y] * xd[j];
-            else if (i == j) S[i * PLD + j] = rk[j];
-        }
+    FOR_X FOR_Y {
+        const int i = tr + 32 * x, j = tc + NW * y;
+        if (i > j) S[i * PLD + j] = a[x][y] * xd[j];
+        else if (i == j) S[i * PLD + j] = rk[j];
+    }
     // X = L^-1 by a forward sweep on W = I: row k of X is W[k, :] / L_kk, then W[i, :] -= L_ik X[k, :] for i > k
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) a[x][y] = (tr + 32 * x == tc + 32 * y) ? T(1) : T(0);
+    FOR_X FOR_Y a[x][y] = (tr + 32 * x == tc + NW * y) ? T(1) : T(0);
     if (tr == 0) {
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
+        FOR_Y {
             a[0][y] *= xd[0];
-            buf[tc + 32 * y] = a[0][y];
+            buf[tc + NW * y] = a[0][y];
         }
     }
     __syncthreads();
     for (int k = 0; k < PN; ++k) {
         const T *rb = buf + (k & 1) * PN;
         T *rn = buf + ((k & 1) ^ 1) * PN;
-        T l[4], u[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) l[x] = (tr + 32 * x > k) ? -S[(tr + 32 * x) * PLD + k] : T(0);
-#pragma unroll
-        for (int y = 0; y < 4; ++y) u[y] = rb[tc + 32 * y];
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
+        T l[4], u[YN];
+        FOR_X l[x] = (tr + 32 * x > k) ? -S[(tr + 32 * x) * PLD + k] : T(0);
+        FOR_Y u[y] = rb[tc + NW * y];
+        FOR_X FOR_Y a[x][y] = fma(l[x], u[y], a[x][y]);
         if (k + 1 < PN && tr == ((k + 1) & 31)) {
             const T sc = xd[k + 1];
             const int xs = (k + 1) >> 5;
-#pragma unroll
-            for (int y = 0; y < 4; ++y) {
+            FOR_Y {
                 const T v = row_of(a, xs, y) * sc;
-                rn[tc + 32 * y] = v;
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-                    if (x == xs) a[x][y] = v;
+                rn[tc + NW * y] = v;
+                FOR_X if (x == xs) a[x][y] = v;
             }
         }
         __syncthreads();
     }
     LFB_MARK(3);
     // X (lower) goes to the strict upper part of S transposed, for the guard sums and a coalesced write
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            const int i = tr + 32 * x, j = tc + 32 * y;
-            if (i > j) S[j * PLD + i] = a[x][y];
-        }
+    FOR_X FOR_Y {
+        const int i = tr + 32 * x, j = tc + NW * y;
+        if (i > j) S[j * PLD + i] = a[x][y];
+    }
     __syncthreads();
     LFB_MARK(4);
     // guard: sqrt(||L||_1 ||L||_inf ||X||_1 ||X||_inf) >= cond_2(L)
@@ -199,7 +195,7 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
         }
     }
     LFB_MARK(5);
-    for (int j = warp; j < PN; j += 32)
+    for (int j = warp; j < PN; j += NW)
         for (int i = lane; i < PN; i += 32) {
             R[i + (int64_t)j * ldr] = i <= j ? S[j * PLD + i] : T(0);                            // L_ji
             Rinv[i + (int64_t)j * ldri] = i < j ? S[i * PLD + j] : (i == j ? xd[j] : T(0));     // X_ji
@@ -208,10 +204,10 @@ __global__ void __launch_bounds__(1024) cholqr128_kernel(const T *__restrict__ G
 }
 
 template <typename T>
-__global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop, int64_t ld, const T *__restrict__ R, int64_t ldr,
-                                                          const T *__restrict__ Rinv, int64_t ldri, T *__restrict__ beta,
-                                                          T *__restrict__ M, int64_t ldm, T *__restrict__ Tm, int64_t ldt,
-                                                          T *__restrict__ Vtop, int64_t ldv, long long *dbg) {
+__global__ void __launch_bounds__(NTH, 1) hr_panel128_kernel(T *__restrict__ Atop, int64_t ld, const T *__restrict__ R, int64_t ldr,
+                                                            const T *__restrict__ Rinv, int64_t ldri, T *__restrict__ beta,
+                                                            T *__restrict__ M, int64_t ldm, T *__restrict__ Tm, int64_t ldt,
+                                                            T *__restrict__ Vtop, int64_t ldv, long long *dbg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *Q = reinterpret_cast<T *>(smem_raw);      // [PN][PLD]: A_top, then Y_1 (strictly lower) and U
     T *P = Q + PN * PLD;                         // packed upper: R^-1, later Z
@@ -224,37 +220,27 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tr = lane, tc = warp;
     LFB_MARK(0);
-    for (int j = warp; j < PN; j += 32)
+    for (int j = warp; j < PN; j += NW)
         for (int i = lane; i < PN; i += 32) {
             Q[i * PLD + j] = Atop[i + (int64_t)j * ld];
             if (i <= j) P[pk(i, j)] = Rinv[i + (int64_t)j * ldri];
         }
     __syncthreads();
     LFB_MARK(1);
-    // Q_top = A_top R^-1, 4 x 4 register tile per thread; the result stays in registers as the input of the LU
-    T a[4][4];
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) a[x][y] = T(0);
-    for (int k = 0; k <= tc + 96; ++k) {         // R^-1 is upper triangular: column j needs k <= j
-        T l[4], u[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) l[x] = Q[(tr + 32 * x) * PLD + k];
-#pragma unroll
-        for (int y = 0; y < 4; ++y) u[y] = (k <= tc + 32 * y) ? P[pk(k, tc + 32 * y)] : T(0);
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
+    // Q_top = A_top R^-1, register tile per thread; the result stays in registers as the input of the LU
+    T a[4][YN];
+    FOR_X FOR_Y a[x][y] = T(0);
+    for (int k = 0; k <= tc + NW * (YN - 1); ++k) {   // R^-1 is upper triangular: column j needs k <= j
+        T l[4], u[YN];
+        FOR_X l[x] = Q[(tr + 32 * x) * PLD + k];
+        FOR_Y u[y] = (k <= tc + NW * y) ? P[pk(k, tc + NW * y)] : T(0);
+        FOR_X FOR_Y a[x][y] = fma(l[x], u[y], a[x][y]);
     }
     if (tc == 0) {
-#pragma unroll
-        for (int x = 0; x < 4; ++x) colb[tr + 32 * x] = a[x][0];
+        FOR_X colb[tr + 32 * x] = a[x][0];
     }
     if (tr == 0) {
-#pragma unroll
-        for (int y = 0; y < 4; ++y) rowb[tc + 32 * y] = a[0][y];
+        FOR_Y rowb[tc + NW * y] = a[0][y];
     }
     __syncthreads();
     LFB_MARK(2);
@@ -267,53 +253,41 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
         const T p = q - sk;
         const T pin = T(1) / p;
         if (tid == 0) { sv[k] = sk; pv[k] = p; pinv[k] = pin; }
-        T l[4], u[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) l[x] = (tr + 32 * x > k) ? -cb[tr + 32 * x] * pin : T(0);
-#pragma unroll
-        for (int y = 0; y < 4; ++y) u[y] = (tc + 32 * y > k) ? rb[tc + 32 * y] : T(0);
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
+        T l[4], u[YN];
+        FOR_X l[x] = (tr + 32 * x > k) ? -cb[tr + 32 * x] * pin : T(0);
+        FOR_Y u[y] = (tc + NW * y > k) ? rb[tc + NW * y] : T(0);
+        FOR_X FOR_Y a[x][y] = fma(l[x], u[y], a[x][y]);
         if (k + 1 < PN) {
-            if (tc == ((k + 1) & 31)) {
-#pragma unroll
-                for (int x = 0; x < 4; ++x) cn[tr + 32 * x] = col_of(a, x, (k + 1) >> 5);
+            if (tc == ((k + 1) & (NW - 1))) {
+                T v[4];
+                get_col(a, (k + 1) / NW, v);
+                FOR_X cn[tr + 32 * x] = v[x];
             }
             if (tr == ((k + 1) & 31)) {
-#pragma unroll
-                for (int y = 0; y < 4; ++y) rn[tc + 32 * y] = row_of(a, (k + 1) >> 5, y);
+                FOR_Y rn[tc + NW * y] = row_of(a, (k + 1) >> 5, y);
             }
         }
         __syncthreads();
     }
     LFB_MARK(3);
     // back to shared memory: Y_1 strictly below the diagonal (scaled now), U on and above it
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            const int i = tr + 32 * x, j = tc + 32 * y;
-            Q[i * PLD + j] = i > j ? a[x][y] * pinv[j] : (i == j ? pv[j] : a[x][y]);
-        }
+    FOR_X FOR_Y {
+        const int i = tr + 32 * x, j = tc + NW * y;
+        Q[i * PLD + j] = i > j ? a[x][y] * pinv[j] : (i == j ? pv[j] : a[x][y]);
+    }
     if (tid < PN) {
         const int k = tid;
         cv[k] = -sv[k] * sqrt(fabs(pv[k]) / T(2));
         beta[k] = sv[k] * fabs(R[k + (int64_t)k * ldr]);
     }
     // M = R^-1 U^-1 by a column sweep on W = R^-1: column j of M is W[:, j] / U_jj, then W[:, j'] -= M[:, j] U[j, j'] for j' > j
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            const int i = tr + 32 * x, j = tc + 32 * y;
-            a[x][y] = i <= j ? P[pk(i, j)] : T(0);
-        }
+    FOR_X FOR_Y {
+        const int i = tr + 32 * x, j = tc + NW * y;
+        a[x][y] = i <= j ? P[pk(i, j)] : T(0);
+    }
     __syncthreads();                             // Q, pinv, cv complete; every thread has its part of R^-1
     if (tc == 0) {
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
+        FOR_X {
             a[x][0] *= pinv[0];
             colb[tr + 32 * x] = a[x][0];
         }
@@ -323,101 +297,70 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
     for (int j = 0; j < PN; ++j) {
         const T *cb = colb + (j & 1) * PN;
         T *cn = colb + ((j & 1) ^ 1) * PN;
-        T l[4], u[4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x) l[x] = -cb[tr + 32 * x];
-#pragma unroll
-        for (int y = 0; y < 4; ++y) u[y] = (tc + 32 * y > j) ? Q[j * PLD + tc + 32 * y] : T(0);
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
-        if (j + 1 < PN && tc == ((j + 1) & 31)) {
+        T l[4], u[YN];
+        FOR_X l[x] = -cb[tr + 32 * x];
+        FOR_Y u[y] = (tc + NW * y > j) ? Q[j * PLD + tc + NW * y] : T(0);
+        FOR_X FOR_Y a[x][y] = fma(l[x], u[y], a[x][y]);
+        if (j + 1 < PN && tc == ((j + 1) & (NW - 1))) {
             const T sc = pinv[j + 1];
-            const int ys = (j + 1) >> 5;
-#pragma unroll
-            for (int x = 0; x < 4; ++x) {
-                const T v = col_of(a, x, ys) * sc;
-                cn[tr + 32 * x] = v;
-#pragma unroll
-                for (int y = 0; y < 4; ++y)
-                    if (y == ys) a[x][y] = v;
+            T v[4];
+            get_col(a, (j + 1) / NW, v);
+            FOR_X {
+                v[x] *= sc;
+                cn[tr + 32 * x] = v[x];
             }
+            set_col(a, (j + 1) / NW, v);
         }
         __syncthreads();
     }
-#pragma unroll
-    for (int x = 0; x < 4; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) {
-            const int i = tr + 32 * x, j = tc + 32 * y;
-            M[i + (int64_t)j * ldm] = i <= j ? a[x][y] * cv[j] : T(0);
-        }
+    FOR_X FOR_Y {
+        const int i = tr + 32 * x, j = tc + NW * y;
+        M[i + (int64_t)j * ldm] = i <= j ? a[x][y] * cv[j] : T(0);
+    }
     LFB_MARK(5);
     if (Tm) {
         // Z = Y_1^-T C^-1 (upper) by a row sweep from the bottom on W = C^-1: row k of Z is final when the sweep reaches it (unit
         // diagonal), then W[i, :] -= Y_1[k, i] Z[k, :] for i < k
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) a[x][y] = (tr + 32 * x == tc + 32 * y) ? T(1) / cv[tc + 32 * y] : T(0);
+        FOR_X FOR_Y a[x][y] = (tr + 32 * x == tc + NW * y) ? T(1) / cv[tc + NW * y] : T(0);
         if (tr == 31) {
-#pragma unroll
-            for (int y = 0; y < 4; ++y) rowb[PN + tc + 32 * y] = a[3][y];       // row 127 goes to buffer (127 & 1) = 1
+            FOR_Y rowb[PN + tc + NW * y] = a[3][y];       // row 127 goes to buffer (127 & 1) = 1
         }
         __syncthreads();
         for (int k = PN - 1; k >= 0; --k) {
             const T *rb = rowb + (k & 1) * PN;
             T *rn = rowb + ((k & 1) ^ 1) * PN;
-            T l[4], u[4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) l[x] = (tr + 32 * x < k) ? -Q[k * PLD + tr + 32 * x] : T(0);
-#pragma unroll
-            for (int y = 0; y < 4; ++y) u[y] = rb[tc + 32 * y];
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
+            T l[4], u[YN];
+            FOR_X l[x] = (tr + 32 * x < k) ? -Q[k * PLD + tr + 32 * x] : T(0);
+            FOR_Y u[y] = rb[tc + NW * y];
+            FOR_X FOR_Y a[x][y] = fma(l[x], u[y], a[x][y]);
             if (k > 0 && tr == ((k - 1) & 31)) {
-#pragma unroll
-                for (int y = 0; y < 4; ++y) rn[tc + 32 * y] = row_of(a, (k - 1) >> 5, y);
+                FOR_Y rn[tc + NW * y] = row_of(a, (k - 1) >> 5, y);
             }
             __syncthreads();
         }
         LFB_MARK(6);
-        // T = -C^-1 (U S) Z: Z to the packed buffer, then a 4 x 4 register-tiled product of two upper triangles
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) {
-                const int i = tr + 32 * x, j = tc + 32 * y;
-                if (i <= j) P[pk(i, j)] = a[x][y];
-                a[x][y] = T(0);
-            }
-        __syncthreads();
-        for (int k = tr; k <= tc + 96; ++k) {    // U_ik needs k >= i, z_kj needs k <= j
-            const T sk = sv[k];
-            T l[4], u[4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) l[x] = (k >= tr + 32 * x) ? Q[(tr + 32 * x) * PLD + k] * sk : T(0);
-#pragma unroll
-            for (int y = 0; y < 4; ++y) u[y] = (k <= tc + 32 * y) ? P[pk(k, tc + 32 * y)] : T(0);
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) a[x][y] = fma(l[x], u[y], a[x][y]);
+        // T = -C^-1 (U S) Z: Z to the packed buffer, then a register-tiled product of two upper triangles
+        FOR_X FOR_Y {
+            const int i = tr + 32 * x, j = tc + NW * y;
+            if (i <= j) P[pk(i, j)] = a[x][y];
+            a[x][y] = T(0);
         }
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) {
-                const int i = tr + 32 * x, j = tc + 32 * y;
-                Tm[i + (int64_t)j * ldt] = i <= j ? -a[x][y] / cv[i] : T(0);
-            }
+        __syncthreads();
+        for (int k = tr; k <= tc + NW * (YN - 1); ++k) {    // U_ik needs k >= i, z_kj needs k <= j
+            const T sk = sv[k];
+            T l[4], u[YN];
+            FOR_X l[x] = (k >= tr + 32 * x) ? Q[(tr + 32 * x) * PLD + k] * sk : T(0);
+            FOR_Y u[y] = (k <= tc + NW * y) ? P[pk(k, tc + NW * y)] : T(0);
+            FOR_X FOR_Y a[x][y] = fma(l[x], u[y], a[x][y]);
+        }
+        FOR_X FOR_Y {
+            const int i = tr + 32 * x, j = tc + NW * y;
+            Tm[i + (int64_t)j * ldt] = i <= j ? -a[x][y] / cv[i] : T(0);
+        }
     }
     LFB_MARK(7);
     // the top block in the driver's convention: s_i R[i, j] above the diagonal, the reflector heads c'_j y_ij on and below it
-    for (int j = warp; j < PN; j += 32)
+    for (int j = warp; j < PN; j += NW)
         for (int i = lane; i < PN; i += 32) {
             T v;
             if (i < j) {
@@ -432,6 +375,9 @@ __global__ void __launch_bounds__(1024) hr_panel128_kernel(T *__restrict__ Atop,
     LFB_MARK(8);
 }
 
+#undef FOR_X
+#undef FOR_Y
+
 }  // namespace
 
 template <typename T>
@@ -444,7 +390,7 @@ void cholqr128(lfb_handle &h, const T *G, int64_t ldg, T *R, int64_t ldr, T *Rin
     static const bool dbg_on = getenv("LFB_PANEL_DBG") != nullptr;     // debug: per-phase clock64 deltas of thread 0 on stderr
     long long *dbg = nullptr;
     if (dbg_on) { LFB_CUDA(cudaMalloc(&dbg, 16 * sizeof(long long))); LFB_CUDA(cudaMemset(dbg, 0, 16 * sizeof(long long))); }
-    cholqr128_kernel<T><<<1, 1024, smem, h.stream>>>(G, ldg, R, ldr, Rinv, ldri, guard, dbg);
+    cholqr128_kernel<T><<<1, NTH, smem, h.stream>>>(G, ldg, R, ldr, Rinv, ldri, guard, dbg);
     LFB_LAUNCH_CHECK(h);
     if (dbg_on) {
         long long hd[16];
@@ -467,7 +413,7 @@ void hr_panel128(lfb_handle &h, T *Atop, int64_t ld, const T *R, int64_t ldr, co
     static const bool dbg_on = getenv("LFB_PANEL_DBG") != nullptr;
     long long *dbg = nullptr;
     if (dbg_on) { LFB_CUDA(cudaMalloc(&dbg, 16 * sizeof(long long))); LFB_CUDA(cudaMemset(dbg, 0, 16 * sizeof(long long))); }
-    hr_panel128_kernel<T><<<1, 1024, smem, h.stream>>>(Atop, ld, R, ldr, Rinv, ldri, beta, M, ldm, Tm, ldt, Vtop, ldv, dbg);
+    hr_panel128_kernel<T><<<1, NTH, smem, h.stream>>>(Atop, ld, R, ldr, Rinv, ldri, beta, M, ldm, Tm, ldt, Vtop, ldv, dbg);
     LFB_LAUNCH_CHECK(h);
     if (dbg_on) {
         long long hd[16];
