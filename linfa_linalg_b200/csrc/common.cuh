@@ -44,7 +44,8 @@ struct CudaError : std::runtime_error {
 struct Options {
     int64_t qr_nb = 128;     // outer panel width of blocked compact-WY QR
     int64_t qr_nb_f32 = 256; // same for f32 when the trailing updates run on the tcgen05 kernel (n >= 2048)
-    int64_t qr_vt = 0;       // f64 QR: rank-nb update through a transposed copy of V (TN form); measured: no gain (263.8 vs 263.5 ms), off
+    int64_t qr_vt = 1;       // f64 QR: rank-nb update through a transposed copy of V (K-major tiles on both sides: 2 TMA box loads per stage instead of 9,
+                             // which matters since the two-CTA kernel issues them from a compute warp): 231.1 vs 234.0 ms, same bits
     int64_t qr_panel_cholqr = 1; // f64 blocked QR: panel = guarded Cholesky-QR + Householder reconstruction (tsqr_hr.cu) when its condition bound passes; else the cluster panel kernels
     int64_t cholqr_fused = 1;    // 128-column Cholesky-QR stages as single-CTA kernels (panel_hr.cu): Cholesky + inverse + guard, and reconstruction + M + T
     int64_t qr_trace = 0;    // debug: event time stamps of every stage of the look-ahead pipeline on stderr
