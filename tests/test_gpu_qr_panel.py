@@ -79,6 +79,21 @@ def test_qr_panel_routes_match_oracle(L, name):
             assert np.array_equal(np.signbit(outs[tag][1]), np.signbit(outs["fused"][1]))
 
 
+@pytest.mark.parametrize("shape", [(700, 200), (1000, 328), (300, 130), (257, 128), (255, 128), (4100, 384)])
+def test_qr_panel_ragged_widths_match_oracle(L, shape):
+    """Last panels of 72 / 72 / 2 columns (the separate-launch Cholesky-QR route for 64 <= nb < 128, cluster panels below that) and
+    panels just above / below the rows >= 2 nb gate."""
+    m, n = shape
+    a0 = np.random.default_rng(m * 7 + n).uniform(-1, 1, (m, n))
+    ref = np.asfortranarray(a0)
+    dref = O.qr(ref)
+    a, d = _qr_with(L, a0)
+    t = 64 * m * EPS * np.linalg.norm(a0)
+    assert np.max(np.abs(a - ref)) <= t
+    assert np.max(np.abs(d - dref)) <= t
+    assert np.array_equal(np.signbit(d), np.signbit(dref))
+
+
 def test_qr_panel_2048_large_entries(L):
     """QR 2176 x 2048 with entries in [-100, 100] (tests/common.rs:9 scale): seventeen 128-column panels on the fused route."""
     m, n = 2176, 2048
