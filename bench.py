@@ -219,6 +219,9 @@ def main():
 
     import linfa_linalg_b200 as L
     eng = L.Engine(local_rank)
+    for kv in filter(None, os.environ.get("LFB_OPTS", "").split(",")):      # A/B runs: LFB_OPTS="chol_waves=1,gemm_tma2=0" python bench.py
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     lib = eng.lib
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)

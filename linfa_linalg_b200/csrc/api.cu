@@ -3,6 +3,8 @@
 // column-major HBM layout, and the device-resident variants.
 #include <memory>
 
+#include <chrono>
+
 #include "common.cuh"
 #include "host_io.cuh"
 
@@ -122,6 +124,9 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
     const int64_t n = rows;
     if (n == 0) return LFB_OK;                                                               // cholesky.rs:270-272
     int64_t info = 0;
+    const auto t_entry = std::chrono::steady_clock::now();
+    auto since_entry = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(); };
+    double t_enq0 = 0, t_enq1 = 0;
     LFB_API_BEGIN(h)
     const int64_t ld = round_up(n, 4);      // 16-byte columns for TMA in both precisions
     DevBuf<T> dA(*h, (size_t)ld * n);
@@ -151,42 +156,6 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
         size_t tri_elems = 0;
         for (int64_t r0 = 0; r0 < n; r0 += BAND) tri_elems += (size_t)(std::min(n, r0 + BAND) - r0) * (size_t)std::max(std::min(n, r0 + BAND), n - r0);
         stagebuf = (T *)h->pinned_buf(sizeof(T) * tri_elems);
-    }
-    std::unique_ptr<DevBuf<T>> rowtmp;
-    if (!tri) {
-        upload<T>(*h, a, n, n, rs, cs, dA, ld);
-    } else if (staged) {
-        T *sp = stagebuf;
-        if (lay != L_COL) rowtmp.reset(new DevBuf<T>(*h, (size_t)hld * n));
-        for (int64_t b0 = 0; b0 < n; b0 += BAND) {
-            const int64_t b1 = std::min(n, b0 + BAND);
-            if (lay == L_COL) {      // columns b0..b1, rows b0..n-1 of each: width n - b0, height b1 - b0, pitch hld
-                host_gather<T>(*h, a + b0 + b0 * hld, hld, n - b0, b1 - b0, sp);
-                LFB_CUDA(cudaMemcpy2DAsync(dA.get() + b0 + b0 * ld, ld * sizeof(T), sp, (n - b0) * sizeof(T), (n - b0) * sizeof(T), b1 - b0,
-                                           cudaMemcpyHostToDevice, h->stream));
-                sp += (size_t)(n - b0) * (b1 - b0);
-            } else {                 // rows b0..b1, columns 0..b1-1 of each: width b1, height b1 - b0
-                host_gather<T>(*h, a + b0 * hld, hld, b1, b1 - b0, sp);
-                LFB_CUDA(cudaMemcpy2DAsync(rowtmp->get() + b0 * hld, hld * sizeof(T), sp, b1 * sizeof(T), b1 * sizeof(T), b1 - b0,
-                                           cudaMemcpyHostToDevice, h->stream));
-                sp += (size_t)b1 * (b1 - b0);
-            }
-        }
-        if (lay != L_COL) transpose<T>(*h, rowtmp->get(), n, n, hld, dA, ld);
-    } else if (lay == L_COL) {   // column j holds rows j..n-1: bands of columns
-        for (int64_t c0 = 0; c0 < n; c0 += BAND) {
-            const int64_t c1 = std::min(n, c0 + BAND);
-            LFB_CUDA(cudaMemcpy2DAsync(dA.get() + c0 + c0 * ld, ld * sizeof(T), a + c0 + c0 * hld, hld * sizeof(T),
-                                       (n - c0) * sizeof(T), c1 - c0, cudaMemcpyHostToDevice, h->stream));
-        }
-    } else {                     // row-major: row i holds columns 0..i: bands of rows, then transpose on the device
-        DevBuf<T> tmp(*h, (size_t)hld * n);
-        for (int64_t r0 = 0; r0 < n; r0 += BAND) {
-            const int64_t r1 = std::min(n, r0 + BAND);
-            LFB_CUDA(cudaMemcpy2DAsync(tmp.get() + r0 * hld, hld * sizeof(T), a + r0 * hld, hld * sizeof(T), r1 * sizeof(T), r1 - r0,
-                                       cudaMemcpyHostToDevice, h->stream));
-        }
-        transpose<T>(*h, tmp.get(), n, n, hld, dA, ld);   // the unread upper triangle carries whatever tmp held
     }
     // Dirty factorisation of a large matrix: every finished block column of L starts its way back to the host as
     // soon as its panel is factored (a copy stream waits on an event recorded behind the panel), so the D2H traffic
@@ -257,9 +226,157 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
             }
         };
     }
+    // Arrival waves (n >= 8192): with the upload first, the 20 ms the lower trapezoid of a 16384^2 f64 matrix spends on PCIe are
+    // fully exposed (a right-looking step 0 touches every column).  Instead the block columns cross in order on their own stream
+    // and the factorisation runs in waves over the columns that have arrived: wave w = one large-K catch-up product for its
+    // trapezoid + a right-looking sweep restricted to its columns (potrf.cu: cholesky_lower_wave).  Boundaries from the model
+    // time(w) = max(arrival, previous wave) + flops(w) / rate: upload-bound up to ~0.3 n, compute-bound afterwards.
+    std::vector<int64_t> wend;
+    if (tri && n >= 8192 && h->opt.chol_waves > 1) {
+        static const double frac[3][3] = {{0.28, 0, 0}, {0.16, 0.31, 0}, {0.09, 0.19, 0.34}};
+        const int nwv = (int)std::min<int64_t>(h->opt.chol_waves, 4);
+        for (int w = 0; w + 1 < nwv; ++w) {
+            int64_t e = std::min<int64_t>(n, std::max<int64_t>(BAND, (int64_t)(frac[nwv - 2][w] * (double)n / (double)BAND + 0.5) * BAND));
+            if (wend.empty() || e > wend.back()) wend.push_back(e);
+        }
+        if (wend.empty() || wend.back() < n) wend.push_back(n);
+        if (wend.size() < 2) wend.clear();
+    }
+    const bool waves = !wend.empty();
+    std::unique_ptr<DevBuf<T>> rowtmp;
+    if (waves) {
+        // uploads are enqueued wave by wave below, next to the compute that consumes them
+    } else if (!tri) {
+        upload<T>(*h, a, n, n, rs, cs, dA, ld);
+    } else if (staged) {
+        T *sp = stagebuf;
+        if (lay != L_COL) rowtmp.reset(new DevBuf<T>(*h, (size_t)hld * n));
+        for (int64_t b0 = 0; b0 < n; b0 += BAND) {
+            const int64_t b1 = std::min(n, b0 + BAND);
+            if (lay == L_COL) {      // columns b0..b1, rows b0..n-1 of each: width n - b0, height b1 - b0, pitch hld
+                host_gather<T>(*h, a + b0 + b0 * hld, hld, n - b0, b1 - b0, sp);
+                LFB_CUDA(cudaMemcpy2DAsync(dA.get() + b0 + b0 * ld, ld * sizeof(T), sp, (n - b0) * sizeof(T), (n - b0) * sizeof(T), b1 - b0,
+                                           cudaMemcpyHostToDevice, h->stream));
+                sp += (size_t)(n - b0) * (b1 - b0);
+            } else {                 // rows b0..b1, columns 0..b1-1 of each: width b1, height b1 - b0
+                host_gather<T>(*h, a + b0 * hld, hld, b1, b1 - b0, sp);
+                LFB_CUDA(cudaMemcpy2DAsync(rowtmp->get() + b0 * hld, hld * sizeof(T), sp, b1 * sizeof(T), b1 * sizeof(T), b1 - b0,
+                                           cudaMemcpyHostToDevice, h->stream));
+                sp += (size_t)b1 * (b1 - b0);
+            }
+        }
+        if (lay != L_COL) transpose<T>(*h, rowtmp->get(), n, n, hld, dA, ld);
+    } else if (lay == L_COL) {   // column j holds rows j..n-1: bands of columns
+        for (int64_t c0 = 0; c0 < n; c0 += BAND) {
+            const int64_t c1 = std::min(n, c0 + BAND);
+            LFB_CUDA(cudaMemcpy2DAsync(dA.get() + c0 + c0 * ld, ld * sizeof(T), a + c0 + c0 * hld, hld * sizeof(T),
+                                       (n - c0) * sizeof(T), c1 - c0, cudaMemcpyHostToDevice, h->stream));
+        }
+    } else {                     // row-major: row i holds columns 0..i: bands of rows, then transpose on the device
+        DevBuf<T> tmp(*h, (size_t)hld * n);
+        for (int64_t r0 = 0; r0 < n; r0 += BAND) {
+            const int64_t r1 = std::min(n, r0 + BAND);
+            LFB_CUDA(cudaMemcpy2DAsync(tmp.get() + r0 * hld, hld * sizeof(T), a + r0 * hld, hld * sizeof(T), r1 * sizeof(T), r1 - r0,
+                                       cudaMemcpyHostToDevice, h->stream));
+        }
+        transpose<T>(*h, tmp.get(), n, n, hld, dA, ld);   // the unread upper triangle carries whatever tmp held
+    }
+    std::vector<cudaEvent_t> wev;
     try {
-        cholesky_lower<T>(*h, dA, n, ld, clean, dInfo);
+        if (!waves) {
+            cholesky_lower<T>(*h, dA, n, ld, clean, dInfo);
+        } else {
+            if (!h->upload_stream) LFB_CUDA(cudaStreamCreateWithFlags(&h->upload_stream, cudaStreamNonBlocking));
+            cudaStream_t us = h->upload_stream, ms = h->stream;
+            {   // the upload stream starts behind whatever the caller's stream holds (dA may be a recycled block)
+                cudaEvent_t e0;
+                LFB_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+                wev.push_back(e0);
+                LFB_CUDA(cudaEventRecord(e0, ms));
+                LFB_CUDA(cudaStreamWaitEvent(us, e0, 0));
+            }
+            static const bool wdbg = getenv("LFB_WAVE_DBG") != nullptr && atoi(getenv("LFB_WAVE_DBG")) == 1;      // debug: event time stamps of every wave on stderr (2: host time stamps only)
+            std::vector<cudaEvent_t> tev;
+            auto stamp = [&](cudaStream_t st) {
+                if (!wdbg) return;
+                cudaEvent_t e;
+                LFB_CUDA(cudaEventCreate(&e));
+                LFB_CUDA(cudaEventRecord(e, st));
+                tev.push_back(e);
+            };
+            stamp(ms);
+            t_enq0 = since_entry();
+            size_t tmp_elems = 0;
+            if (lay != L_COL)
+                for (int64_t c0 = 0; c0 < n; c0 += BAND) tmp_elems += (size_t)(n - c0) * (size_t)(std::min(n, c0 + BAND) - c0);
+            if (lay != L_COL) rowtmp.reset(new DevBuf<T>(*h, tmp_elems));
+            T *sp = stagebuf;
+            T *tp = rowtmp ? rowtmp->get() : nullptr;
+            int64_t c_begin = 0;
+            for (size_t w = 0; w < wend.size(); ++w) {
+                const int64_t c_end = wend[w];
+                for (int64_t c0 = c_begin; c0 < c_end; c0 += BAND) {       // block columns c0..c1, rows c0..n-1
+                    const int64_t c1 = std::min(c_end, c0 + BAND), wd = c1 - c0, ht = n - c0;
+                    if (lay == L_COL) {
+                        if (staged) {
+                            host_gather<T>(*h, a + c0 + c0 * hld, hld, ht, wd, sp);
+                            LFB_CUDA(cudaMemcpy2DAsync(dA.get() + c0 + c0 * ld, ld * sizeof(T), sp, ht * sizeof(T), ht * sizeof(T), wd,
+                                                       cudaMemcpyHostToDevice, us));
+                            sp += (size_t)ht * wd;
+                        } else {
+                            LFB_CUDA(cudaMemcpy2DAsync(dA.get() + c0 + c0 * ld, ld * sizeof(T), a + c0 + c0 * hld, hld * sizeof(T), ht * sizeof(T), wd,
+                                                       cudaMemcpyHostToDevice, us));
+                        }
+                    } else {             // row-major host: row r holds this block column as wd contiguous entries
+                        if (staged) {
+                            host_gather<T>(*h, a + c0 * hld + c0, hld, wd, ht, sp);
+                            LFB_CUDA(cudaMemcpyAsync(tp, sp, sizeof(T) * (size_t)ht * wd, cudaMemcpyHostToDevice, us));
+                            sp += (size_t)ht * wd;
+                        } else {
+                            LFB_CUDA(cudaMemcpy2DAsync(tp, wd * sizeof(T), a + c0 * hld + c0, hld * sizeof(T), wd * sizeof(T), ht,
+                                                       cudaMemcpyHostToDevice, us));
+                        }
+                        h->stream = us;
+                        try {
+                            transpose<T>(*h, tp, wd, ht, wd, dA.get() + c0 + c0 * ld, ld);
+                        } catch (...) {
+                            h->stream = ms;
+                            throw;
+                        }
+                        h->stream = ms;
+                        tp += (size_t)ht * wd;
+                    }
+                }
+                cudaEvent_t e;
+                LFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                wev.push_back(e);
+                LFB_CUDA(cudaEventRecord(e, us));
+                stamp(us);
+                stamp(ms);
+                LFB_CUDA(cudaStreamWaitEvent(ms, e, 0));
+                cholesky_lower_wave<T>(*h, dA, n, ld, c_begin, c_end, dInfo, w == 0);
+                stamp(ms);
+                c_begin = c_end;
+            }
+            t_enq1 = since_entry();
+            if (wdbg) {
+                fprintf(stderr, "chol waves host: first enqueue at %.3f ms after entry, all waves enqueued at %.3f ms\n", t_enq0, t_enq1);
+                LFB_CUDA(cudaStreamSynchronize(ms));
+                LFB_CUDA(cudaStreamSynchronize(us));
+                fprintf(stderr, "chol waves n=%lld (ms from start): wave end-col | upload done | main stream free | wave done\n", (long long)n);
+                for (size_t w = 0; w < wend.size(); ++w) {
+                    float t[3];
+                    for (int q = 0; q < 3; ++q) cudaEventElapsedTime(&t[q], tev[0], tev[1 + 3 * w + q]);
+                    fprintf(stderr, "  %6lld | %8.3f | %8.3f | %8.3f\n", (long long)wend[w], t[0], t[1], t[2]);
+                }
+                for (auto e : tev) cudaEventDestroy(e);
+            }
+            if (clean) triangular_zero<T>(*h, dA.get(), n, ld, /*keep_lower=*/1);
+        }
     } catch (...) {
+        if (h->upload_stream) cudaStreamSynchronize(h->upload_stream);
+        for (auto e : wev) cudaEventDestroy(e);
+        wev.clear();
         h->chol_panel_hook = nullptr;
         // copies queued by the hook may still be reading dA / the staging buffer: drain before the DevBufs are released
         if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
@@ -268,6 +385,7 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
         throw;
     }
     h->chol_panel_hook = nullptr;
+    for (auto e : wev) cudaEventDestroy(e);      // (destroying a recorded event is legal: its waits stay in place)
     LFB_CUDA(cudaMemcpyAsync(&info, dInfo.get(), sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     if (overlap) {
         // staged: scatter every block column into the caller's storage as soon as its D2H has landed -- the factorisation
@@ -324,6 +442,7 @@ int cholesky_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, i
         }
         LFB_CUDA(cudaStreamSynchronize(h->stream));
     }
+    if (getenv("LFB_WAVE_DBG")) fprintf(stderr, "chol host: returning %.3f ms after entry\n", since_entry());
     if (info != 0) {
         if (fail_index) *fail_index = info - 1;
         h->err = "Matrix is not positive definite";
@@ -764,6 +883,7 @@ int lfb_destroy(lfb_handle *h) {
     if (h->pinned) cudaFreeHost(h->pinned);
     delete h->host_pool;
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->upload_stream) cudaStreamDestroy(h->upload_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->aux2_stream) cudaStreamDestroy(h->aux2_stream);
@@ -826,7 +946,7 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
         {"chol_nb", &o.chol_nb, 64, 8192}, {"chol_tn", &o.chol_tn, 0, 1}, {"chol_nb_tail", &o.chol_nb_tail, 64, 8192}, {"chol_tail_rows", &o.chol_tail_rows, 0, BIG}, {"chol_split_panel", &o.chol_split_panel, 0, 1}, {"chol_trace", &o.chol_trace, 0, 1}, {"chol_potf2_rl", &o.chol_potf2_rl, 0, 1}, {"gemm_tma", &o.gemm_tma, 0, 1}, {"gemm_splitk", &o.gemm_splitk, 0, 1}, {"gemm_deterministic", &o.gemm_deterministic, 0, 1}, {"tsqr_cholqr_cond", &o.tsqr_cholqr_cond, 0, 1 << 20},
         {"gemm_v2", &o.gemm_v2, 0, 1}, {"sgemm_tc", &o.sgemm_tc, 0, 2}, {"gemm_split_waves", &o.gemm_split_waves, 1, 64}, {"panel_cluster", &o.panel_cluster, 0, 2},
         {"panel_cluster_max", &o.panel_cluster_max, 1, 16}, {"lookahead", &o.lookahead, 0, 1}, {"tsqr_chunk", &o.tsqr_chunk, 64, BIG},
-        {"batched_quad", &o.batched_quad, 0, 4}, {"gemm_tma2", &o.gemm_tma2, 0, 2}, {"qr_trace", &o.qr_trace, 0, 1}, {"qr_panel_cholqr", &o.qr_panel_cholqr, 0, 2}, {"cholqr_fused", &o.cholqr_fused, 0, 1}, {"gemm_tma2_maxk", &o.gemm_tma2_maxk, 16, 1 << 30}, {"tsqr_streams", &o.tsqr_streams, 1, 64}, {"tsqr_graph", &o.tsqr_graph, 0, 1}, {"hr_lu_blocked", &o.hr_lu_blocked, 0, 1},
+        {"batched_quad", &o.batched_quad, 0, 4}, {"gemm_tma2", &o.gemm_tma2, 0, 2}, {"qr_trace", &o.qr_trace, 0, 1}, {"chol_waves", &o.chol_waves, 1, 4}, {"qr_panel_cholqr", &o.qr_panel_cholqr, 0, 2}, {"cholqr_fused", &o.cholqr_fused, 0, 1}, {"gemm_tma2_maxk", &o.gemm_tma2_maxk, 16, 1 << 30}, {"tsqr_streams", &o.tsqr_streams, 1, 64}, {"tsqr_graph", &o.tsqr_graph, 0, 1}, {"hr_lu_blocked", &o.hr_lu_blocked, 0, 1},
         {"qr_tsqr_auto", &o.qr_tsqr_auto, 0, 1}, {"trd_fused", &o.trd_fused, 0, 1}, {"chol_overlap_d2h", &o.chol_overlap_d2h, 0, 1}, {"host_staging", &o.host_staging, 0, 1},
         {"rot_staged", &o.rot_staged, 0, 1}, {"eigh_stable_2x2", &o.eigh_stable_2x2, 0, 1}, {"rot_serial", &o.rot_serial, 0, 1},
         {"fast_hypot", &o.fast_hypot, 0, 1}, {"bd_blocked", &o.bd_blocked, 0, 1}, {"trd_profile", &o.trd_profile, 0, 1},

@@ -81,6 +81,7 @@ struct Options {
     int64_t rot_serial = 0;         // debug: one chain per pass
     int64_t eigh_stable_2x2 = 1;    // eigh.rs:111 basis without cancellation (0 = the reference's formula verbatim)
     int64_t fast_hypot = 1;         // host recurrence: sqrt(x^2 + y^2) instead of hypot when far from underflow
+    int64_t chol_waves = 3;         // host Cholesky (n >= 8192): factor in this many arrival waves of block columns while the rest is still crossing PCIe (1 = upload first)
     int64_t chol_overlap_d2h = 1;   // host Cholesky (dirty, n >= 2048): finished block columns go back to the host during the factorisation
     int64_t host_staging = 1;       // host Cholesky on PAGEABLE memory (n >= 2048): gather / scatter through the pinned buffer with host threads
     int64_t tsqr_streams = 8;       // chunks in flight (each panel kernel occupies one 16-SM cluster)
@@ -195,6 +196,7 @@ struct lfb_handle {
     //      so that the finished block column can start its way back to the host while the trailing update runs ----
     std::function<void(int64_t k0, int64_t nb)> chol_panel_hook;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t upload_stream = nullptr;   // host Cholesky in arrival waves: H2D pieces (and their transposes) while earlier columns are factored
     void drop_graphs() {
         for (auto &g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
         graphs.clear();
@@ -310,6 +312,7 @@ template <typename T> void assemble_q(lfb_handle &h, const T *M, int64_t rows, i
 template <typename T> void qt_mul(lfb_handle &h, const T *QR, int64_t rows, int64_t cols, int64_t ld, const T *diag,
                                   T *B, int64_t bcols, int64_t ldb);
 template <typename T> void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64_t *d_info);
+template <typename T> void cholesky_lower_wave(lfb_handle &h, T *A, int64_t n, int64_t ld, int64_t c0, int64_t c1, int64_t *d_info, int first);
 // op(A) X = B, A n x n column-major, lower != 0 -> A is lower triangular; trans != 0 -> solve A^T X = B.
 template <typename T> void trsm_left(lfb_handle &h, int lower, int trans, int64_t n, int64_t nrhs, const T *A, int64_t lda,
                                      const T *ext_diag, T *B, int64_t ldb);

@@ -316,10 +316,15 @@ __global__ void __launch_bounds__(256) trsm_mult_kernel(T *B, int64_t ldb, int64
 
 }  // namespace
 
+// ncols < n: factor only the first ncols columns (full height n) -- the trapezoid of one "arrival wave" of the host path
+// (api.cu: cholesky_host), whose trailing columns are brought up to date later by one large-K product.  col_base: global index of
+// column 0 (failure index, panel hook); reset_info = 0 keeps an earlier wave's failure.
 template <typename T>
-static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64_t *d_info) {
-    LFB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int64_t), h.stream));
+static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64_t *d_info, int64_t ncols = -1,
+                              int64_t col_base = 0, int reset_info = 1) {
+    if (reset_info) LFB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int64_t), h.stream));
     if (n <= 0) return;
+    if (ncols < 0 || ncols > n) ncols = n;
     const size_t smem_p = sizeof(T) * (2 * CB * SP + 32 * SP);
     const size_t smem_t = sizeof(T) * (CB * 132 + CB * 68);
     static DeviceOnce cfg;   // function attributes are per device
@@ -336,8 +341,8 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
         for (int64_t j0 = k0; j0 < pend; j0 += CB) {
             const int jb = (int)std::min<int64_t>(CB, pend - j0);
             T *Ajj = A + j0 + j0 * ld;
-            if (h.opt.chol_potf2_rl) potf2_rl_inv_kernel<T><<<1, 256, smem_p, h.stream>>>(Ajj, ld, jb, j0, d_info, Linv.get());
-            else potf2_inv_kernel<T><<<1, 256, smem_p, h.stream>>>(Ajj, ld, jb, j0, d_info, Linv.get());
+            if (h.opt.chol_potf2_rl) potf2_rl_inv_kernel<T><<<1, 256, smem_p, h.stream>>>(Ajj, ld, jb, j0 + col_base, d_info, Linv.get());
+            else potf2_inv_kernel<T><<<1, 256, smem_p, h.stream>>>(Ajj, ld, jb, j0 + col_base, d_info, Linv.get());
             LFB_LAUNCH_CHECK(h);
             const int64_t below = n - (j0 + jb);
             if (below <= 0) continue;
@@ -380,8 +385,8 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
             const int jb = (int)std::min<int64_t>(CB, pend - j0);
             T *Ajj = A + j0 + j0 * ld;
             T *Lj = LinvAll.get() + (size_t)jb_i * CB * CB;
-            if (h.opt.chol_potf2_rl) potf2_rl_inv_kernel<T><<<1, 256, smem_p, s1>>>(Ajj, ld, jb, j0, d_info, Lj);
-            else potf2_inv_kernel<T><<<1, 256, smem_p, s1>>>(Ajj, ld, jb, j0, d_info, Lj);
+            if (h.opt.chol_potf2_rl) potf2_rl_inv_kernel<T><<<1, 256, smem_p, s1>>>(Ajj, ld, jb, j0 + col_base, d_info, Lj);
+            else potf2_inv_kernel<T><<<1, 256, smem_p, s1>>>(Ajj, ld, jb, j0 + col_base, d_info, Lj);
             LFB_LAUNCH_CHECK(h);
             LFB_CUDA(cudaEventRecord(evP[jb_i], s1));
             const int64_t inner = pend - (j0 + jb);             // rows of the diagonal block below this 64-block
@@ -457,26 +462,27 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
     // step is bound by the panel chain, whose granularity (not its length) is what a narrower panel improves, while the
     // SYRKs that lose efficiency at the smaller K are short anyway (n = 8192: 12.2 ms at nb 256 against 13.0 at 512).
     const int64_t NBT = std::min<int64_t>(NB, std::max<int64_t>(CB, round_up(h.opt.chol_nb_tail, CB)));
-    auto width_at = [&](int64_t k0) { return std::min<int64_t>((n - k0 > h.opt.chol_tail_rows) ? NB : NBT, n - k0); };
+    auto width_at = [&](int64_t k0) { return std::min<int64_t>((n - k0 > h.opt.chol_tail_rows) ? NB : NBT, ncols - k0); };
     const int64_t nb0 = width_at(0);
     factor_panel(0, nb0);
-    if (h.chol_panel_hook) h.chol_panel_hook(0, nb0);
-    if (tn && n > nb0) transpose<T>(h, A + nb0, n - nb0, nb0, ld, PtBuf[0]->get(), ldpt);
+    if (h.chol_panel_hook) h.chol_panel_hook(col_base, nb0);
+    if (tn && ncols > nb0) transpose<T>(h, A + nb0, n - nb0, nb0, ld, PtBuf[0]->get(), ldpt);
     mark(h.stream, -1, 0);
     int cur = 0;
     int pi = -1;
-    for (int64_t k0 = 0, nb_step = nb0; k0 < n; k0 += nb_step, cur ^= 1) {
+    for (int64_t k0 = 0, nb_step = nb0; k0 < ncols; k0 += nb_step, cur ^= 1) {
         const int64_t nb = width_at(k0);
         nb_step = nb;
         ++pi;
         const int64_t pend = k0 + nb;
         const int64_t rows = n - pend;
-        if (rows <= 0) break;
+        if (rows <= 0 || pend >= ncols) break;      // no further column of this call to update
         const int64_t nbn = width_at(pend);
         T *P = A + pend + k0 * ld;
         const T *Pt = tn ? PtBuf[cur]->get() : nullptr;
         T *PtNext = tn ? PtBuf[cur ^ 1]->get() : nullptr;
         const int64_t rows2 = rows - nbn;
+        const int64_t cols2 = std::min(rows2, ncols - (pend + nbn));   // columns of the rest of the update (= rows2 for the whole matrix)
         if (la) {
             mark(sm, pi, 1);
             syrk(P, Pt, 0, rows, nbn, nb, A + pend + pend * ld);
@@ -489,22 +495,22 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
                 if (split_ok) factor_panel_split(pend, nbn);
                 else factor_panel(pend, nbn);
                 mark(sp, pi, 4);
-                if (h.chol_panel_hook) h.chol_panel_hook(pend, nbn);     // h.stream is the side stream here
-                if (tn && rows2 > 0) transpose<T>(h, A + (pend + nbn) + pend * ld, rows2, nbn, ld, PtNext, ldpt);
+                if (h.chol_panel_hook) h.chol_panel_hook(col_base + pend, nbn);     // h.stream is the side stream here
+                if (tn && cols2 > 0) transpose<T>(h, A + (pend + nbn) + pend * ld, rows2, nbn, ld, PtNext, ldpt);
             } catch (...) {
                 h.stream = sm;
                 throw;
             }
             LFB_CUDA(cudaEventRecord(h.ev[1], sp));
             h.stream = sm;
-            if (rows2 > 0) syrk(P, Pt, nbn, rows2, rows2, nb, A + (pend + nbn) + (pend + nbn) * ld);
+            if (cols2 > 0) syrk(P, Pt, nbn, rows2, cols2, nb, A + (pend + nbn) + (pend + nbn) * ld);
             mark(sm, pi, 5);
             LFB_CUDA(cudaStreamWaitEvent(sm, h.ev[1], 0));
         } else {
-            syrk(P, Pt, 0, rows, rows, nb, A + pend + pend * ld);
+            syrk(P, Pt, 0, rows, std::min(rows, ncols - pend), nb, A + pend + pend * ld);
             factor_panel(pend, nbn);
-            if (h.chol_panel_hook) h.chol_panel_hook(pend, nbn);
-            if (tn && rows2 > 0) transpose<T>(h, A + (pend + nbn) + pend * ld, rows2, nbn, ld, PtNext, ldpt);
+            if (h.chol_panel_hook) h.chol_panel_hook(col_base + pend, nbn);
+            if (tn && cols2 > 0) transpose<T>(h, A + (pend + nbn) + pend * ld, rows2, nbn, ld, PtNext, ldpt);
         }
     }
     if (trace) {
@@ -524,7 +530,7 @@ static void cholesky_lower_v1(lfb_handle &h, T *A, int64_t n, int64_t ld, int cl
             fprintf(stderr, "  %3d | %8.3f %8.3f | %8.3f %8.3f | %8.3f\n", kv.first, kv.second[1], kv.second[2], kv.second[3], kv.second[4],
                     kv.second[5]);
     }
-    if (clean) triangular_zero<T>(h, A, n, ld, /*keep_lower=*/1);
+    if (clean && ncols == n) triangular_zero<T>(h, A, n, ld, /*keep_lower=*/1);
 }
 
 template <typename T>
@@ -536,6 +542,21 @@ void cholesky_lower(lfb_handle &h, T *A, int64_t n, int64_t ld, int clean, int64
     // dropped rather than kept as a slower option.
     cholesky_lower_v1<T>(h, A, n, ld, clean, d_info);
 }
+
+// One arrival wave of the host path: columns [c0, c1) of the n x n matrix A, whose columns < c0 already hold L and whose columns
+// [c0, c1) hold the caller's entries.  (a) catch-up: the trapezoid A[c0:, c0:c1] -= L[c0:, 0:c0] L[c0:c1, 0:c0]^T -- one product with
+// K = c0 (the large-K regime of the GEMM, where a right-looking sweep would have made c0 / nb passes with K = nb); (b) the
+// right-looking factorisation of the trapezoid with look-ahead.  first = 1 clears the failure index.
+template <typename T>
+void cholesky_lower_wave(lfb_handle &h, T *A, int64_t n, int64_t ld, int64_t c0, int64_t c1, int64_t *d_info, int first) {
+    if (c1 <= c0) return;
+    if (first) LFB_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int64_t), h.stream));
+    if (c0 > 0)
+        gemm<T>(h, 0, 1, n - c0, c1 - c0, c0, T(-1), A + c0, ld, A + c0, ld, T(1), A + c0 + c0 * ld, ld, /*lower_only=*/1);
+    cholesky_lower_v1<T>(h, A + c0 + c0 * ld, n - c0, ld, /*clean=*/0, d_info, c1 - c0, c0, /*reset_info=*/0);
+}
+template void cholesky_lower_wave<float>(lfb_handle &, float *, int64_t, int64_t, int64_t, int64_t, int64_t *, int);
+template void cholesky_lower_wave<double>(lfb_handle &, double *, int64_t, int64_t, int64_t, int64_t, int64_t *, int);
 
 // Device time (us per launch) of one diagonal-block kernel on a 64 x 64 SPD block: kind 0 = left-looking (first
 // generation), 1 = right-looking register-blocked; +2 = factor only (no inverse).  The input is restored before every
