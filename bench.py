@@ -326,7 +326,8 @@ def main():
         eng.set_stream(None)
         ksteps = max(1, min(args.steps, 3))
         fail = C.c_int64(-1)
-        # only lower-triangular trapezoids (bands of 1024 rows) cross PCIe: csrc/api.cu cholesky_host
+        # only lower-triangular trapezoids (1024-wide block columns, rows from the diagonal block down) cross PCIe, in arrival
+        # waves that overlap the factorisation: csrc/api.cu cholesky_host (option chol_waves)
         tri_bytes = sum(min(n, r0 + 1024) * (min(n, r0 + 1024) - r0) * 8 for r0 in range(0, n, 1024)) if n >= 2048 else n * n * 8
 
         def e2e_leg(host_src, host_work):
