@@ -736,13 +736,22 @@ def run_extras(args, eng, lib, dev, stream, world, rank, timed, barrier):
         flipped = int((~same).sum())
         ferr = float(np.max(np.abs(np.abs(dgot[~same]) - np.abs(dref[~same])))) if flipped else 0.0
         sign_ok = flipped <= 4 and ferr <= 1e-3
-        ok_t = torch.tensor([1 if (berr <= 16 * 32 * 1.2e-7 * 32 ** 0.5 and sign_ok) else 0], device=dev)
+        # elementwise tolerance per matrix: 16 n eps sqrt(n) for a well-conditioned sample, widened in proportion to the spread of
+        # |diag(R)| (a lower bound of cond_2): among the 32768 matrices sampled over 8 ranks a few have a pivot ~1e-3 of the
+        # largest, and the forward error of ANY backward-stable QR -- the oracle's too -- grows with that ratio
+        base_tol = 16 * 32 * 1.2e-7 * 32 ** 0.5
+        kap = np.abs(dref).max(axis=1) / np.maximum(np.abs(dref).min(axis=1), 1e-30)
+        e_b = np.maximum(np.abs(got - ref).reshape(len(ref), -1).max(axis=1), np.abs(dgot - dref).max(axis=1))
+        tol_b = base_tol * np.maximum(1.0, kap / 64.0)
+        worst = float(np.max(e_b[same] / tol_b[same])) if same.any() else 0.0
+        ok_t = torch.tensor([1 if (worst <= 1.0 and sign_ok) else 0], device=dev)
         if world > 1:
             dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
         out["batched_qr_f32"] = {"workload": f"{B} x (32x32) f32, {per} per GPU (C3)", "matrices_per_s": B * 20 / (ms_k * 1e-3),
                                  "ms_per_step": ms_k / 20, "kernel_GBps_per_gpu": gbs, "hbm_peak_GBps": hbm,
                                  "frac_of_hbm": gbs / hbm, "scaling": "strong", "note": "restore copy timed separately and subtracted",
-                                 "check": {"sampled": 4096, "max_abs_err_vs_oracle": berr, "matrices_with_a_flipped_near_zero_pivot": flipped},
+                                 "check": {"sampled": 4096, "max_abs_err_vs_oracle": berr, "worst_err_over_conditioned_tol": worst,
+                                           "matrices_with_a_flipped_near_zero_pivot": flipped},
                                  "check_ok": bool(ok_t.item())}
         # batched Cholesky on the same shard (north star: "batched small-matrix QR/Cholesky is split by batch")
         M0.copy_(torch.bmm(M0, M0.transpose(1, 2)))
