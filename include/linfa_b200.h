@@ -68,7 +68,13 @@ int lfb_synchronize(lfb_handle *h);
 /* Version / build string, and the number of kernels this handle has launched so far. */
 const char *lfb_version(void);
 int64_t lfb_launch_count(lfb_handle *h);
-/* Tunables: "qr_nb", "qr_sub", "chol_base", "gemm_tma" (0/1), ...; returns LFB_INVALID_ARGUMENT if unknown. */
+/* Tunables: "qr_nb", "qr_sub", "chol_base", "gemm_tma" (0/1), ...; returns LFB_INVALID_ARGUMENT if unknown or out of range.
+ * Routes that depend on the data and can be pinned for reproducibility studies (results agree to rounding either way):
+ *   "qr_panel_cholqr" (default 1): 128-column panels of lfb_qr_f64 as guarded Cholesky-QR + Householder reconstruction when
+ *       the panel's condition bound is <= "tsqr_cholqr_cond" (16), else Householder panel kernels; 0 = always Householder.
+ *   "chol_waves" (default 3): lfb_cholesky_* on a host view with n >= 8192 factors in that many arrival waves of block columns
+ *       while the rest of the matrix is still crossing PCIe; 1 = upload first (the summation order of the updates differs).
+ *   "gemm_deterministic" (default 1): split-K partial sums reduced in a fixed order (bit-reproducible run to run). */
 int lfb_set_option(lfb_handle *h, const char *key, int64_t value);
 
 /* ---- QR: qr.rs:29-45 QRInto::qr_into (driver loop :38-41 over householder.rs:34-51) --------- */
