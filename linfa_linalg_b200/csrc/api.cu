@@ -55,10 +55,76 @@ int qr_host(lfb_handle *h, T *a, int64_t rows, int64_t cols, int64_t rs, int64_t
     const int64_t ld = round_up(rows, 4);     // 16-byte columns for TMA in both precisions
     DevBuf<T> dA(*h, (size_t)ld * cols), dD(*h, cols);
     upload<T>(*h, a, rows, cols, rs, cs, dA, ld);
-    if (tsqr_route(*h, rows, cols, force_tsqr)) qr_tsqr<T>(*h, dA, rows, cols, ld, dD);
-    else qr_factor<T>(*h, dA, rows, cols, ld, dD);
-    download<T>(*h, dA, ld, a, rows, cols, rs, cs);
-    download_vec<T>(*h, dD, cols, diag);
+    if (tsqr_route(*h, rows, cols, force_tsqr)) {
+        qr_tsqr<T>(*h, dA, rows, cols, ld, dD);
+        download<T>(*h, dA, ld, a, rows, cols, rs, cs);
+        download_vec<T>(*h, dD, cols, diag);
+    } else {
+        // Large matrix in page-locked host memory: every block column of the factor starts its way back as soon as its panel is
+        // factored and signed (householder.cu: finish_panel), on a copy stream behind an event -- the D2H traffic (2 GiB at
+        // 16384^2 f64, ~43 ms) hides behind the trailing updates, as in cholesky_host.
+        int64_t hld = 0;
+        const Layout lay = classify(rows, cols, rs, cs, &hld);
+        bool pinned_host = false;
+        {
+            cudaPointerAttributes pa;
+            if (cudaPointerGetAttributes(&pa, a) == cudaSuccess) pinned_host = pa.type == cudaMemoryTypeHost || pa.type == cudaMemoryTypeManaged;
+            else cudaGetLastError();
+        }
+        const bool overlap = h->opt.qr_overlap_d2h && pinned_host && lay != L_GEN && cols >= 2048;
+        std::vector<cudaEvent_t> pev;
+        std::unique_ptr<DevBuf<T>> stage;
+        if (overlap) {
+            if (!h->copy_stream) LFB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            if (lay == L_ROW) stage.reset(new DevBuf<T>(*h, (size_t)rows * cols));
+            lfb_handle *hh = h;
+            T *dAp = dA.get();
+            T *stg = stage ? stage->get() : nullptr;
+            h->qr_panel_hook = [hh, dAp, stg, a, rows, ld, hld, lay, &pev](int64_t k0, int64_t nb) {
+                cudaEvent_t e;
+                LFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                pev.push_back(e);
+                LFB_CUDA(cudaEventRecord(e, hh->stream));
+                LFB_CUDA(cudaStreamWaitEvent(hh->copy_stream, e, 0));
+                if (lay == L_COL) {
+                    LFB_CUDA(cudaMemcpy2DAsync(a + k0 * hld, hld * sizeof(T), dAp + k0 * ld, ld * sizeof(T), rows * sizeof(T), nb,
+                                               cudaMemcpyDeviceToHost, hh->copy_stream));
+                } else {                 // row-major host: the block column as rows of nb entries
+                    T *t = stg + (size_t)k0 * rows;
+                    cudaStream_t keep = hh->stream;
+                    hh->stream = hh->copy_stream;
+                    try {
+                        transpose<T>(*hh, dAp + k0 * ld, rows, nb, ld, t, nb);
+                    } catch (...) {
+                        hh->stream = keep;
+                        throw;
+                    }
+                    hh->stream = keep;
+                    LFB_CUDA(cudaMemcpy2DAsync(a + k0, hld * sizeof(T), t, nb * sizeof(T), nb * sizeof(T), rows, cudaMemcpyDeviceToHost,
+                                               hh->copy_stream));
+                }
+            };
+        }
+        try {
+            qr_factor<T>(*h, dA, rows, cols, ld, dD);
+        } catch (...) {
+            h->qr_panel_hook = nullptr;
+            if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+            cudaStreamSynchronize(h->stream);
+            for (auto e : pev) cudaEventDestroy(e);
+            throw;
+        }
+        h->qr_panel_hook = nullptr;
+        if (overlap) {
+            download_vec<T>(*h, dD, cols, diag);
+            LFB_CUDA(cudaStreamSynchronize(h->copy_stream));
+            LFB_CUDA(cudaStreamSynchronize(h->stream));
+            for (auto e : pev) cudaEventDestroy(e);
+        } else {
+            download<T>(*h, dA, ld, a, rows, cols, rs, cs);
+            download_vec<T>(*h, dD, cols, diag);
+        }
+    }
     LFB_API_END(h)
 }
 
@@ -946,7 +1012,7 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
         {"chol_nb", &o.chol_nb, 64, 8192}, {"chol_tn", &o.chol_tn, 0, 1}, {"chol_nb_tail", &o.chol_nb_tail, 64, 8192}, {"chol_tail_rows", &o.chol_tail_rows, 0, BIG}, {"chol_split_panel", &o.chol_split_panel, 0, 1}, {"chol_trace", &o.chol_trace, 0, 1}, {"chol_potf2_rl", &o.chol_potf2_rl, 0, 1}, {"gemm_tma", &o.gemm_tma, 0, 1}, {"gemm_splitk", &o.gemm_splitk, 0, 1}, {"gemm_deterministic", &o.gemm_deterministic, 0, 1}, {"tsqr_cholqr_cond", &o.tsqr_cholqr_cond, 0, 1 << 20},
         {"gemm_v2", &o.gemm_v2, 0, 1}, {"sgemm_tc", &o.sgemm_tc, 0, 2}, {"gemm_split_waves", &o.gemm_split_waves, 1, 64}, {"panel_cluster", &o.panel_cluster, 0, 2},
         {"panel_cluster_max", &o.panel_cluster_max, 1, 16}, {"lookahead", &o.lookahead, 0, 1}, {"tsqr_chunk", &o.tsqr_chunk, 64, BIG},
-        {"batched_quad", &o.batched_quad, 0, 4}, {"gemm_tma2", &o.gemm_tma2, 0, 2}, {"qr_trace", &o.qr_trace, 0, 1}, {"chol_waves", &o.chol_waves, 1, 4}, {"qr_panel_cholqr", &o.qr_panel_cholqr, 0, 2}, {"cholqr_fused", &o.cholqr_fused, 0, 1}, {"gemm_tma2_maxk", &o.gemm_tma2_maxk, 16, 1 << 30}, {"tsqr_streams", &o.tsqr_streams, 1, 64}, {"tsqr_graph", &o.tsqr_graph, 0, 1}, {"hr_lu_blocked", &o.hr_lu_blocked, 0, 1},
+        {"batched_quad", &o.batched_quad, 0, 4}, {"gemm_tma2", &o.gemm_tma2, 0, 2}, {"qr_trace", &o.qr_trace, 0, 1}, {"qr_overlap_d2h", &o.qr_overlap_d2h, 0, 1}, {"chol_waves", &o.chol_waves, 1, 4}, {"qr_panel_cholqr", &o.qr_panel_cholqr, 0, 2}, {"cholqr_fused", &o.cholqr_fused, 0, 1}, {"gemm_tma2_maxk", &o.gemm_tma2_maxk, 16, 1 << 30}, {"tsqr_streams", &o.tsqr_streams, 1, 64}, {"tsqr_graph", &o.tsqr_graph, 0, 1}, {"hr_lu_blocked", &o.hr_lu_blocked, 0, 1},
         {"qr_tsqr_auto", &o.qr_tsqr_auto, 0, 1}, {"trd_fused", &o.trd_fused, 0, 1}, {"chol_overlap_d2h", &o.chol_overlap_d2h, 0, 1}, {"host_staging", &o.host_staging, 0, 1},
         {"rot_staged", &o.rot_staged, 0, 1}, {"eigh_stable_2x2", &o.eigh_stable_2x2, 0, 1}, {"rot_serial", &o.rot_serial, 0, 1},
         {"fast_hypot", &o.fast_hypot, 0, 1}, {"bd_blocked", &o.bd_blocked, 0, 1}, {"trd_profile", &o.trd_profile, 0, 1},

@@ -48,6 +48,7 @@ struct Options {
                              // which matters since the two-CTA kernel issues them from a compute warp): 231.1 vs 234.0 ms, same bits
     int64_t qr_panel_cholqr = 1; // f64 blocked QR: panel = guarded Cholesky-QR + Householder reconstruction (tsqr_hr.cu) when its condition bound passes; else the cluster panel kernels
     int64_t cholqr_fused = 1;    // 128-column Cholesky-QR stages as single-CTA kernels (panel_hr.cu): Cholesky + inverse + guard, and reconstruction + M + T
+    int64_t qr_overlap_d2h = 1;  // host QR (pinned memory, cols >= 2048): finished block columns go back to the host during the factorisation
     int64_t qr_trace = 0;    // debug: event time stamps of every stage of the look-ahead pipeline on stderr
     int64_t qr_sub = 32;     // inner BLAS-2 sub-panel width (<= 32)
     int64_t chol_base = 64;  // recursion base of Cholesky / TRSM (<= 64)
@@ -195,6 +196,7 @@ struct lfb_handle {
     // ---- Cholesky host path: called (at enqueue time) right after panel [k0, k0 + nb) has been factored on `stream`,
     //      so that the finished block column can start its way back to the host while the trailing update runs ----
     std::function<void(int64_t k0, int64_t nb)> chol_panel_hook;
+    std::function<void(int64_t k0, int64_t nb)> qr_panel_hook;     // host QR: block column [k0, k0 + nb) is final (reference signs applied) on h.stream
     cudaStream_t copy_stream = nullptr;
     cudaStream_t upload_stream = nullptr;   // host Cholesky in arrival waves: H2D pieces (and their transposes) while earlier columns are factored
     void drop_graphs() {

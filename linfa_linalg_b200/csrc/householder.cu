@@ -460,6 +460,32 @@ __global__ void sign_fix_kernel(T *A, int64_t ld, int64_t m, int64_t n, const T 
     }
 }
 
+// The same two passes for ONE panel [k0, k0 + nb), so that a finished block column can leave for the host while the
+// factorisation goes on (api.cu: qr_host): the running sign continues from *carry (P_{k0-1}; 1 before the first panel).
+template <typename T>
+__global__ void sign_scan_panel_kernel(const T *__restrict__ beta, int64_t k0, int nb, T *__restrict__ carry, T *__restrict__ psign,
+                                       T *__restrict__ diag) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    T p = *carry;
+    for (int64_t j = k0; j < k0 + nb; ++j) {
+        const T b = beta[j];
+        diag[j] = (b != T(0)) ? p * b : T(0);
+        if (b != T(0)) p = t_signum(b);
+        psign[j] = p;
+    }
+    *carry = p;
+}
+
+template <typename T>
+__global__ void sign_fix_panel_kernel(T *A, int64_t ld, int64_t m, int64_t k0, int nb, const T *__restrict__ psign) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    for (int64_t c = k0 + blockIdx.y; c < k0 + nb; c += gridDim.y) {
+        const T f = (r < c) ? psign[r] : (c > 0 ? psign[c - 1] : T(1));
+        if (f < T(0)) A[r + c * ld] = -A[r + c * ld];
+    }
+}
+
 // cum[j] = prod_{i <= j} signum(signs[i]) for j < cnt.
 template <typename T>
 __global__ void sign_cumprod_kernel(const T *__restrict__ signs, int64_t cnt, T *__restrict__ cum) {
@@ -629,8 +655,11 @@ bool factor_subpanel_cluster(lfb_handle &h, T *A, int64_t ld, int64_t m, int64_t
 }  // namespace
 
 // Standard (unscaled) blocked Householder QR of A (m x n, m >= n); beta[n] on device.
+// fin != nullptr (host path with overlapped download): after a panel is factored its block column gets the reference's signs at
+// once (fin->psign / fin->diag / fin->carry) and h.qr_panel_hook is told; the caller then skips the global sign pass.
+template <typename T> struct QrFinish { T *psign, *diag, *carry; };
 template <typename T>
-static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld, T *beta) {
+static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld, T *beta, const QrFinish<T> *fin = nullptr) {
     // f32 on the tensor-core GEMM: K = nb = 256 amortises the per-tile prologue / epilogue of the rank-nb update (124 vs 141 ms at 16384^2)
     const bool f32_tc = sizeof(T) == 4 && h.opt.sgemm_tc != 0 && n >= 2048;
     const int NB = (int)std::max<int64_t>(W, std::min<int64_t>(f32_tc ? h.opt.qr_nb_f32 : h.opt.qr_nb, 256));
@@ -688,7 +717,16 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
         return true;
     };
 
-    auto factor_panel = [&](int64_t k0, int nb, T *V, T *Tm, T *Vt) {
+    auto finish_panel = [&](int64_t k0, int nb) {        // on the stream the panel was factored on
+        if (!fin) return;
+        sign_scan_panel_kernel<T><<<1, 32, 0, h.stream>>>(beta, k0, nb, fin->carry, fin->psign, fin->diag);
+        LFB_LAUNCH_CHECK(h);
+        dim3 grid((unsigned)cdiv(m, 256), (unsigned)std::min(nb, 64));
+        sign_fix_panel_kernel<T><<<grid, 256, 0, h.stream>>>(A, ld, m, k0, nb, fin->psign);
+        LFB_LAUNCH_CHECK(h);
+        if (h.qr_panel_hook) h.qr_panel_hook(k0, nb);
+    };
+    auto factor_panel_raw = [&](int64_t k0, int nb, T *V, T *Tm, T *Vt) {
         bool t_built = false;
         if ((sizeof(T) == 8 ? h.opt.qr_panel_cholqr >= 1 : h.opt.qr_panel_cholqr >= 2) && nb >= 64 && (m - k0) >= 2 * (int64_t)nb &&
             panel_cholqr(k0, nb, V, Tm, &t_built)) {
@@ -737,6 +775,10 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
             build_t<T>(h, V, ldv, rows, nb, G, Tm, NB);
             if (Vt) transpose<T>(h, V, rows, nb, ldv, Vt, NB);
         }
+    };
+    auto factor_panel = [&](int64_t k0, int nb, T *V, T *Tm, T *Vt) {
+        factor_panel_raw(k0, nb, V, Tm, Vt);
+        finish_panel(k0, nb);
     };
 
     cudaStream_t sm = h.stream, sp = h.aux_stream;
@@ -820,6 +862,13 @@ template <typename T>
 void qr_factor(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld, T *diag) {
     if (n <= 0) return;
     DevBuf<T> beta(h, n), psign(h, n);
+    if (h.qr_panel_hook) {      // per-panel sign pass: block columns are final as soon as their panel is
+        DevBuf<T> carry(h, 1);
+        fill<T>(h, carry.get(), 1, 1, 1, T(1), T(1));
+        const QrFinish<T> fin{psign.get(), diag, carry.get()};
+        qr_factor_std<T>(h, A, m, n, ld, beta, &fin);
+        return;
+    }
     qr_factor_std<T>(h, A, m, n, ld, beta);
     sign_scan_kernel<T><<<1, 32, 0, h.stream>>>(beta, n, psign, diag);
     LFB_LAUNCH_CHECK(h);

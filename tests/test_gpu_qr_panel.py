@@ -131,3 +131,26 @@ def test_gemm_two_cta_tiles_bitwise(L, shape):
     ref = C0.t() - (A.t() if ta else A) @ (B.t() if tb else B)
     assert float((outs[1].t() - ref).abs().max()) <= 64 * K * EPS
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("shape", [(2304, 2048), (4096, 2176)])
+def test_qr_host_overlapped_download_is_identical(L, order, shape):
+    """Page-locked host memory, cols >= 2048: block columns leave for the host during the factorisation, after a per-panel pass of
+    the reference's running sign (householder.rs:45-50).  Negations only: bit-identical to the download-at-the-end path."""
+    import torch
+    m, n = shape
+    a0 = np.random.default_rng(m + n).uniform(-1, 1, (m, n))
+    ref = np.array(a0, order=order)
+    e0 = L.Engine(0)
+    e0.set_option("qr_overlap_d2h", 0)
+    d0 = L.qr_into(ref, eng=e0).diag.copy()
+    t = torch.from_numpy(a0.copy()).pin_memory()
+    a = t.numpy() if order == "C" else None
+    if order == "F":
+        tf = torch.empty((n, m), dtype=torch.float64).pin_memory()          # column-major m x n view of a pinned buffer
+        a = tf.numpy().T
+        a[...] = a0
+    d1 = L.qr_into(a, eng=L.Engine(0)).diag.copy()
+    assert np.array_equal(a, ref)
+    assert np.array_equal(d1, d0) and np.array_equal(np.signbit(d1), np.signbit(d0))
