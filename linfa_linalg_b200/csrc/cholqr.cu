@@ -13,6 +13,8 @@
 // Householder leaf unchanged (A is not modified by the attempt).  The guard costs one 32-byte D2H copy and a stream sync.
 // What the callers build on top (explicit Q = A R^-1, the reconstruction of the reference's reflectors) is in
 // householder.cu / tsqr_hr.cu.
+#include <memory>
+
 #include "common.cuh"
 
 namespace lfb {
@@ -75,6 +77,63 @@ __global__ void __launch_bounds__(1024) cholqr_guard_kernel(const T *__restrict_
     }
 }
 
+// The same guard numbers from the UPPER factors R = L^T and RI = R^-1 (the bound is symmetric under transposition of both), for
+// the blocked 256-column stage; g0 / g1: the guard outputs of the two diagonal-block launches, whose failure flags are folded in.
+template <typename T>
+__global__ void __launch_bounds__(1024) cholqr_guard_upper_kernel(const T *__restrict__ R, int64_t ldr, const T *__restrict__ RI, int64_t ldi, int n,
+                                                                  const double *__restrict__ g0, const double *__restrict__ g1, double *out) {
+    __shared__ double rowR[1024], rowI[1024];
+    __shared__ double colR[32], colI[32], dmin[32];
+    __shared__ int okf[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += 1024) rowR[i] = rowI[i] = 0.0;
+    __syncthreads();
+    double mr = 0.0, mi = 0.0, md = 1e300;
+    int ok = 1;
+    for (int c = warp; c < n; c += 32) {
+        double sr = 0.0, si = 0.0;
+        for (int r = lane; r <= c; r += 32) {
+            const double a = fabs((double)R[r + (int64_t)c * ldr]), b = fabs((double)RI[r + (int64_t)c * ldi]);
+            sr += a;
+            si += b;
+            atomicAdd(&rowR[r], a);
+            atomicAdd(&rowI[r], b);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sr += __shfl_xor_sync(0xffffffffu, sr, o);
+            si += __shfl_xor_sync(0xffffffffu, si, o);
+        }
+        if (!isfinite(sr) || !isfinite(si)) ok = 0;
+        mr = fmax(mr, sr);
+        mi = fmax(mi, si);
+        md = fmin(md, (double)R[c + (int64_t)c * ldr]);
+    }
+    if (lane == 0) { colR[warp] = mr; colI[warp] = mi; dmin[warp] = md; okf[warp] = ok; }
+    __syncthreads();
+    if (warp == 0) {
+        double rr = 0.0, ri = 0.0;
+        for (int i = lane; i < n; i += 32) { rr = fmax(rr, rowR[i]); ri = fmax(ri, rowI[i]); }
+        double cr = colR[lane], ci = colI[lane], dm = dmin[lane];
+        int k = okf[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            rr = fmax(rr, __shfl_xor_sync(0xffffffffu, rr, o));
+            ri = fmax(ri, __shfl_xor_sync(0xffffffffu, ri, o));
+            cr = fmax(cr, __shfl_xor_sync(0xffffffffu, cr, o));
+            ci = fmax(ci, __shfl_xor_sync(0xffffffffu, ci, o));
+            dm = fmin(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+            k &= __shfl_xor_sync(0xffffffffu, k, o);
+        }
+        if (lane == 0) {
+            const bool blocks_ok = g0[2] == 1.0 && g1[2] == 1.0;
+            out[0] = blocks_ok ? sqrt(cr * rr * ci * ri) : 1e300;
+            out[1] = blocks_ok ? dm : 0.0;
+            out[2] = (blocks_ok && k) ? 1.0 : 0.0;
+        }
+    }
+}
+
 // R = L^T (upper, strict lower zeroed) and, if asked, Rinv = X^T with X = L^-1.
 template <typename T>
 __global__ void cholqr_emit_kernel(const T *__restrict__ Lm, const T *__restrict__ X, int64_t ld, int n, T *__restrict__ R, int64_t ldr,
@@ -102,6 +161,33 @@ bool cholqr_factor(lfb_handle &h, const T *A, int64_t rows, int64_t n, int64_t l
         // one single-CTA launch for the n x n stage (panel_hr.cu): Cholesky, inverse, guard numbers, R and R^-1 -- the scratch
         // outputs are written before the verdict is known, the caller's matrix is not touched
         cholqr128<T>(h, G.get(), ldg, R, ldr, Rinv, ldri, guard.get());
+        LFB_CUDA(cudaMemcpyAsync(hg, guard.get(), sizeof hg, cudaMemcpyDeviceToHost, h.stream));
+        LFB_CUDA(cudaStreamSynchronize(h.stream));
+        return hg[2] == 1.0 && hg[1] > 0.0 && std::isfinite(hg[0]) && hg[0] <= (double)h.opt.tsqr_cholqr_cond;
+    }
+    if (n == 256 && h.opt.cholqr_fused) {
+        // 2 x 2 blocks of 128 on the single-CTA kernel: R = [R11, L21^T; 0, R22], R^-1 = [R11^-1, -R11^-1 L21^T R22^-1; 0, R22^-1]
+        // with L21 = G21 R11^-1 and R22 = chol(G22 - L21 L21^T)^T -- ten short launches instead of ~25 (cholesky_lower, the
+        // triangular solve for the inverse, guard, emit), which is most of what is left of a TSQR stage at 8 GPUs
+        constexpr int b = 128;
+        std::unique_ptr<DevBuf<T>> ritmp;
+        T *RI = Rinv;
+        int64_t ldi = ldri;
+        if (!RI) { ritmp.reset(new DevBuf<T>(h, (size_t)ldg * n)); RI = ritmp->get(); ldi = ldg; }
+        DevBuf<T> L21(h, b * b), T1(h, b * b);
+        DevBuf<double> gb(h, 8);
+        T *Gm = G.get();
+        fill<T>(h, R + b, b, b, ldr, T(0), T(0));
+        fill<T>(h, RI + b, b, b, ldi, T(0), T(0));
+        cholqr128<T>(h, Gm, ldg, R, ldr, RI, ldi, gb.get());
+        gemm<T>(h, 0, 0, b, b, b, T(1), Gm + b, ldg, RI, ldi, T(0), L21.get(), b);                                     // L21 = G21 R11^-1
+        gemm<T>(h, 0, 1, b, b, b, T(-1), L21.get(), b, L21.get(), b, T(1), Gm + b + (int64_t)b * ldg, ldg, /*lower_only=*/1);
+        cholqr128<T>(h, Gm + b + (int64_t)b * ldg, ldg, R + b + (int64_t)b * ldr, ldr, RI + b + (int64_t)b * ldi, ldi, gb.get() + 4);
+        transpose<T>(h, L21.get(), b, b, b, R + (int64_t)b * ldr, ldr);                                                // R12 = L21^T
+        gemm<T>(h, 1, 0, b, b, b, T(1), L21.get(), b, RI + b + (int64_t)b * ldi, ldi, T(0), T1.get(), b);              // L21^T R22^-1
+        gemm<T>(h, 0, 0, b, b, b, T(-1), RI, ldi, T1.get(), b, T(0), RI + (int64_t)b * ldi, ldi);                      // (R^-1)12
+        cholqr_guard_upper_kernel<T><<<1, 1024, 0, h.stream>>>(R, ldr, RI, ldi, (int)n, gb.get(), gb.get() + 4, guard.get());
+        LFB_LAUNCH_CHECK(h);
         LFB_CUDA(cudaMemcpyAsync(hg, guard.get(), sizeof hg, cudaMemcpyDeviceToHost, h.stream));
         LFB_CUDA(cudaStreamSynchronize(h.stream));
         return hg[2] == 1.0 && hg[1] > 0.0 && std::isfinite(hg[0]) && hg[0] <= (double)h.opt.tsqr_cholqr_cond;

@@ -12,6 +12,9 @@ import linfa_linalg_b200 as L  # noqa: E402
 
 cols = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 eng = L.Engine(0)
+for kv in sys.argv[2:]:
+    k, v = kv.split("=")
+    eng.set_option(k, int(v))
 eng.set_stream(torch.cuda.current_stream().cuda_stream)
 p = lambda t: C.c_void_p(t.data_ptr())
 for rows in (4194304, 2097152, 1048576, 524288, 2048):
