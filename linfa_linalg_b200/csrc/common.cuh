@@ -49,6 +49,7 @@ struct Options {
     int64_t qr_panel_cholqr = 1; // f64 blocked QR: panel = guarded Cholesky-QR + Householder reconstruction (tsqr_hr.cu) when its condition bound passes; else the cluster panel kernels
     int64_t cholqr_fused = 1;    // 128-column Cholesky-QR stages as single-CTA kernels (panel_hr.cu): Cholesky + inverse + guard, and reconstruction + M + T
     int64_t qr_overlap_d2h = 1;  // host QR (pinned memory, cols >= 2048): finished block columns go back to the host during the factorisation
+    int64_t qr_fold_t = 1;       // f64 QR: VT = V T once per panel on the look-ahead stream, so the trailing update needs (V T)^T C instead of T^T (V^T C)
     int64_t qr_trace = 0;    // debug: event time stamps of every stage of the look-ahead pipeline on stderr
     int64_t qr_sub = 32;     // inner BLAS-2 sub-panel width (<= 32)
     int64_t chol_base = 64;  // recursion base of Cholesky / TRSM (<= 64)

@@ -571,10 +571,17 @@ void build_t(lfb_handle &h, const T *V, int64_t ldv, int64_t rows, int nb, T *G,
 // on both sides -- the only operand layout of the f32 tensor-core kernel (gemm_tf32.cu).
 template <typename T>
 void apply_block_reflector(lfb_handle &h, const T *V, int64_t ldv, int64_t rows, int nb, const T *Tm, int64_t ldt,
-                           int trans_t, T *C, int64_t ldc, int64_t ncols, T *W1, T *W2, const T *Vt = nullptr, int64_t ldvt = 0) {
+                           int trans_t, T *C, int64_t ldc, int64_t ncols, T *W1, T *W2, const T *Vt = nullptr, int64_t ldvt = 0,
+                           const T *VT = nullptr) {
     if (ncols <= 0 || rows <= 0) return;
-    gemm<T>(h, 1, 0, nb, ncols, rows, T(1), V, ldv, C, ldc, T(0), W1, nb);          // W1 = V^T C
-    gemm<T>(h, trans_t, 0, nb, ncols, nb, T(1), Tm, ldt, W1, nb, T(0), W2, nb);     // W2 = op(T) W1
+    if (VT && trans_t) {
+        // T folded into the reflectors once per panel (VT = V T): W2 = T^T (V^T C) = (V T)^T C is ONE long-K product instead of a
+        // long-K product followed by a 128 x ncols x 128 one that runs almost alone on the main stream
+        gemm<T>(h, 1, 0, nb, ncols, rows, T(1), VT, ldv, C, ldc, T(0), W2, nb);
+    } else {
+        gemm<T>(h, 1, 0, nb, ncols, rows, T(1), V, ldv, C, ldc, T(0), W1, nb);          // W1 = V^T C
+        gemm<T>(h, trans_t, 0, nb, ncols, nb, T(1), Tm, ldt, W1, nb, T(0), W2, nb);     // W2 = op(T) W1
+    }
     if (Vt) gemm<T>(h, 1, 0, rows, ncols, nb, T(-1), Vt, ldvt, W2, nb, T(1), C, ldc);   // C -= (V^T)^T W2
     else gemm<T>(h, 0, 0, rows, ncols, nb, T(-1), V, ldv, W2, nb, T(1), C, ldc);    // C -= V W2
 }
@@ -670,6 +677,9 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
     const bool use_vt = ((sizeof(T) == 4 && h.opt.sgemm_tc != 0) || (sizeof(T) == 8 && h.opt.qr_vt != 0)) && m >= 256 && n > NB;
     DevBuf<T> Vt0(h, use_vt ? (size_t)NB * ldv : 1), Vt1(h, use_vt ? (size_t)NB * ldv : 1);
     T *Vtbuf[2] = {use_vt ? Vt0.get() : nullptr, use_vt ? Vt1.get() : nullptr};
+    const bool fold_t = sizeof(T) == 8 && h.opt.qr_fold_t != 0 && n > NB;
+    DevBuf<T> VT0(h, fold_t ? (size_t)NB * ldv : 1), VT1(h, fold_t ? (size_t)NB * ldv : 1);
+    T *VTbuf[2] = {fold_t ? VT0.get() : nullptr, fold_t ? VT1.get() : nullptr};
     // two generations of the panel workspaces (V, T): with look-ahead panel k+1 is factored while the
     // trailing update of panel k still reads V_k / T_k
     DevBuf<T> Vb0(h, (size_t)ldv * NB), Vb1(h, (size_t)ldv * NB);
@@ -776,8 +786,9 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
             if (Vt) transpose<T>(h, V, rows, nb, ldv, Vt, NB);
         }
     };
-    auto factor_panel = [&](int64_t k0, int nb, T *V, T *Tm, T *Vt) {
+    auto factor_panel = [&](int64_t k0, int nb, T *V, T *Tm, T *Vt, T *VT) {
         factor_panel_raw(k0, nb, V, Tm, Vt);
+        if (VT && n - (k0 + nb) > 0) gemm<T>(h, 0, 0, m - k0, nb, nb, T(1), V, ldv, Tm, NB, T(0), VT, ldv);   // VT = V T
         finish_panel(k0, nb);
     };
 
@@ -799,7 +810,7 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
         LFB_CUDA(cudaEventCreate(&t_base));
         LFB_CUDA(cudaEventRecord(t_base, h.stream));
     }
-    factor_panel(0, (int)std::min<int64_t>(NB, n), Vbuf[0], Tbuf[0], Vtbuf[0]);
+    factor_panel(0, (int)std::min<int64_t>(NB, n), Vbuf[0], Tbuf[0], Vtbuf[0], VTbuf[0]);
     int cur = 0;
     int pi = -1;
     for (int64_t k0 = 0; k0 < n; k0 += NB, cur ^= 1) {
@@ -814,19 +825,19 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
             // trailing update of the NEXT panel's columns first, then factor that panel on the side
             // stream while the rest of the trailing matrix is updated here
             mark(sm, pi, 0);
-            apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C, ld, nbn, W1, W2, Vtbuf[cur], NB);
+            apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C, ld, nbn, W1, W2, Vtbuf[cur], NB, VTbuf[cur]);
             mark(sm, pi, 1);
             LFB_CUDA(cudaEventRecord(h.ev[2], sm));
             LFB_CUDA(cudaStreamWaitEvent(sp, h.ev[2], 0));
             // the rest of the update is queued BEFORE the panel: the Cholesky-QR panel ends its guard with a host
             // synchronisation of the side stream, and the main stream must already hold its work by then
             if (trail > nbn)
-                apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C + (int64_t)nbn * ld, ld, trail - nbn, W1, W2, Vtbuf[cur], NB);
+                apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C + (int64_t)nbn * ld, ld, trail - nbn, W1, W2, Vtbuf[cur], NB, VTbuf[cur]);
             mark(sm, pi, 4);
             h.stream = sp;
             try {
                 mark(sp, pi, 2);
-                factor_panel(k0 + nb, nbn, Vbuf[cur ^ 1], Tbuf[cur ^ 1], Vtbuf[cur ^ 1]);
+                factor_panel(k0 + nb, nbn, Vbuf[cur ^ 1], Tbuf[cur ^ 1], Vtbuf[cur ^ 1], VTbuf[cur ^ 1]);
                 mark(sp, pi, 3);
             } catch (...) {
                 h.stream = sm;
@@ -836,8 +847,8 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
             h.stream = sm;
             LFB_CUDA(cudaStreamWaitEvent(sm, h.ev[3], 0));
         } else {
-            apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C, ld, trail, W1, W2, Vtbuf[cur], NB);
-            factor_panel(k0 + nb, nbn, Vbuf[cur ^ 1], Tbuf[cur ^ 1], Vtbuf[cur ^ 1]);
+            apply_block_reflector<T>(h, Vbuf[cur], ldv, rows, nb, Tbuf[cur], NB, 1, C, ld, trail, W1, W2, Vtbuf[cur], NB, VTbuf[cur]);
+            factor_panel(k0 + nb, nbn, Vbuf[cur ^ 1], Tbuf[cur ^ 1], Vtbuf[cur ^ 1], VTbuf[cur ^ 1]);
         }
     }
     if (trace) {
