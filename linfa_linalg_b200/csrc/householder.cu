@@ -677,7 +677,7 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
     const bool use_vt = ((sizeof(T) == 4 && h.opt.sgemm_tc != 0) || (sizeof(T) == 8 && h.opt.qr_vt != 0)) && m >= 256 && n > NB;
     DevBuf<T> Vt0(h, use_vt ? (size_t)NB * ldv : 1), Vt1(h, use_vt ? (size_t)NB * ldv : 1);
     T *Vtbuf[2] = {use_vt ? Vt0.get() : nullptr, use_vt ? Vt1.get() : nullptr};
-    const bool fold_t = sizeof(T) == 8 && h.opt.qr_fold_t != 0 && n > NB;
+    const bool fold_t = (sizeof(T) == 8 ? h.opt.qr_fold_t != 0 : h.opt.qr_fold_t >= 2) && n > NB;
     DevBuf<T> VT0(h, fold_t ? (size_t)NB * ldv : 1), VT1(h, fold_t ? (size_t)NB * ldv : 1);
     T *VTbuf[2] = {fold_t ? VT0.get() : nullptr, fold_t ? VT1.get() : nullptr};
     // two generations of the panel workspaces (V, T): with look-ahead panel k+1 is factored while the
