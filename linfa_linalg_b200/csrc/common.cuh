@@ -46,7 +46,7 @@ struct Options {
     int64_t qr_nb_f32 = 256; // same for f32 when the trailing updates run on the tcgen05 kernel (n >= 2048)
     int64_t qr_vt = 1;       // f64 QR: rank-nb update through a transposed copy of V (K-major tiles on both sides: 2 TMA box loads per stage instead of 9,
                              // which matters since the two-CTA kernel issues them from a compute warp): 231.1 vs 234.0 ms, same bits
-    int64_t qr_panel_cholqr = 1; // f64 blocked QR: panel = guarded Cholesky-QR + Householder reconstruction (tsqr_hr.cu) when its condition bound passes; else the cluster panel kernels
+    int64_t qr_panel_cholqr = 2; // blocked QR: panel = guarded Cholesky-QR + Householder reconstruction (tsqr_hr.cu) when its condition bound passes, else the cluster panel kernels; 1 = f64 only, 2 = f32 too (256-column panels as two fused 128-column ones: 125 -> 106 ms at 16384^2), 0 = off
     int64_t cholqr_fused = 1;    // 128-column Cholesky-QR stages as single-CTA kernels (panel_hr.cu): Cholesky + inverse + guard, and reconstruction + M + T
     int64_t qr_overlap_d2h = 1;  // host QR (pinned memory, cols >= 2048): finished block columns go back to the host during the factorisation
     int64_t qr_fold_t = 1;       // f64 QR: VT = V T once per panel on the look-ahead stream, so the trailing update needs (V T)^T C instead of T^T (V^T C)

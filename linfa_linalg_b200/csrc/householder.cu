@@ -738,8 +738,32 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
     };
     auto factor_panel_raw = [&](int64_t k0, int nb, T *V, T *Tm, T *Vt) {
         bool t_built = false;
-        if ((sizeof(T) == 8 ? h.opt.qr_panel_cholqr >= 1 : h.opt.qr_panel_cholqr >= 2) && nb >= 64 && (m - k0) >= 2 * (int64_t)nb &&
-            panel_cholqr(k0, nb, V, Tm, &t_built)) {
+        const bool chq = (sizeof(T) == 8 ? h.opt.qr_panel_cholqr >= 1 : h.opt.qr_panel_cholqr >= 2);
+        int s_start = 0;
+        if (chq && nb == 256 && h.opt.cholqr_fused && (m - k0) >= 2 * (int64_t)nb) {
+            // A 256-column panel (what the f32 tensor-core update wants as K) as TWO fused 128-column Cholesky-QR panels: factor A,
+            // apply it to B's 128 columns, factor B, and assemble the compact-WY factor of the pair,
+            //   T = [T_A, -T_A (V_A^T V_B) T_B; 0, T_B].
+            // If B is declined by the guard the Householder sub-panels take over from column 128 (A stays).
+            bool tA = false, tB = false;
+            const int64_t prow = m - k0;
+            if (panel_cholqr(k0, 128, V, Tm, &tA) && tA) {
+                apply_block_reflector<T>(h, V, ldv, prow, 128, Tm, NB, /*trans_t=*/1, A + k0 + (k0 + 128) * ld, ld, 128, W1p, W2p);
+                fill<T>(h, V + (int64_t)128 * ldv, 128, 128, ldv, T(0), T(0));      // V_B has no rows above its diagonal block
+                if (panel_cholqr(k0 + 128, 128, V + 128 + (int64_t)128 * ldv, Tm + 128 + (int64_t)128 * NB, &tB) && tB) {
+                    if (n - (k0 + nb) > 0) {
+                        gemm<T>(h, 1, 0, 128, 128, prow - 128, T(1), V + 128, ldv, V + 128 + (int64_t)128 * ldv, ldv, T(0), G, 128);   // V_A^T V_B
+                        gemm<T>(h, 0, 0, 128, 128, 128, T(1), Tm, NB, G, 128, T(0), W1p, 128);
+                        gemm<T>(h, 0, 0, 128, 128, 128, T(-1), W1p, 128, Tm + 128 + (int64_t)128 * NB, NB, T(0), Tm + (int64_t)128 * NB, NB);
+                        fill<T>(h, Tm + 128, 128, 128, NB, T(0), T(0));
+                        if (Vt) transpose<T>(h, V, prow, nb, ldv, Vt, NB);
+                    }
+                    return;
+                }
+                s_start = 128;
+            }
+        }
+        if (s_start == 0 && chq && nb >= 64 && (m - k0) >= 2 * (int64_t)nb && panel_cholqr(k0, nb, V, Tm, &t_built)) {
             if (n - (k0 + nb) > 0) {
                 if (!t_built) build_t<T>(h, V, ldv, m - k0, nb, G, Tm, NB);
                 if (Vt) transpose<T>(h, V, m - k0, nb, ldv, Vt, NB);
@@ -747,7 +771,7 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
             return;
         }
         bool v_staged = true;   // the cluster kernels stage V as they go
-        for (int s0 = 0; s0 < nb;) {
+        for (int s0 = s_start; s0 < nb;) {
             const int64_t c0 = k0 + s0;
             const int64_t rows = m - c0;
             int w = std::min(SUB, nb - s0);

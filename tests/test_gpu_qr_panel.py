@@ -154,3 +154,26 @@ def test_qr_host_overlapped_download_is_identical(L, order, shape):
     d1 = L.qr_into(a, eng=L.Engine(0)).diag.copy()
     assert np.array_equal(a, ref)
     assert np.array_equal(d1, d0) and np.array_equal(np.signbit(d1), np.signbit(d0))
+
+
+def test_qr_f32_two_level_panel_matches_householder_route(L):
+    """f32, 2560 x 2304: 256-column panels (K of the tcgen05 update) as two fused 128-column Cholesky-QR panels with the pair's
+    compact-WY factor assembled from T_A, T_B and V_A^T V_B -- against the Householder panels (qr_panel_cholqr = 0) and the
+    invariants in f64 (R^T R = A^T A with R from into_r, qr.rs:91-98; unit-norm reflectors, householder.rs:23)."""
+    m, n = 2560, 2304
+    a0 = np.random.default_rng(23).uniform(-1, 1, (m, n)).astype(np.float32)
+    a_h, d_h = _qr_with(L, a0, qr_panel_cholqr=0)
+    e = L.Engine(0)
+    a_c = a0.copy()
+    dec = L.qr_into(a_c, eng=e)
+    d_c = dec.diag.copy()
+    eps = 1.1920929e-07
+    scale = float(np.linalg.norm(a0.astype(np.float64)))
+    assert np.array_equal(np.signbit(d_c), np.signbit(d_h))
+    assert np.max(np.abs(a_c - a_h)) <= 16 * m * eps * scale / np.sqrt(m)
+    v = np.tril(a_c.astype(np.float64))
+    assert np.max(np.abs(np.sqrt((v * v).sum(axis=0)) - 1)) <= 64 * eps
+    r = dec.into_r().astype(np.float64)
+    g = a0.astype(np.float64).T @ a0.astype(np.float64)
+    assert np.all(np.diag(r) >= 0)
+    assert np.linalg.norm(r.T @ r - g) / np.linalg.norm(g) <= 64 * eps
