@@ -950,6 +950,7 @@ int lfb_destroy(lfb_handle *h) {
     delete h->host_pool;
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->upload_stream) cudaStreamDestroy(h->upload_stream);
+    if (h->hr_scratch) { cudaFree(h->hr_scratch); cudaEventDestroy(h->hr_ev[0]); cudaEventDestroy(h->hr_ev[1]); }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->aux2_stream) cudaStreamDestroy(h->aux2_stream);
@@ -1012,7 +1013,7 @@ int lfb_set_option(lfb_handle *h, const char *key, int64_t value) {
         {"chol_nb", &o.chol_nb, 64, 8192}, {"chol_tn", &o.chol_tn, 0, 1}, {"chol_nb_tail", &o.chol_nb_tail, 64, 8192}, {"chol_tail_rows", &o.chol_tail_rows, 0, BIG}, {"chol_split_panel", &o.chol_split_panel, 0, 1}, {"chol_trace", &o.chol_trace, 0, 1}, {"chol_potf2_rl", &o.chol_potf2_rl, 0, 1}, {"gemm_tma", &o.gemm_tma, 0, 1}, {"gemm_splitk", &o.gemm_splitk, 0, 1}, {"gemm_deterministic", &o.gemm_deterministic, 0, 1}, {"tsqr_cholqr_cond", &o.tsqr_cholqr_cond, 0, 1 << 20},
         {"gemm_v2", &o.gemm_v2, 0, 1}, {"sgemm_tc", &o.sgemm_tc, 0, 2}, {"gemm_split_waves", &o.gemm_split_waves, 1, 64}, {"panel_cluster", &o.panel_cluster, 0, 2},
         {"panel_cluster_max", &o.panel_cluster_max, 1, 16}, {"lookahead", &o.lookahead, 0, 1}, {"tsqr_chunk", &o.tsqr_chunk, 64, BIG},
-        {"batched_quad", &o.batched_quad, 0, 4}, {"gemm_tma2", &o.gemm_tma2, 0, 2}, {"qr_trace", &o.qr_trace, 0, 1}, {"qr_fold_t", &o.qr_fold_t, 0, 2}, {"qr_overlap_d2h", &o.qr_overlap_d2h, 0, 1}, {"chol_waves", &o.chol_waves, 1, 4}, {"qr_panel_cholqr", &o.qr_panel_cholqr, 0, 2}, {"cholqr_fused", &o.cholqr_fused, 0, 1}, {"gemm_tma2_maxk", &o.gemm_tma2_maxk, 16, 1 << 30}, {"tsqr_streams", &o.tsqr_streams, 1, 64}, {"tsqr_graph", &o.tsqr_graph, 0, 1}, {"hr_lu_blocked", &o.hr_lu_blocked, 0, 1},
+        {"batched_quad", &o.batched_quad, 0, 4}, {"gemm_tma2", &o.gemm_tma2, 0, 2}, {"qr_trace", &o.qr_trace, 0, 1}, {"hr_split", &o.hr_split, 0, 1}, {"qr_fold_t", &o.qr_fold_t, 0, 2}, {"qr_overlap_d2h", &o.qr_overlap_d2h, 0, 1}, {"chol_waves", &o.chol_waves, 1, 4}, {"qr_panel_cholqr", &o.qr_panel_cholqr, 0, 2}, {"cholqr_fused", &o.cholqr_fused, 0, 1}, {"gemm_tma2_maxk", &o.gemm_tma2_maxk, 16, 1 << 30}, {"tsqr_streams", &o.tsqr_streams, 1, 64}, {"tsqr_graph", &o.tsqr_graph, 0, 1}, {"hr_lu_blocked", &o.hr_lu_blocked, 0, 1},
         {"qr_tsqr_auto", &o.qr_tsqr_auto, 0, 1}, {"trd_fused", &o.trd_fused, 0, 1}, {"chol_overlap_d2h", &o.chol_overlap_d2h, 0, 1}, {"host_staging", &o.host_staging, 0, 1},
         {"rot_staged", &o.rot_staged, 0, 1}, {"eigh_stable_2x2", &o.eigh_stable_2x2, 0, 1}, {"rot_serial", &o.rot_serial, 0, 1},
         {"fast_hypot", &o.fast_hypot, 0, 1}, {"bd_blocked", &o.bd_blocked, 0, 1}, {"trd_profile", &o.trd_profile, 0, 1},

@@ -50,6 +50,7 @@ struct Options {
     int64_t cholqr_fused = 1;    // 128-column Cholesky-QR stages as single-CTA kernels (panel_hr.cu): Cholesky + inverse + guard, and reconstruction + M + T
     int64_t qr_overlap_d2h = 1;  // host QR (pinned memory, cols >= 2048): finished block columns go back to the host during the factorisation
     int64_t qr_fold_t = 1;       // f64 QR: VT = V T once per panel on the look-ahead stream, so the trailing update needs (V T)^T C instead of T^T (V^T C)
+    int64_t hr_split = 1;        // fused QR panel: the Z / T stage of the reconstruction kernel on the second side stream, beside the tall GEMM
     int64_t qr_trace = 0;    // debug: event time stamps of every stage of the look-ahead pipeline on stderr
     int64_t qr_sub = 32;     // inner BLAS-2 sub-panel width (<= 32)
     int64_t chol_base = 64;  // recursion base of Cholesky / TRSM (<= 64)
@@ -199,7 +200,10 @@ struct lfb_handle {
     std::function<void(int64_t k0, int64_t nb)> chol_panel_hook;
     std::function<void(int64_t k0, int64_t nb)> qr_panel_hook;     // host QR: block column [k0, k0 + nb) is final (reference signs applied) on h.stream
     cudaStream_t copy_stream = nullptr;
-    cudaStream_t upload_stream = nullptr;   // host Cholesky in arrival waves: H2D pieces (and their transposes) while earlier columns are factored
+    cudaStream_t upload_stream = nullptr;
+    void *hr_scratch = nullptr;             // panel_hr.cu: Y_1 / U and the pivot vectors handed from the LU stage to the M and T stages
+    cudaEvent_t hr_ev[2] = {nullptr, nullptr};
+    bool hr_pending = false;   // host Cholesky in arrival waves: H2D pieces (and their transposes) while earlier columns are factored
     void drop_graphs() {
         for (auto &g : graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
         graphs.clear();
@@ -353,6 +357,7 @@ template <typename T> void qr_tsqr(lfb_handle &h, T *A, int64_t rows, int64_t co
 template <typename T> void cholqr128(lfb_handle &h, const T *G, int64_t ldg, T *R, int64_t ldr, T *Rinv, int64_t ldri, double *guard);
 template <typename T> void hr_panel128(lfb_handle &h, T *Atop, int64_t ld, const T *R, int64_t ldr, const T *Rinv, int64_t ldri, T *beta, T *M, int64_t ldm,
                                        T *Tm, int64_t ldt, T *Vtop, int64_t ldv);
+void hr_panel128_join(lfb_handle &h);
 template <typename T> bool cholqr_factor(lfb_handle &h, const T *A, int64_t rows, int64_t n, int64_t ld, T *R, int64_t ldr, T *Rinv, int64_t ldri);
 template <typename T> void triangular_zero(lfb_handle &h, T *A, int64_t n, int64_t ld, int keep_lower);
 double microbench_fp64(lfb_handle &h, int kind);

@@ -712,6 +712,7 @@ static void qr_factor_std(lfb_handle &h, T *A, int64_t m, int64_t n, int64_t ld,
                 gemm<T>(h, 0, 0, prow - nb, nb, nb, T(1), P + nb, ld, U.get(), ldu, T(0), V + nb, ldv);
                 copy2d<T>(h, V + nb, ldv, P + nb, ld, prow - nb, nb);
             }
+            hr_panel128_join(h);       // T (second side stream) is complete from here on
             *t_built = true;
             return true;
         }

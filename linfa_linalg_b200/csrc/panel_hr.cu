@@ -203,11 +203,14 @@ __global__ void __launch_bounds__(NTH, 1) cholqr128_kernel(const T *__restrict__
     LFB_MARK(6);
 }
 
-template <typename T>
+// STAGE 0: everything in one launch.  STAGES 1 / 2 / 3 split it so that the part nothing downstream waits for runs beside the tall
+// GEMM on a second stream: 1 = Q_top and its LU (Y_1, U and the s / pivot / c' vectors go to the scratch block Qg), 2 = M and the top
+// block (what the tall GEMM V_2 = A_2 M and the panel's write-back need), 3 = Z and T (needed only when the reflector is APPLIED).
+template <typename T, int STAGE>
 __global__ void __launch_bounds__(NTH, 1) hr_panel128_kernel(T *__restrict__ Atop, int64_t ld, const T *__restrict__ R, int64_t ldr,
                                                             const T *__restrict__ Rinv, int64_t ldri, T *__restrict__ beta,
                                                             T *__restrict__ M, int64_t ldm, T *__restrict__ Tm, int64_t ldt,
-                                                            T *__restrict__ Vtop, int64_t ldv, long long *dbg) {
+                                                            T *__restrict__ Vtop, int64_t ldv, T *__restrict__ Qg, long long *dbg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *Q = reinterpret_cast<T *>(smem_raw);      // [PN][PLD]: A_top, then Y_1 (strictly lower) and U
     T *P = Q + PN * PLD;                         // packed upper: R^-1, later Z
@@ -219,7 +222,18 @@ __global__ void __launch_bounds__(NTH, 1) hr_panel128_kernel(T *__restrict__ Ato
     T *rowb = colb + 2 * PN;                     // [2][PN]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tr = lane, tc = warp;
+    T a[4][YN];
     LFB_MARK(0);
+    if constexpr (STAGE >= 2) {                  // Y_1 / U and the vectors come from stage 1
+        for (int e = tid; e < PN * PLD; e += NTH) Q[e] = Qg[e];
+        for (int e = tid; e < 4 * PN; e += NTH) sv[e] = Qg[PN * PLD + e];      // sv, pv, pinv, cv are contiguous
+        if constexpr (STAGE == 2) {
+            for (int j = warp; j < PN; j += NW)
+                for (int i = lane; i <= j; i += 32) P[pk(i, j)] = Rinv[i + (int64_t)j * ldri];
+        }
+        __syncthreads();
+    }
+    if constexpr (STAGE <= 1) {
     for (int j = warp; j < PN; j += NW)
         for (int i = lane; i < PN; i += 32) {
             Q[i * PLD + j] = Atop[i + (int64_t)j * ld];
@@ -228,7 +242,6 @@ __global__ void __launch_bounds__(NTH, 1) hr_panel128_kernel(T *__restrict__ Ato
     __syncthreads();
     LFB_MARK(1);
     // Q_top = A_top R^-1, register tile per thread; the result stays in registers as the input of the LU
-    T a[4][YN];
     FOR_X FOR_Y a[x][y] = T(0);
     for (int k = 0; k <= tc + NW * (YN - 1); ++k) {   // R^-1 is upper triangular: column j needs k <= j
         T l[4], u[YN];
@@ -280,6 +293,14 @@ __global__ void __launch_bounds__(NTH, 1) hr_panel128_kernel(T *__restrict__ Ato
         cv[k] = -sv[k] * sqrt(fabs(pv[k]) / T(2));
         beta[k] = sv[k] * fabs(R[k + (int64_t)k * ldr]);
     }
+    if constexpr (STAGE == 1) {
+        __syncthreads();
+        for (int e = tid; e < PN * PLD; e += NTH) Qg[e] = Q[e];
+        for (int e = tid; e < 4 * PN; e += NTH) Qg[PN * PLD + e] = sv[e];
+        return;
+    }
+    }   // STAGE <= 1
+    if constexpr (STAGE == 0 || STAGE == 2) {
     // M = R^-1 U^-1 by a column sweep on W = R^-1: column j of M is W[:, j] / U_jj, then W[:, j'] -= M[:, j] U[j, j'] for j' > j
     FOR_X FOR_Y {
         const int i = tr + 32 * x, j = tc + NW * y;
@@ -317,8 +338,9 @@ __global__ void __launch_bounds__(NTH, 1) hr_panel128_kernel(T *__restrict__ Ato
         const int i = tr + 32 * x, j = tc + NW * y;
         M[i + (int64_t)j * ldm] = i <= j ? a[x][y] * cv[j] : T(0);
     }
+    }   // M
     LFB_MARK(5);
-    if (Tm) {
+    if ((STAGE == 0 || STAGE == 3) && Tm) {
         // Z = Y_1^-T C^-1 (upper) by a row sweep from the bottom on W = C^-1: row k of Z is final when the sweep reaches it (unit
         // diagonal), then W[i, :] -= Y_1[k, i] Z[k, :] for i < k
         FOR_X FOR_Y a[x][y] = (tr + 32 * x == tc + NW * y) ? T(1) / cv[tc + NW * y] : T(0);
@@ -360,6 +382,7 @@ __global__ void __launch_bounds__(NTH, 1) hr_panel128_kernel(T *__restrict__ Ato
     }
     LFB_MARK(7);
     // the top block in the driver's convention: s_i R[i, j] above the diagonal, the reflector heads c'_j y_ij on and below it
+    if constexpr (STAGE == 0 || STAGE == 2)
     for (int j = warp; j < PN; j += NW)
         for (int i = lane; i < PN; i += 32) {
             T v;
@@ -408,12 +431,39 @@ void hr_panel128(lfb_handle &h, T *Atop, int64_t ld, const T *R, int64_t ldr, co
     const size_t smem = sizeof(T) * (size_t)(PN * PLD + PN * (PN + 1) / 2 + 8 * PN);
     static DeviceOnce cfg;
     cfg.run(h.device, [&] {
-        LFB_CUDA(cudaFuncSetAttribute(hr_panel128_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LFB_CUDA(cudaFuncSetAttribute(hr_panel128_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LFB_CUDA(cudaFuncSetAttribute(hr_panel128_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LFB_CUDA(cudaFuncSetAttribute(hr_panel128_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LFB_CUDA(cudaFuncSetAttribute(hr_panel128_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     });
     static const bool dbg_on = getenv("LFB_PANEL_DBG") != nullptr;
+    // Split launch (option hr_split): LU stage, then the M / top-block stage on this stream and the Z / T stage on the handle's second
+    // side stream -- T is not needed until the reflector is applied, so its two sweeps run beside the tall GEMM V_2 = A_2 M and the
+    // write-back of the panel.  hr_panel128_join() makes this stream wait for it.
+    const bool split = h.opt.hr_split && Tm && !dbg_on && h.aux2_stream && h.aux2_stream != h.stream && !h.in_capture;
+    if (split) {
+        if (!h.hr_scratch) {
+            LFB_CUDA(cudaMalloc(&h.hr_scratch, sizeof(double) * (size_t)(PN * PLD + 4 * PN)));
+            LFB_CUDA(cudaEventCreateWithFlags(&h.hr_ev[0], cudaEventDisableTiming));
+            LFB_CUDA(cudaEventCreateWithFlags(&h.hr_ev[1], cudaEventDisableTiming));
+        }
+        T *Qg = reinterpret_cast<T *>(h.hr_scratch);
+        cudaStream_t s1 = h.stream, s2 = h.aux2_stream;
+        hr_panel128_kernel<T, 1><<<1, NTH, smem, s1>>>(Atop, ld, R, ldr, Rinv, ldri, beta, M, ldm, Tm, ldt, Vtop, ldv, Qg, nullptr);
+        LFB_LAUNCH_CHECK(h);
+        LFB_CUDA(cudaEventRecord(h.hr_ev[0], s1));
+        LFB_CUDA(cudaStreamWaitEvent(s2, h.hr_ev[0], 0));
+        hr_panel128_kernel<T, 3><<<1, NTH, smem, s2>>>(Atop, ld, R, ldr, Rinv, ldri, beta, M, ldm, Tm, ldt, Vtop, ldv, Qg, nullptr);
+        LFB_LAUNCH_CHECK(h);
+        LFB_CUDA(cudaEventRecord(h.hr_ev[1], s2));
+        h.hr_pending = true;
+        hr_panel128_kernel<T, 2><<<1, NTH, smem, s1>>>(Atop, ld, R, ldr, Rinv, ldri, beta, M, ldm, Tm, ldt, Vtop, ldv, Qg, nullptr);
+        LFB_LAUNCH_CHECK(h);
+        return;
+    }
     long long *dbg = nullptr;
     if (dbg_on) { LFB_CUDA(cudaMalloc(&dbg, 16 * sizeof(long long))); LFB_CUDA(cudaMemset(dbg, 0, 16 * sizeof(long long))); }
-    hr_panel128_kernel<T><<<1, NTH, smem, h.stream>>>(Atop, ld, R, ldr, Rinv, ldri, beta, M, ldm, Tm, ldt, Vtop, ldv, dbg);
+    hr_panel128_kernel<T, 0><<<1, NTH, smem, h.stream>>>(Atop, ld, R, ldr, Rinv, ldri, beta, M, ldm, Tm, ldt, Vtop, ldv, (T *)nullptr, dbg);
     LFB_LAUNCH_CHECK(h);
     if (dbg_on) {
         long long hd[16];
@@ -423,6 +473,13 @@ void hr_panel128(lfb_handle &h, T *Atop, int64_t ld, const T *R, int64_t ldr, co
         fprintf(stderr, "hr_panel128 cycles: load %lld | Q R^-1 %lld | LU %lld | write-back + M init %lld | M sweep %lld | Z sweep %lld | T %lld | top block %lld\n",
                 hd[1] - hd[0], hd[2] - hd[1], hd[3] - hd[2], hd[4] - hd[3], hd[5] - hd[4], hd[6] - hd[5], hd[7] - hd[6], hd[8] - hd[7]);
     }
+}
+
+// The stream that launched a split hr_panel128 waits here for its Z / T stage (T is complete afterwards).
+void hr_panel128_join(lfb_handle &h) {
+    if (!h.hr_pending) return;
+    LFB_CUDA(cudaStreamWaitEvent(h.stream, h.hr_ev[1], 0));
+    h.hr_pending = false;
 }
 
 #define INST(T)                                                                                                      \
