@@ -177,3 +177,18 @@ def test_qr_f32_two_level_panel_matches_householder_route(L):
     g = a0.astype(np.float64).T @ a0.astype(np.float64)
     assert np.all(np.diag(r) >= 0)
     assert np.linalg.norm(r.T @ r - g) / np.linalg.norm(g) <= 64 * eps
+
+
+def test_every_documented_option_is_settable(L):
+    """Every tunable of lfb::Options (csrc/common.cuh) is registered in lfb_set_option's table and accepts its own default."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "linfa_linalg_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("struct Options"):]
+    body = body[:body.index("};")]
+    opts = re.findall(r"^\s*int64_t\s+([a-z0-9_]+)\s*=\s*(-?\d+)\s*;", body, flags=re.M)
+    assert len(opts) >= 40
+    e = L.Engine(0)
+    missing = [name for name, dflt in opts if e.lib.lfb_set_option(e.h, name.encode(), int(dflt)) != 0]
+    assert not missing, missing
